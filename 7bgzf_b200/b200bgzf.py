@@ -1,0 +1,162 @@
+"""ctypes binding of the C ABI in include/b200bgzf.h — used by tests/ and bench.py only.
+
+The product is the C library (lib7bgzf_b200.so / 7bgzf.so / 7bgzf); this module adds no logic of its own and
+never falls back to a CPU path: if the shared library or a GPU is missing the calls raise.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib7bgzf_b200.so")
+HOOK_PATH = os.path.join(_HERE, "7bgzf.so")
+APPLET_PATH = os.path.join(_HERE, "7bgzf")
+
+BLOCK_SIZE = 0xFF00
+MAX_BLOCK_SIZE = 0x10000
+APPEND_EOF = 1
+VERIFY = 2
+EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+EXPORTS = [
+    "b200bgzf_create", "b200bgzf_destroy", "b200bgzf_strerror", "b200bgzf_last_error", "b200bgzf_compress_bound",
+    "b200bgzf_compress_device", "b200bgzf_compress_host", "b200bgzf_compress_blocks_host", "b200bgzf_inflate_size_host",
+    "b200bgzf_inflate_device", "b200bgzf_inflate_host", "b200bgzf_profile", "b200bgzf_launch_count", "b200bgzf_parse_method",
+]
+
+
+class B200BgzfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200bgzf error {code}: {msg}")
+        self.code = code
+
+
+def load(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise B200BgzfError(-2, f"{path} is missing: run `make` (there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, sz, u32, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+    psz = ctypes.POINTER(sz)
+    lib.b200bgzf_create.argtypes = [ctypes.POINTER(vp), i32]
+    lib.b200bgzf_destroy.argtypes = [vp]
+    lib.b200bgzf_destroy.restype = None
+    lib.b200bgzf_strerror.argtypes = [i32]
+    lib.b200bgzf_strerror.restype = ctypes.c_char_p
+    lib.b200bgzf_last_error.argtypes = [vp]
+    lib.b200bgzf_last_error.restype = ctypes.c_char_p
+    lib.b200bgzf_compress_bound.argtypes = [sz, u32]
+    lib.b200bgzf_compress_bound.restype = sz
+    lib.b200bgzf_compress_device.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint, vp]
+    lib.b200bgzf_compress_host.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint]
+    lib.b200bgzf_compress_blocks_host.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(vp), psz,
+                                                  ctypes.POINTER(i32), u32, i32]
+    lib.b200bgzf_inflate_size_host.argtypes = [vp, sz, psz, psz]
+    lib.b200bgzf_inflate_device.argtypes = [vp, vp, sz, vp, sz, psz, ctypes.c_uint, vp]
+    lib.b200bgzf_inflate_host.argtypes = [vp, vp, sz, vp, sz, psz, ctypes.c_uint]
+    lib.b200bgzf_profile.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_ulonglong), i32, i32]
+    lib.b200bgzf_launch_count.argtypes = [vp]
+    lib.b200bgzf_launch_count.restype = ctypes.c_ulonglong
+    lib.b200bgzf_parse_method.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32), ctypes.c_char_p, sz]
+    return lib
+
+
+def _addr(buf):
+    """address of a bytes / bytearray / ctypes buffer / numpy array / int"""
+    if isinstance(buf, int):
+        return buf
+    if isinstance(buf, bytes):
+        return ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p).value
+    if hasattr(buf, "ctypes"):
+        return buf.ctypes.data
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr()
+    return ctypes.addressof((ctypes.c_char * len(buf)).from_buffer(buf))
+
+
+class Codec:
+    """One GPU context."""
+
+    def __init__(self, device=-1, path=LIB_PATH):
+        self.lib = load(path)
+        h = ctypes.c_void_p()
+        rc = self.lib.b200bgzf_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise B200BgzfError(rc, self.lib.b200bgzf_strerror(rc).decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.b200bgzf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, ok=(0,)):
+        if rc not in ok:
+            raise B200BgzfError(rc, self.lib.b200bgzf_strerror(rc).decode() + " / " + self.lib.b200bgzf_last_error(self.h).decode())
+        return rc
+
+    def bound(self, n, block_size=BLOCK_SIZE):
+        return self.lib.b200bgzf_compress_bound(n, block_size)
+
+    # ---- host buffers ----
+    def compress(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
+        out = bytearray(self.bound(len(data), block_size))
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_compress_host(self.h, _addr(data) if len(data) else None, len(data), block_size, level,
+                                                    _addr(out), len(out), ctypes.byref(n), APPEND_EOF if eof else 0))
+        return bytes(out[: n.value])
+
+    def compress_into(self, src_addr, nbytes, dst_addr, dst_cap, level=6, block_size=BLOCK_SIZE, eof=True):
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_compress_host(self.h, src_addr, nbytes, block_size, level, dst_addr, dst_cap, ctypes.byref(n),
+                                                    APPEND_EOF if eof else 0))
+        return n.value
+
+    def inflate(self, data, flags=0):
+        total, nm = ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_inflate_size_host(_addr(data), len(data), ctypes.byref(total), ctypes.byref(nm)))
+        out = bytearray(max(total.value, 1))
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_inflate_host(self.h, _addr(data), len(data), _addr(out), len(out), ctypes.byref(n), flags))
+        return bytes(out[: n.value])
+
+    def inflate_into(self, src_addr, nbytes, dst_addr, dst_cap, flags=0):
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_inflate_host(self.h, src_addr, nbytes, dst_addr, dst_cap, ctypes.byref(n), flags))
+        return n.value
+
+    def compress_blocks(self, payloads, level=6, caps=None):
+        nb = len(payloads)
+        srcs = (ctypes.c_void_p * nb)(*[_addr(p) if len(p) else None for p in payloads])
+        slen = (ctypes.c_uint32 * nb)(*[len(p) for p in payloads])
+        bufs = [bytearray(MAX_BLOCK_SIZE) for _ in range(nb)]
+        dsts = (ctypes.c_void_p * nb)(*[_addr(b) for b in bufs])
+        dlen = (ctypes.c_size_t * nb)(*(caps or [MAX_BLOCK_SIZE] * nb))
+        st = (ctypes.c_int * nb)()
+        rc = self.lib.b200bgzf_compress_blocks_host(self.h, srcs, slen, dsts, dlen, st, nb, level)
+        self._check(rc, ok=(0, 1))
+        return [bytes(bufs[i][: dlen[i]]) if st[i] == 0 else None for i in range(nb)], list(st)
+
+    # ---- device buffers (addresses) ----
+    def compress_device(self, d_in, nbytes, d_out, out_cap, level=6, block_size=BLOCK_SIZE, eof=True, stream=None):
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_compress_device(self.h, d_in, nbytes, block_size, level, d_out, out_cap, ctypes.byref(n),
+                                                      APPEND_EOF if eof else 0, stream))
+        return n.value
+
+    def inflate_device(self, d_in, nbytes, d_out, out_cap, flags=0, stream=None):
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_inflate_device(self.h, d_in, nbytes, d_out, out_cap, ctypes.byref(n), flags, stream))
+        return n.value
+
+    def profile(self, enable=True, reset=True):
+        arr = (ctypes.c_ulonglong * 16)()
+        self._check(self.lib.b200bgzf_profile(self.h, 1 if enable else 0, arr, 16, 1 if reset else 0))
+        return list(arr)
+
+    def launches(self):
+        return self.lib.b200bgzf_launch_count(self.h)

@@ -1,0 +1,635 @@
+/*
+ * b200bgzf_api.cu — the C-ABI shim over the sm_100a kernels (see include/b200bgzf.h).
+ *
+ * Owns, per context: the device tables, a few "lanes" (stream + pinned staging + device workspaces) that the
+ * host-buffer paths rotate through so H2D copies, kernels and D2H copies of consecutive batches overlap, and a
+ * pool of one-block lanes for the LD_PRELOAD hook so concurrent htslib threads each drive their own SM.
+ * No CPU fallback anywhere: a failing CUDA call surfaces as B200BGZF_E_CUDA.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <vector>
+
+#include "../../include/b200bgzf.h"
+#include "bgzf_block.h"
+#include "bgzf_kernels.h"
+#include "bgzf_tables.h"
+
+namespace {
+
+constexpr uint32_t kHostBatchBlocks = 1024;     /* 64 MiB of payload per pipelined batch */
+constexpr uint32_t kDeviceBatchBlocks = 16384;  /* 1 GiB of payload per device-resident batch */
+constexpr int kLanes = 3;
+constexpr int kHookLanes = 32;
+constexpr uint32_t kHookLaneBlocks = 4;
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    uint32_t cap_blocks = 0;
+    size_t in_cap = 0, out_cap = 0, host_in_cap = 0, host_out_cap = 0, meta_cap = 0;
+    uint8_t *d_in = nullptr, *d_slots = nullptr, *d_out = nullptr;
+    uint32_t *d_len = nullptr, *d_status = nullptr, *d_scratch = nullptr;
+    uint64_t *d_off = nullptr, *d_inoff = nullptr, *d_outoff = nullptr;
+    uint32_t *d_inlen = nullptr;
+    uint64_t *d_total = nullptr;   /* [0] running stream size, [1] error flags, [2..3] spare */
+    uint64_t *h_total = nullptr;   /* pinned mirror */
+    uint8_t *h_in = nullptr, *h_out = nullptr;   /* pinned staging (hook / block-list paths) */
+    uint64_t *h_meta = nullptr;                  /* pinned: offsets / lengths */
+    /* bookkeeping of an in-flight host batch */
+    bool pending = false;
+    size_t pend_out_off = 0;
+    bool busy = false;
+    int scratch_ctas = 0;
+};
+
+}  // namespace
+
+struct b200bgzf_ctx {
+    int device = 0;
+    int sms = 0;
+    uint32_t *d_crctab = nullptr, *d_crcpow = nullptr;
+    unsigned long long *d_prof = nullptr;
+    bool prof_on = false;
+    std::mutex mu;                 /* serialises the bulk APIs */
+    Lane lanes[kLanes];
+    std::mutex hook_mu;
+    std::condition_variable hook_cv;
+    Lane hook_lanes[kHookLanes];
+    /* device-resident inflate index workspaces */
+    uint64_t *d_idx_inoff = nullptr, *d_idx_outoff = nullptr, *d_idx_tileoff = nullptr, *d_idx_counts = nullptr;
+    uint32_t *d_idx_tilecount = nullptr, *d_idx_isize = nullptr, *d_idx_status = nullptr, *d_inf_status = nullptr;
+    size_t idx_cap = 0, idx_tiles = 0;
+    uint64_t *h_idx = nullptr;
+    unsigned long long launches = 0;
+    char err[256] = { 0 };
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(b200bgzf_ctx *c, cudaError_t e, const char *where)
+{
+    snprintf(c->err, sizeof c->err, "%s: %s", where, cudaGetErrorString(e));
+    return B200BGZF_E_CUDA;
+}
+#define CK(call)                                            \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return fail(ctx, e_, #call); \
+    } while (0)
+
+template <typename T>
+cudaError_t grow(T **p, size_t *cap, size_t need, bool pinned = false)
+{
+    if (need <= *cap && *p) return cudaSuccess;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; }
+    size_t n = std::max(need, *cap + *cap / 2);
+    cudaError_t e = pinned ? cudaMallocHost((void **)p, n * sizeof(T)) : cudaMalloc((void **)p, n * sizeof(T));
+    *cap = e == cudaSuccess ? n : 0;
+    return e;
+}
+
+void lane_free(Lane &l)
+{
+    cudaFree(l.d_in); cudaFree(l.d_slots); cudaFree(l.d_out); cudaFree(l.d_len); cudaFree(l.d_status);
+    cudaFree(l.d_scratch); cudaFree(l.d_off); cudaFree(l.d_inoff); cudaFree(l.d_outoff); cudaFree(l.d_inlen);
+    cudaFree(l.d_total);
+    if (l.h_total) cudaFreeHost(l.h_total);
+    if (l.h_in) cudaFreeHost(l.h_in);
+    if (l.h_out) cudaFreeHost(l.h_out);
+    if (l.h_meta) cudaFreeHost(l.h_meta);
+    if (l.stream) cudaStreamDestroy(l.stream);
+    l = Lane();
+}
+
+/* make sure a lane can process `blocks` compress blocks (device side); staging is grown on demand elsewhere */
+int lane_reserve(b200bgzf_ctx *ctx, Lane &l, uint32_t blocks, size_t in_bytes, size_t out_bytes, bool slots = true, int ctas = 0)
+{
+    if (!l.stream) CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    if (!l.d_total) {
+        CK(cudaMalloc((void **)&l.d_total, 4 * sizeof(uint64_t)));
+        CK(cudaMallocHost((void **)&l.h_total, 4 * sizeof(uint64_t)));
+    }
+    if (slots && !l.d_scratch) {
+        l.scratch_ctas = ctas > 0 ? ctas : ctx->sms;
+        CK(cudaMalloc((void **)&l.d_scratch, (size_t)l.scratch_ctas * BGZF_SCRATCH_WORDS * sizeof(uint32_t)));
+    }
+    if (blocks > l.cap_blocks || (slots && !l.d_slots)) {
+        cudaFree(l.d_slots); cudaFree(l.d_len); cudaFree(l.d_status); cudaFree(l.d_off);
+        cudaFree(l.d_inoff); cudaFree(l.d_outoff); cudaFree(l.d_inlen);
+        l.d_slots = nullptr; l.cap_blocks = 0;
+        if (slots) CK(cudaMalloc((void **)&l.d_slots, (size_t)blocks * BG_SLOT_BYTES + 64));
+        CK(cudaMalloc((void **)&l.d_len, (size_t)blocks * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&l.d_status, (size_t)blocks * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&l.d_inlen, (size_t)blocks * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&l.d_off, (size_t)blocks * sizeof(uint64_t)));
+        CK(cudaMalloc((void **)&l.d_inoff, (size_t)blocks * sizeof(uint64_t)));
+        CK(cudaMalloc((void **)&l.d_outoff, (size_t)blocks * sizeof(uint64_t)));
+        l.cap_blocks = blocks;
+    }
+    if (in_bytes) CK(grow(&l.d_in, &l.in_cap, in_bytes + 64));
+    if (out_bytes) CK(grow(&l.d_out, &l.out_cap, out_bytes + 64));
+    return 0;
+}
+
+/* one batch: compress kernel into slots, then scan + gather into `d_out` continuing at *d_total */
+int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint64_t in_bytes, uint32_t block_size,
+                          const uint64_t *d_inoff, const uint32_t *d_inlen, uint32_t nblocks, int level, uint8_t *d_out,
+                          int append_eof, cudaStream_t stream)
+{
+    if (nblocks) {
+        BgzfCompressArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = d_in;
+        a.in_off = d_inoff;
+        a.in_len = d_inlen;
+        a.in_bytes = in_bytes;
+        a.block_size = block_size;
+        a.nblocks = nblocks;
+        a.prm = bg_level_params(level);
+        a.slots = l.d_slots;
+        a.out_len = l.d_len;
+        a.status = l.d_status;
+        a.scratch = l.d_scratch;
+        a.crctab = ctx->d_crctab;
+        a.crcpow = ctx->d_crcpow;
+        a.err_flag = (uint32_t *)(l.d_total + 1);
+        a.prof = ctx->prof_on ? ctx->d_prof : nullptr;
+        const int grid = (int)std::min<uint32_t>(nblocks, (uint32_t)l.scratch_ctas);
+        CK(bgzf_launch_compress(&a, grid, stream));
+        ctx->launches += 1;
+    }
+    CK(bgzf_launch_compact(l.d_slots, l.d_len, l.d_off, nblocks, d_out, l.d_total, append_eof, stream));
+    ctx->launches += 2;
+    return 0;
+}
+
+bool level_ok(int level) { return level >= 1 && level <= 12; }
+
+}  // namespace
+
+extern "C" const char *b200bgzf_strerror(int code)
+{
+    switch (code) {
+    case B200BGZF_OK: return "ok";
+    case B200BGZF_E_NOFIT: return "compressed member does not fit";
+    case B200BGZF_E_ARG: return "bad argument";
+    case B200BGZF_E_CUDA: return "CUDA failure (no device, out of memory or launch error)";
+    case B200BGZF_E_FORMAT: return "not BGZF or corrupt data";
+    case B200BGZF_E_NOSPACE: return "output buffer too small";
+    case B200BGZF_E_CRC: return "CRC32/ISIZE mismatch";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *b200bgzf_last_error(const b200bgzf_ctx *ctx) { return ctx ? ctx->err : ""; }
+extern "C" unsigned long long b200bgzf_launch_count(const b200bgzf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" size_t b200bgzf_compress_bound(size_t in_bytes, uint32_t block_size)
+{
+    if (block_size == 0 || block_size > B200BGZF_MAX_BLOCK_SIZE) return 0;
+    const size_t nb = (in_bytes + block_size - 1) / block_size;
+    return in_bytes + nb * 36 + B200BGZF_EOF_BYTES;   /* 18 + 8 framing + up to two stored-block headers */
+}
+
+extern "C" int b200bgzf_create(b200bgzf_ctx **out, int device)
+{
+    if (!out) return B200BGZF_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return B200BGZF_E_CUDA;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return B200BGZF_E_CUDA;
+    if (device >= ndev) return B200BGZF_E_ARG;
+    b200bgzf_ctx *ctx = new b200bgzf_ctx();
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || (size_t)prop.sharedMemPerBlockOptin < bgzf_compress_smem_bytes()) {
+        snprintf(ctx->err, sizeof ctx->err, "device %d lacks the %zu bytes of shared memory per CTA this codec needs", device,
+                 bgzf_compress_smem_bytes());
+        delete ctx;
+        return B200BGZF_E_CUDA;
+    }
+    ctx->sms = prop.multiProcessorCount;
+    uint32_t tab[256];
+    std::vector<uint32_t> pw(BG_THREADS);
+    bg_make_crc_table(tab);
+    bg_make_crc_pow(pw.data(), BG_THREADS);
+    bool ok = cudaMalloc((void **)&ctx->d_crctab, sizeof tab) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->d_crcpow, pw.size() * 4) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->d_prof, BGZF_PROF_SLOTS * 8) == cudaSuccess &&
+              cudaMemcpy(ctx->d_crctab, tab, sizeof tab, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(ctx->d_crcpow, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemset(ctx->d_prof, 0, BGZF_PROF_SLOTS * 8) == cudaSuccess;
+    if (!ok) {
+        b200bgzf_destroy(ctx);
+        return B200BGZF_E_CUDA;
+    }
+    *out = ctx;
+    return B200BGZF_OK;
+}
+
+extern "C" void b200bgzf_destroy(b200bgzf_ctx *ctx)
+{
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx->device);
+        cudaDeviceSynchronize();
+        for (auto &l : ctx->lanes) lane_free(l);
+        for (auto &l : ctx->hook_lanes) lane_free(l);
+        cudaFree(ctx->d_crctab); cudaFree(ctx->d_crcpow); cudaFree(ctx->d_prof);
+        cudaFree(ctx->d_idx_inoff); cudaFree(ctx->d_idx_outoff); cudaFree(ctx->d_idx_tileoff); cudaFree(ctx->d_idx_counts);
+        cudaFree(ctx->d_idx_tilecount); cudaFree(ctx->d_idx_isize); cudaFree(ctx->d_idx_status); cudaFree(ctx->d_inf_status);
+        if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
+    }
+    delete ctx;
+}
+
+extern "C" int b200bgzf_profile(b200bgzf_ctx *ctx, int enable, unsigned long long *cycles, int n, int reset)
+{
+    if (!ctx) return B200BGZF_E_ARG;
+    DeviceGuard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->prof_on = enable != 0;
+    CK(cudaDeviceSynchronize());
+    if (cycles && n > 0) CK(cudaMemcpy(cycles, ctx->d_prof, std::min(n, BGZF_PROF_SLOTS) * 8, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(ctx->d_prof, 0, BGZF_PROF_SLOTS * 8));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* compress                                                                                         */
+
+extern "C" int b200bgzf_compress_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes, uint32_t block_size, int level,
+                                        void *d_out, size_t out_cap, size_t *out_bytes, unsigned flags, void *stream_)
+{
+    if (!ctx || !d_out || !out_bytes || (!d_in && in_bytes) || block_size == 0 || block_size > B200BGZF_MAX_BLOCK_SIZE || !level_ok(level))
+        return B200BGZF_E_ARG;
+    if (out_cap < b200bgzf_compress_bound(in_bytes, block_size)) return B200BGZF_E_NOSPACE;
+    DeviceGuard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane &l = ctx->lanes[0];
+    const uint64_t nb_total = (in_bytes + block_size - 1) / block_size;
+    const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), kDeviceBatchBlocks);
+    int r = lane_reserve(ctx, l, batch, 0, 0);
+    if (r) return r;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : l.stream;
+    CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), stream));
+    const int eof = (flags & B200BGZF_APPEND_EOF) ? 1 : 0;
+    uint64_t done = 0;
+    do {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nb_total - done);
+        const uint64_t off = done * block_size;
+        const bool last = done + nb >= nb_total;
+        r = launch_compress_batch(ctx, l, (const uint8_t *)d_in + off, in_bytes - off, block_size, nullptr, nullptr, nb, level,
+                                  (uint8_t *)d_out, eof && last, stream);
+        if (r) return r;
+        done += nb;
+    } while (done < nb_total);
+    CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    *out_bytes = (size_t)l.h_total[0] + (eof ? B200BGZF_EOF_BYTES : 0);
+    return l.h_total[1] ? B200BGZF_E_NOFIT : B200BGZF_OK;
+}
+
+extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                                      size_t out_cap, size_t *out_bytes, unsigned flags)
+{
+    if (!ctx || !out || !out_bytes || (!in && in_bytes) || block_size == 0 || block_size > B200BGZF_MAX_BLOCK_SIZE || !level_ok(level))
+        return B200BGZF_E_ARG;
+    if (out_cap < b200bgzf_compress_bound(in_bytes, block_size)) return B200BGZF_E_NOSPACE;
+    DeviceGuard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const uint64_t nb_total = (in_bytes + block_size - 1) / block_size;
+    const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), kHostBatchBlocks);
+    const size_t batch_in = (size_t)batch * block_size, batch_out = b200bgzf_compress_bound(batch_in, block_size);
+    size_t host_off = 0;
+    bool nofit = false;
+    int r;
+    auto complete = [&](Lane &l) -> int {
+        CK(cudaStreamSynchronize(l.stream));
+        const size_t total = (size_t)l.h_total[0];
+        if (l.h_total[1]) nofit = true;
+        CK(cudaMemcpyAsync((uint8_t *)out + host_off, l.d_out, total, cudaMemcpyDeviceToHost, l.stream));
+        host_off += total;
+        l.pending = false;
+        return 0;
+    };
+    uint64_t done = 0, i = 0;
+    while (done < nb_total) {
+        Lane &l = ctx->lanes[i % kLanes];
+        if (l.pending && (r = complete(l))) return r;
+        if ((r = lane_reserve(ctx, l, batch, batch_in, batch_out))) return r;
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nb_total - done);
+        const uint64_t off = done * block_size;
+        const size_t bytes = (size_t)std::min<uint64_t>((uint64_t)nb * block_size, in_bytes - off);
+        CK(cudaMemcpyAsync(l.d_in, (const uint8_t *)in + off, bytes, cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
+        if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream))) return r;
+        CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+        l.pending = true;
+        done += nb;
+        i++;
+    }
+    /* drain in submission order */
+    for (uint64_t k = 0; k < (uint64_t)kLanes; k++) {
+        Lane &l = ctx->lanes[(i + k) % kLanes];
+        if (l.pending && (r = complete(l))) return r;
+    }
+    for (auto &l : ctx->lanes)
+        if (l.stream) CK(cudaStreamSynchronize(l.stream));
+    if (flags & B200BGZF_APPEND_EOF) {
+        static const uint8_t eof[28] = { 0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0,
+                                         0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        memcpy((uint8_t *)out + host_off, eof, sizeof eof);
+        host_off += sizeof eof;
+    }
+    *out_bytes = host_off;
+    return nofit ? B200BGZF_E_NOFIT : B200BGZF_OK;
+}
+
+namespace {
+
+/* one staged batch of independent payloads on a given lane (used by the hook and the block-list API) */
+int compress_blocks_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *const *src, const uint32_t *slen, void *const *dst, size_t *dlen,
+                            int *status, uint32_t nb, int level)
+{
+    int r = lane_reserve(ctx, l, nb, (size_t)nb * BG_SLOT_BYTES, (size_t)nb * BG_SLOT_BYTES, true, nb <= kHookLaneBlocks ? (int)kHookLaneBlocks : 0);
+    if (r) return r;
+    CK(grow(&l.h_in, &l.host_in_cap, (size_t)nb * BG_SLOT_BYTES, true));
+    CK(grow(&l.h_out, &l.host_out_cap, (size_t)nb * BG_SLOT_BYTES, true));
+    size_t meta_need = (size_t)nb * 3;
+    CK(grow(&l.h_meta, &l.meta_cap, meta_need, true));
+    uint64_t *h_inoff = l.h_meta;
+    uint32_t *h_inlen = (uint32_t *)(l.h_meta + nb);
+    uint32_t *h_len = (uint32_t *)(l.h_meta + 2 * nb);
+    size_t pos = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        h_inoff[b] = pos;
+        h_inlen[b] = slen[b];
+        memcpy(l.h_in + pos, src[b], slen[b]);
+        pos += (slen[b] + 15u) & ~(size_t)15u;    /* keep every payload 16-byte aligned for the TMA path */
+    }
+    CK(cudaMemcpyAsync(l.d_in, l.h_in, pos ? pos : 16, cudaMemcpyHostToDevice, l.stream));
+    CK(cudaMemcpyAsync(l.d_inoff, h_inoff, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+    CK(cudaMemcpyAsync(l.d_inlen, h_inlen, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
+    CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
+    if ((r = launch_compress_batch(ctx, l, l.d_in, 0, 0, l.d_inoff, l.d_inlen, nb, level, l.d_out, 0, l.stream))) return r;
+    CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaMemcpyAsync(h_len, l.d_len, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaStreamSynchronize(l.stream));
+    const size_t total = (size_t)l.h_total[0];
+    if (total) {
+        CK(cudaMemcpyAsync(l.h_out, l.d_out, total, cudaMemcpyDeviceToHost, l.stream));
+        CK(cudaStreamSynchronize(l.stream));
+    }
+    size_t o = 0;
+    int worst = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t n = h_len[b];
+        int st = 0;
+        if (n == 0 || n > dlen[b]) st = B200BGZF_E_NOFIT;
+        else { memcpy(dst[b], l.h_out + o, n); dlen[b] = n; }
+        o += n;
+        if (status) status[b] = st;
+        if (st) worst = st;
+    }
+    return worst;
+}
+
+}  // namespace
+
+extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, const uint32_t *slen, void *const *dst,
+                                             size_t *dlen, int *status, uint32_t nblocks, int level)
+{
+    if (!ctx || !src || !slen || !dst || !dlen || !level_ok(level)) return B200BGZF_E_ARG;
+    for (uint32_t b = 0; b < nblocks; b++)
+        if (slen[b] > B200BGZF_MAX_BLOCK_SIZE || dlen[b] < 26) return B200BGZF_E_ARG;
+    if (nblocks == 0) return 0;
+    DeviceGuard g(ctx->device);
+    if (nblocks <= kHookLaneBlocks) {
+        /* small calls (the hook): grab any free one-block lane so concurrent callers run on different SMs */
+        Lane *l = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(ctx->hook_mu);
+            for (;;) {
+                for (auto &h : ctx->hook_lanes)
+                    if (!h.busy) { l = &h; break; }
+                if (l) break;
+                ctx->hook_cv.wait(lk);
+            }
+            l->busy = true;
+        }
+        int r = compress_blocks_on_lane(ctx, *l, src, slen, dst, dlen, status, nblocks, level);
+        {
+            std::lock_guard<std::mutex> lk(ctx->hook_mu);
+            l->busy = false;
+        }
+        ctx->hook_cv.notify_one();
+        return r;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int worst = 0;
+    for (uint32_t done = 0; done < nblocks; done += kHostBatchBlocks) {
+        const uint32_t nb = std::min(kHostBatchBlocks, nblocks - done);
+        int r = compress_blocks_on_lane(ctx, ctx->lanes[0], src + done, slen + done, dst + done, dlen + done,
+                                        status ? status + done : nullptr, nb, level);
+        if (r < 0) return r;
+        if (r) worst = r;
+    }
+    return worst;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* inflate                                                                                          */
+
+namespace {
+
+/* applet/7bgzf.c:81-131 for the BGZF flavour: returns the member size, 0 if this is not a BGZF member */
+uint32_t member_size(const uint8_t *p, size_t avail)
+{
+    if (avail < 28) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || p[3] != 4) return 0;
+    if (p[10] != 6 || p[11] != 0 || p[12] != 'B' || p[13] != 'C' || p[14] != 2 || p[15] != 0) return 0;
+    const uint32_t sz = ((uint32_t)p[16] | ((uint32_t)p[17] << 8)) + 1u;
+    if (sz < 28 || sz > avail) return 0;
+    return sz;
+}
+
+int inflate_status_to_code(uint32_t st) { return st == 0 ? B200BGZF_OK : B200BGZF_E_FORMAT; }
+
+}  // namespace
+
+extern "C" int b200bgzf_inflate_size_host(const void *in, size_t in_bytes, size_t *out_bytes, size_t *nmembers)
+{
+    if (!in && in_bytes) return B200BGZF_E_ARG;
+    const uint8_t *p = (const uint8_t *)in;
+    size_t off = 0, total = 0, n = 0;
+    while (off < in_bytes) {
+        const uint32_t sz = member_size(p + off, in_bytes - off);
+        if (!sz) return B200BGZF_E_FORMAT;
+        const uint8_t *t = p + off + sz - 4;
+        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (isize > B200BGZF_MAX_BLOCK_SIZE) return B200BGZF_E_FORMAT;
+        total += isize;
+        off += sz;
+        n++;
+    }
+    if (out_bytes) *out_bytes = total;
+    if (nmembers) *nmembers = n;
+    return B200BGZF_OK;
+}
+
+extern "C" int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes, void *d_out, size_t out_cap,
+                                       size_t *out_bytes, unsigned flags, void *stream_)
+{
+    (void)flags;
+    if (!ctx || !d_in || !out_bytes || in_bytes < 28) return B200BGZF_E_ARG;
+    DeviceGuard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane &l = ctx->lanes[0];
+    int r = lane_reserve(ctx, l, 1, 0, 0, false);
+    if (r) return r;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : l.stream;
+    const size_t tiles = bgzf_index_tiles(in_bytes);
+    if (!ctx->h_idx) CK(cudaMallocHost((void **)&ctx->h_idx, 8 * sizeof(uint64_t)));
+    if (!ctx->d_idx_counts) {
+        CK(cudaMalloc((void **)&ctx->d_idx_counts, 4 * sizeof(uint64_t)));
+        CK(cudaMalloc((void **)&ctx->d_idx_status, 4 * sizeof(uint32_t)));
+    }
+    if (tiles > ctx->idx_tiles) {
+        cudaFree(ctx->d_idx_tilecount); cudaFree(ctx->d_idx_tileoff);
+        CK(cudaMalloc((void **)&ctx->d_idx_tilecount, tiles * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_idx_tileoff, tiles * sizeof(uint64_t)));
+        ctx->idx_tiles = tiles;
+    }
+    /* first guess: members average >= 1 KiB; retry with the 28-byte worst case if there are more */
+    size_t guess = in_bytes / 1024 + 4096;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (guess > ctx->idx_cap) {
+            cudaFree(ctx->d_idx_inoff); cudaFree(ctx->d_idx_outoff); cudaFree(ctx->d_idx_isize); cudaFree(ctx->d_inf_status);
+            ctx->idx_cap = 0;
+            CK(cudaMalloc((void **)&ctx->d_idx_inoff, guess * sizeof(uint64_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_outoff, guess * sizeof(uint64_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_isize, guess * sizeof(uint32_t)));
+            CK(cudaMalloc((void **)&ctx->d_inf_status, guess * sizeof(uint32_t)));
+            ctx->idx_cap = guess;
+        }
+        CK(cudaMemsetAsync(ctx->d_idx_status, 0, 4 * sizeof(uint32_t), stream));
+        CK(bgzf_launch_index((const uint8_t *)d_in, in_bytes, ctx->d_idx_inoff, ctx->d_idx_outoff, (uint32_t)ctx->idx_cap,
+                             ctx->d_idx_tilecount, ctx->d_idx_tileoff, ctx->d_idx_isize, ctx->d_idx_counts, ctx->d_idx_counts + 1,
+                             ctx->d_idx_status, stream));
+        ctx->launches += 5;
+        CK(cudaMemcpyAsync(ctx->h_idx, ctx->d_idx_counts, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(ctx->h_idx + 2, ctx->d_idx_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const uint32_t st = (uint32_t)ctx->h_idx[2];
+        if (st & 2u) { guess = in_bytes / 28 + 1; continue; }
+        if (st) return B200BGZF_E_FORMAT;
+        break;
+    }
+    if ((uint32_t)ctx->h_idx[2]) return B200BGZF_E_FORMAT;
+    const uint64_t nm = ctx->h_idx[0], total = ctx->h_idx[1];
+    *out_bytes = (size_t)total;
+    if (total > out_cap || (!d_out && total)) return B200BGZF_E_NOSPACE;
+    BgzfInflateArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = (const uint8_t *)d_in;
+    a.in_off = ctx->d_idx_inoff;
+    a.out_off = ctx->d_idx_outoff;
+    a.nblocks = (uint32_t)nm;
+    a.out = (uint8_t *)d_out;
+    a.status = ctx->d_inf_status;
+    a.err_flag = ctx->d_idx_status + 1;
+    a.crctab = ctx->d_crctab;
+    CK(bgzf_launch_inflate(&a, stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_idx + 3, ctx->d_idx_status + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return (uint32_t)ctx->h_idx[3] ? B200BGZF_E_FORMAT : B200BGZF_OK;
+}
+
+extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
+                                     unsigned flags)
+{
+    (void)flags;
+    if (!ctx || !in || !out_bytes) return B200BGZF_E_ARG;
+    /* host walk of the member headers (applet/7bgzf.c:306-330) */
+    const uint8_t *p = (const uint8_t *)in;
+    std::vector<uint64_t> in_off, out_off;
+    size_t off = 0, total = 0;
+    while (off < in_bytes) {
+        const uint32_t sz = member_size(p + off, in_bytes - off);
+        if (!sz) return B200BGZF_E_FORMAT;
+        const uint8_t *t = p + off + sz - 4;
+        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (isize > B200BGZF_MAX_BLOCK_SIZE) return B200BGZF_E_FORMAT;
+        in_off.push_back(off);
+        out_off.push_back(total);
+        total += isize;
+        off += sz;
+    }
+    *out_bytes = total;
+    if (total > out_cap || (!out && total)) return B200BGZF_E_NOSPACE;
+    const size_t nm = in_off.size();
+    in_off.push_back(in_bytes);
+    out_off.push_back(total);
+    DeviceGuard g(ctx->device);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t batch = 4096;
+    int r;
+    bool bad = false;
+    size_t i = 0;
+    auto complete = [&](Lane &l) -> int {
+        CK(cudaStreamSynchronize(l.stream));
+        if (l.h_total[1]) bad = true;
+        l.pending = false;
+        return 0;
+    };
+    for (size_t first = 0; first < nm; first += batch, i++) {
+        Lane &l = ctx->lanes[i % kLanes];
+        if (l.pending && (r = complete(l))) return r;
+        const size_t nb = std::min(batch, nm - first);
+        const size_t cbytes = (size_t)(in_off[first + nb] - in_off[first]);
+        const size_t obytes = (size_t)(out_off[first + nb] - out_off[first]);
+        if ((r = lane_reserve(ctx, l, (uint32_t)batch, cbytes + 256, obytes + 256, false))) return r;
+        CK(grow(&l.h_meta, &l.meta_cap, 2 * batch, true));
+        for (size_t k = 0; k < nb; k++) {
+            l.h_meta[k] = in_off[first + k] - in_off[first];
+            l.h_meta[batch + k] = out_off[first + k] - out_off[first];
+        }
+        CK(cudaMemcpyAsync(l.d_in, p + in_off[first], cbytes, cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemcpyAsync(l.d_inoff, l.h_meta, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemcpyAsync(l.d_outoff, l.h_meta + batch, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
+        BgzfInflateArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = l.d_in;
+        a.in_off = l.d_inoff;
+        a.out_off = l.d_outoff;
+        a.nblocks = (uint32_t)nb;
+        a.out = l.d_out;
+        a.status = l.d_status;
+        a.err_flag = (uint32_t *)(l.d_total + 1);
+        a.crctab = ctx->d_crctab;
+        CK(bgzf_launch_inflate(&a, l.stream));
+        ctx->launches += 1;
+        if (obytes) CK(cudaMemcpyAsync((uint8_t *)out + out_off[first], l.d_out, obytes, cudaMemcpyDeviceToHost, l.stream));
+        CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+        l.pending = true;
+    }
+    for (auto &l : ctx->lanes)
+        if (l.pending && (r = complete(l))) return r;
+    return bad ? B200BGZF_E_FORMAT : B200BGZF_OK;
+}

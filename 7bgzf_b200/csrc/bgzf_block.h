@@ -1,0 +1,964 @@
+/*
+ * bgzf_block.h — the per-BGZF-block DEFLATE encoder, written as per-thread *phase* functions.
+ *
+ * One CTA of BG_THREADS threads owns one BGZF block (<= 64 KiB) that sits in shared memory.  Every phase
+ * below is a function of (context, thread index t, thread count T); the CUDA kernel (bgzf_compress.cu) calls
+ * the phases with t = threadIdx.x and a __syncthreads() between them, and the development emulator
+ * (tests/model/emul.cpp) calls the very same functions in a loop over t — in forward, reverse and shuffled
+ * order, which doubles as a race detector: a phase may only read what an earlier phase wrote.
+ * Warp-collective pieces (chain build with __match_any_sync, bitonic sort, block scan, TMA load) live in the
+ * .cu file and have plain sequential twins in the emulator; their results are order-independent by
+ * construction, so GPU output == emulator output, byte for byte.
+ *
+ * What it replaces in the reference (the CPU hot path, re-designed, not translated):
+ *   libdeflate_deflate_compress  lib/libdeflate/deflate_compress.c:4024-4066  (dispatcher, passthrough rule :4035)
+ *   deflate_compress_lazy_generic :2605-2809 + hc_matchfinder.h:182-399  -> all-position chain search + local lazy rule
+ *   choose_min_match_len :2295-2379                                      -> bg_min_match_len()
+ *   deflate_make_huffman_code :1318-1396                                 -> bg_huff_lengths()/bg_huff_codes()
+ *   deflate_precompute_huffman_header :1570-1631, compute_precode_items :1482-1557 -> bg_header_items()
+ *   deflate_flush_block :1706-2038                                       -> bg_decide()/emit phases
+ *   crc32 (hook) lib/zlib/crc32.c:1015, combine :155-186,1021-1026       -> bg_crc_* (per-thread slices + x^n combine)
+ *   framing bgzf_compress.c:191-196                                      -> bg_emit_frame()
+ *
+ * The compressed bytes are NOT meant to equal libdeflate's (the search is all-position parallel, one dynamic
+ * block per BGZF block); they must decode everywhere, CRC32/ISIZE must be exact and the size must stay
+ * within 3 % of the reference at the matching level.
+ */
+#ifndef BGZF_BLOCK_H
+#define BGZF_BLOCK_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BG_HD __host__ __device__ __forceinline__
+#else
+#define BG_HD static inline
+#endif
+
+#define BG_MAX_BLOCK 65536u   /* largest payload a block may carry (applet -@1 uses 0x10000, htslib 0xff00) */
+#define BG_DATA_BYTES (BG_MAX_BLOCK + 32u)
+#define BG_HASH_BITS 14
+#define BG_HASH_SIZE (1u << BG_HASH_BITS)
+#define BG_NOPOS 0xFFFFu
+#define BG_CHUNK 64u          /* parse/emit granule: one thread per chunk */
+#define BG_THREADS 1024u
+#define BG_MAX_CHUNKS (BG_MAX_BLOCK / BG_CHUNK)
+#define BG_SLOT_BYTES 65536u  /* one output slot = the largest legal BGZF member */
+#define BG_CRC_WORDS 17u      /* CRC slice per thread, in 32-bit words (odd => conflict-free smem striding) */
+#define BG_MIN_LOOKUP 4       /* shortest match the chain search can return */
+
+/* ---- region B overlay (32 KiB): the hash heads during the build, then everything Huffman ---- */
+#define BG_B_LFREQ 0        /* u32[288] */
+#define BG_B_DFREQ 1152     /* u32[32]  */
+#define BG_B_PFREQ 1280     /* u32[20]  */
+#define BG_B_LLEN 1360      /* u8[288]  */
+#define BG_B_DLEN 1648      /* u8[32]   */
+#define BG_B_PLEN 1680      /* u8[32]   */
+#define BG_B_LCODE 1712     /* u16[288] */
+#define BG_B_DCODE 2288     /* u16[32]  */
+#define BG_B_PCODE 2352     /* u16[24]  */
+#define BG_B_KEYS 2400      /* u32[512]  sort keys (freq<<9 | sym) */
+#define BG_B_TREEW 4448     /* u32[640]  node weights, then depths */
+#define BG_B_TREEP 7008     /* u16[640]  parent links */
+#define BG_B_ENTRY 8288     /* u16[1024] first token start inside each chunk, chunk-relative (BG_NOPOS: none) */
+#define BG_B_CBITS 10336    /* u32[1024] token bits per chunk, then exclusive prefix */
+#define BG_B_ITEMS 14432    /* u16[320]  precode items: sym | extra<<5 */
+#define BG_B_SCRATCH 15072  /* u32[64]   small-array scratch for the sequential Huffman code */
+#define BG_B_DKEYS 15328    /* u32[32]   dist sort keys */
+#define BG_B_PKEYS 15456    /* u32[32]   precode sort keys */
+#define BG_B_DTREEW 15584   /* u32[64]   */
+#define BG_B_DTREEP 15840   /* u16[64]   */
+#define BG_B_END 15968
+
+/* scalars kept in the always-live misc area (u32 each) */
+enum {
+    BG_S_NUSED = 0, BG_S_MINLEN, BG_S_HBYTES, BG_S_CRC, BG_S_NITEMS, BG_S_NL, BG_S_ND, BG_S_NP,
+    BG_S_BTYPE, BG_S_HDRBITS, BG_S_TOKBITS, BG_S_PAYLOAD, BG_S_STATUS, BG_S_NLKEYS, BG_S_NDKEYS, BG_S_WALKEND,
+    BG_S_COUNT = 32
+};
+
+struct BgParams {
+    int depth;        /* chain nodes visited per position */
+    int nice;         /* stop searching at this length */
+    int lazy;         /* 0 greedy, 1 one-ahead, 2 two-ahead */
+    int passthrough;  /* inputs this short are stored (reference: 55 - 4*level) */
+};
+
+/* level 1..12 -> search effort; the classes follow libdeflate_alloc_compressor_ex (deflate_compress.c:3921-4007):
+ * 1-4 greedy, 5-7 lazy, 8-9 lazy2, 10-12 deepest setting of this codec. */
+BG_HD BgParams bg_level_params(int level)
+{
+    BgParams p;
+    const int depth[13] = { 0, 2, 4, 6, 8, 10, 16, 32, 64, 128, 256, 384, 512 };
+    const int nice[13] = { 0, 32, 32, 48, 64, 64, 65, 130, 258, 258, 258, 258, 258 };
+    if (level < 1) level = 1;
+    if (level > 12) level = 12;
+    p.depth = depth[level];
+    p.nice = nice[level];
+    p.lazy = level <= 4 ? 0 : level <= 7 ? 1 : 2;
+    p.passthrough = 55 - 4 * level;
+    return p;
+}
+
+struct BgCtx {
+    uint32_t *dataw;    /* smem: the block, BG_DATA_BYTES */
+    uint16_t *prev;     /* smem region A (128 KiB): hash, then chain links */
+    uint8_t *stepcode;  /* region A[0..64K): 0 literal, 1..254 match len-2, 255 len >= 257 (see R) */
+    uint8_t *jump8;     /* region A[64K..128K): exit offset past the chunk end, 255 = walk it */
+    uint16_t *offarr;   /* region A[64K..128K) again, after the walk: match offset at [pos>>1] */
+    uint16_t *head;     /* smem region B (32 KiB): hash heads, later the overlay above */
+    uint8_t *regb;      /* region B as bytes */
+    uint8_t *litflag;   /* smem u8[256] */
+    uint32_t *crctab;   /* smem u32[256] */
+    uint32_t *scal;     /* smem u32[BG_S_COUNT] */
+    uint32_t *R;        /* global scratch u32[BG_MAX_BLOCK+8]: len<<16 | offset per position */
+    uint32_t *out;      /* global: this block's output slot, BG_SLOT_BYTES, 16-byte aligned */
+    const uint32_t *crcpow; /* global u32[BG_THREADS]: x^(8*4*BG_CRC_WORDS*k) mod P */
+    uint32_t n;         /* payload bytes */
+    BgParams prm;
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* small helpers                                                                                    */
+
+BG_HD uint32_t bg_ld32(const uint32_t *w, uint32_t p)
+{
+    uint32_t i = p >> 2, s = (p & 3u) * 8u;
+    uint32_t lo = w[i], hi = w[i + 1];
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32u - s)) : lo;
+#endif
+}
+
+BG_HD uint32_t bg_ld8(const uint32_t *w, uint32_t p) { return ((const uint8_t *)w)[p]; }
+
+BG_HD int bg_bsr(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz(v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
+BG_HD int bg_ctz(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs(v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
+BG_HD uint32_t bg_brev(uint32_t v, int nbits)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - nbits);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < nbits; i++)
+        r |= ((v >> i) & 1u) << (nbits - 1 - i);
+    return r;
+#endif
+}
+
+BG_HD void bg_add32(uint32_t *a, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(a, v);
+#else
+    *a += v;
+#endif
+}
+
+BG_HD void bg_or32(uint32_t *a, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicOr(a, v);
+#else
+    *a |= v;
+#endif
+}
+
+/* DEFLATE length (3..258) -> slot 0..28, extra bit count and value (RFC 1951 3.2.5) computed, not tabled */
+BG_HD uint32_t bg_len_slot(uint32_t len, uint32_t *nextra, uint32_t *extra)
+{
+    uint32_t l = len - 3;
+    if (l < 8) { *nextra = 0; *extra = 0; return l; }
+    if (len == 258) { *nextra = 0; *extra = 0; return 28; }
+    uint32_t nb = (uint32_t)bg_bsr(l) - 2;
+    *nextra = nb;
+    *extra = l & ((1u << nb) - 1);
+    return 8 + 4 * (nb - 1) + ((l >> nb) & 3);
+}
+
+/* offset (1..32768) -> slot 0..29 */
+BG_HD uint32_t bg_off_slot(uint32_t off, uint32_t *nextra, uint32_t *extra)
+{
+    uint32_t d = off - 1;
+    if (d < 4) { *nextra = 0; *extra = 0; return d; }
+    uint32_t b = (uint32_t)bg_bsr(d);
+    *nextra = b - 1;
+    *extra = d & ((1u << (b - 1)) - 1);
+    return 2 * b + ((d >> (b - 1)) & 1);
+}
+
+BG_HD uint32_t bg_len_slot_extra_bits(uint32_t slot) { return slot < 8 || slot == 28 ? 0 : (slot - 4) >> 2; }
+BG_HD uint32_t bg_off_slot_extra_bits(uint32_t slot) { return slot < 4 ? 0 : (slot - 2) >> 1; }
+
+/* static litlen code length (RFC 1951 3.2.6) */
+BG_HD uint32_t bg_static_llen(uint32_t sym) { return sym < 144 ? 8 : sym < 256 ? 9 : sym < 280 ? 7 : 8; }
+
+/* ---- CRC-32 (reflected 0xEDB88320) ------------------------------------------------------------- */
+
+#define BG_CRC_POLY 0xEDB88320u
+
+/* a(x)*b(x) mod P in the reflected representation (bit 31 = x^0); same algebra as zlib's multmodp */
+BG_HD uint32_t bg_crc_mul(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (int i = 0; i < 32; i++) {
+        p ^= b & (0u - ((a >> (31 - i)) & 1u));
+        b = (b >> 1) ^ (BG_CRC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+
+BG_HD uint32_t bg_crc_byte(const uint32_t *tab, uint32_t r, uint32_t b) { return tab[(r ^ b) & 0xff] ^ (r >> 8); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* phase 0: clear                                                                                   */
+
+BG_HD void bg_phase_init(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    for (uint32_t i = t; i < BG_HASH_SIZE; i += T)
+        c.head[i] = BG_NOPOS;
+    if (t < 256)
+        c.litflag[t] = 0;
+    if (t < 28)
+        ((uint8_t *)c.dataw)[c.n + t] = 0;  /* zero tail so word reads past n are defined */
+    if (t < BG_S_COUNT)
+        c.scal[t] = 0;
+}
+
+/* phase 1: which literals occur (benign same-value stores) + CRC slice per thread */
+BG_HD void bg_phase_scan(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    for (uint32_t p = t; p < n; p += T)
+        c.litflag[bg_ld8(c.dataw, p)] = 1;
+    /* CRC over the first m = n/4 words, slices right-aligned so the combine exponents are constants */
+    const uint32_t m = n >> 2;
+    const uint32_t k = T - 1 - t;                 /* slices after mine */
+    const uint32_t endw = m >= BG_CRC_WORDS * k ? m - BG_CRC_WORDS * k : 0;
+    const uint32_t begw = endw >= BG_CRC_WORDS ? endw - BG_CRC_WORDS : 0;
+    uint32_t r = 0;
+    if (endw > begw) {
+        r = begw == 0 ? 0xFFFFFFFFu : 0u;
+        for (uint32_t w = begw; w < endw; w++) {
+            uint32_t v = c.dataw[w];
+            r = bg_crc_byte(c.crctab, r, v & 0xff);
+            r = bg_crc_byte(c.crctab, r, (v >> 8) & 0xff);
+            r = bg_crc_byte(c.crctab, r, (v >> 16) & 0xff);
+            r = bg_crc_byte(c.crctab, r, v >> 24);
+        }
+        r = bg_crc_mul(r, c.crcpow[k]);
+    }
+    /* XOR is order-independent: fold inside the warp, then one shared atomic per warp */
+#if defined(__CUDA_ARCH__)
+    for (int d = 16; d > 0; d >>= 1)
+        r ^= __shfl_xor_sync(0xffffffffu, r, d);
+    if ((t & 31u) == 0 && r)
+        atomicXor(&c.scal[BG_S_CRC], r);
+#else
+    c.scal[BG_S_CRC] ^= r;
+#endif
+}
+
+/* phase 2: distinct-literal count (t < 256) */
+BG_HD void bg_phase_count(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    if (t < 256 && c.litflag[t])
+        bg_add32(&c.scal[BG_S_NUSED], 1);
+}
+
+/* Minimum useful match length from the number of distinct literals: cheap literals (DNA, quality strings)
+ * make short matches a loss for a lazy parser.  Same thresholds as the reference's heuristic table
+ * (deflate_compress.c:2295-2327), expressed as ranges. */
+BG_HD uint32_t bg_min_match_len(uint32_t nused, int depth, uint32_t n)
+{
+    uint32_t ml;
+    if (n < 512) return 3;
+    ml = nused < 6 ? 9 : nused < 8 ? 8 : nused < 10 ? 7 : nused < 16 ? 6 : nused < 45 ? 5 : nused < 80 ? 4 : 3;
+    if (depth < 16) {
+        uint32_t cap = depth < 5 ? 4 : depth < 10 ? 5 : 7;
+        if (ml > cap) ml = cap;
+    }
+    return ml;
+}
+
+/* phase 3: finish CRC (thread 0), settle minlen/hash width (thread 0) */
+BG_HD void bg_phase_settle(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    if (t != 0) return;
+    const uint32_t n = c.n;
+    uint32_t r = c.scal[BG_S_CRC];
+    if ((n >> 2) == 0) r = 0xFFFFFFFFu;
+    for (uint32_t p = n & ~3u; p < n; p++)
+        r = bg_crc_byte(c.crctab, r, bg_ld8(c.dataw, p));
+    c.scal[BG_S_CRC] = ~r;
+    uint32_t ml = bg_min_match_len(c.scal[BG_S_NUSED], c.prm.depth, n);
+    c.scal[BG_S_MINLEN] = ml;
+    c.scal[BG_S_HBYTES] = ml >= 5 ? 5 : 4;
+}
+
+/* phase 4: hash every position that has a full hash window into prev[] */
+BG_HD uint32_t bg_hash(const uint32_t *dataw, uint32_t p, uint32_t hbytes)
+{
+    uint32_t v = bg_ld32(dataw, p);
+    uint32_t h = v * 0x1E35A7BDu;
+    if (hbytes == 5)
+        h ^= bg_ld8(dataw, p + 4) * 0x9E3779B1u;
+    return h >> (32 - BG_HASH_BITS);
+}
+
+BG_HD void bg_phase_hash(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n, hb = c.scal[BG_S_HBYTES];
+    for (uint32_t p = t; p < n; p += T)
+        c.prev[p] = (p + hb <= n) ? (uint16_t)bg_hash(c.dataw, p, hb) : (uint16_t)BG_NOPOS;
+}
+
+/* phase 5 (sequential twin of the warp build in the .cu): prev[p] = nearest earlier position with my hash */
+BG_HD void bg_build_sequential(const BgCtx &c)
+{
+    for (uint32_t p = 0; p < c.n; p++) {
+        uint32_t h = c.prev[p];
+        if (h == BG_NOPOS) continue;
+        c.prev[p] = c.head[h];
+        c.head[h] = (uint16_t)p;
+    }
+}
+
+/* phase 6: all-position search */
+BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
+{
+    const uint32_t n = c.n;
+    uint32_t maxl = n - p;
+    if (maxl > 258) maxl = 258;
+    if (maxl < (uint32_t)BG_MIN_LOOKUP) return 0;
+    uint32_t q = c.prev[p];
+    if (q == BG_NOPOS) return 0;
+    const uint32_t *dw = c.dataw;
+    const uint32_t wp = bg_ld32(dw, p);
+    uint32_t best = 3, boff = 0, wtail = 0;
+    int depth = c.prm.depth;
+    const uint32_t nice = (uint32_t)c.prm.nice;
+    for (;;) {
+        uint32_t dist = p - q;
+        if (dist > 32768u) break;
+        if (bg_ld32(dw, q) == wp && (best == 3 || bg_ld32(dw, q + best - 3) == wtail)) {
+            uint32_t l = 4;
+            while (l < maxl) {
+                uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
+                if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
+                l += 4;
+            }
+            if (l > maxl) l = maxl;
+            if (l > best) {
+                best = l;
+                boff = dist;
+                if (l >= nice || l == maxl) break;
+                wtail = bg_ld32(dw, p + best - 3);
+            }
+        }
+        if (--depth <= 0) break;
+        q = c.prev[q];
+        if (q == BG_NOPOS) break;
+    }
+    return best > 3 ? (best << 16) | boff : 0;
+}
+
+BG_HD void bg_phase_search(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    for (uint32_t p = t; p < c.n; p += T)
+        c.R[p] = bg_search_one(c, p);
+}
+
+/* phase 7: local accept + lazy rule -> stepcode (deflate_compress.c:2664-2670, 2723-2726, 2753-2756 restated
+ * as a function of the matches at p, p+1, p+2 only, so that every position decides independently) */
+BG_HD bool bg_match_ok(uint32_t r, uint32_t minlen)
+{
+    uint32_t len = r >> 16, off = r & 0xffffu;
+    return len >= minlen && len >= 3 && !(len == 3 && off > 8192);
+}
+
+BG_HD void bg_phase_accept(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n, minlen = c.scal[BG_S_MINLEN];
+    const int lazy = c.prm.lazy;
+    const uint32_t nice = (uint32_t)c.prm.nice;
+    for (uint32_t p = t; p < n; p += T) {
+        uint32_t r0 = c.R[p];
+        uint32_t code = 0;
+        if (bg_match_ok(r0, minlen)) {
+            uint32_t cl = r0 >> 16, co = r0 & 0xffffu;
+            bool take = true;
+            if (lazy >= 1 && cl < nice && p + 1 < n) {
+                uint32_t r1 = c.R[p + 1];
+                if (bg_match_ok(r1, minlen)) {
+                    int nl = (int)(r1 >> 16);
+                    if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r1 & 0xffffu)) > 2)
+                        take = false;
+                }
+                if (take && lazy >= 2 && p + 2 < n) {
+                    uint32_t r2 = c.R[p + 2];
+                    if (bg_match_ok(r2, minlen)) {
+                        int nl = (int)(r2 >> 16);
+                        if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r2 & 0xffffu)) > 6)
+                            take = false;
+                    }
+                }
+            }
+            if (take)
+                code = cl <= 256 ? cl - 2 : 255;
+        }
+        c.stepcode[p] = (uint8_t)code;
+    }
+}
+
+BG_HD uint32_t bg_step(const BgCtx &c, uint32_t p)
+{
+    uint32_t sc = c.stepcode[p];
+    if (sc == 0) return 1;
+    if (sc == 255) return c.R[p] >> 16;
+    return sc + 2;
+}
+
+/* phase 8: per chunk, from the back: where does a parse entering at p leave the chunk? */
+BG_HD void bg_phase_jump(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    for (uint32_t ch = t; ch * BG_CHUNK < n; ch += T) {
+        uint32_t s = ch * BG_CHUNK, e = s + BG_CHUNK;
+        if (e > n) e = n;
+        for (uint32_t p = e; p-- > s;) {
+            uint32_t nx = p + bg_step(c, p);
+            uint32_t j;
+            if (nx >= e) { j = nx - e; if (j > 255) j = 255; }
+            else j = c.jump8[nx];
+            c.jump8[p] = (uint8_t)j;
+        }
+    }
+}
+
+/* phase 9 (thread 0): walk chunk to chunk, recording where the parse enters each chunk */
+BG_HD void bg_phase_walk(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    if (t != 0) return;
+    const uint32_t n = c.n;
+    uint16_t *entry = (uint16_t *)(c.regb + BG_B_ENTRY);
+    uint32_t e = 0;
+    for (uint32_t ch = 0; ch * BG_CHUNK < n; ch++) {
+        uint32_t end = ch * BG_CHUNK + BG_CHUNK;
+        if (end > n) end = n;
+        if (e >= end) { entry[ch] = BG_NOPOS; continue; }
+        entry[ch] = (uint16_t)(e - ch * BG_CHUNK);   /* chunk-relative: 65535 is a legal position */
+        uint32_t j = c.jump8[e];
+        if (j == 255) {
+            uint32_t q = e;
+            while (q < end) q += bg_step(c, q);
+            e = q;
+        } else {
+            e = end + j;
+        }
+    }
+    c.scal[BG_S_WALKEND] = e;   /* must equal n */
+}
+
+/* phase 10: clear histograms (region B is free now) */
+BG_HD void bg_phase_clear_freq(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint32_t *f = (uint32_t *)(c.regb + BG_B_LFREQ);
+    for (uint32_t i = t; i < (BG_B_LLEN - BG_B_LFREQ) / 4; i += T)
+        f[i] = 0;
+}
+
+/* phase 11: tally symbols along the parse; remember match offsets in smem */
+BG_HD void bg_phase_tally(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    uint32_t *lfreq = (uint32_t *)(c.regb + BG_B_LFREQ);
+    uint32_t *dfreq = (uint32_t *)(c.regb + BG_B_DFREQ);
+    const uint16_t *entry = (const uint16_t *)(c.regb + BG_B_ENTRY);
+    for (uint32_t ch = t; ch * BG_CHUNK < n; ch += T) {
+        uint32_t p = entry[ch];
+        if (p == BG_NOPOS) continue;
+        p += ch * BG_CHUNK;
+        uint32_t end = ch * BG_CHUNK + BG_CHUNK;
+        if (end > n) end = n;
+        while (p < end) {
+            if (c.stepcode[p] == 0) {
+                bg_add32(&lfreq[bg_ld8(c.dataw, p)], 1);
+                p++;
+            } else {
+                uint32_t r = c.R[p], len = r >> 16, off = r & 0xffffu, nb, ex;
+                bg_add32(&lfreq[257 + bg_len_slot(len, &nb, &ex)], 1);
+                bg_add32(&dfreq[bg_off_slot(off, &nb, &ex)], 1);
+                c.offarr[p >> 1] = (uint16_t)(off - 1);
+                p += len;
+            }
+        }
+    }
+    if (t == 0)
+        bg_add32(&lfreq[256], 1);
+}
+
+/* phase 12: make sort keys for the litlen code (parallel) */
+BG_HD void bg_phase_lkeys(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t *lfreq = (const uint32_t *)(c.regb + BG_B_LFREQ);
+    uint32_t *keys = (uint32_t *)(c.regb + BG_B_KEYS);
+    for (uint32_t i = t; i < 512; i += T)
+        keys[i] = (i < 288 && lfreq[i]) ? (lfreq[i] << 9) | i : 0xFFFFFFFFu;
+}
+
+/* ---- sequential Huffman pieces (one thread; arrays in shared memory) ---------------------------- */
+
+/* insertion sort of up to 32 keys, used for the distance and precode alphabets */
+BG_HD uint32_t bg_small_keys(const uint32_t *freq, uint32_t nsym, uint32_t *keys)
+{
+    uint32_t m = 0;
+    for (uint32_t s = 0; s < nsym; s++) {
+        if (!freq[s]) continue;
+        uint32_t k = (freq[s] << 9) | s, i = m++;
+        while (i > 0 && keys[i - 1] > k) { keys[i] = keys[i - 1]; i--; }
+        keys[i] = k;
+    }
+    return m;
+}
+
+/* keys: ascending (freq<<9|sym) for the m used symbols.  lens[] must be zeroed by the caller.
+ * Two-queue Huffman tree, depths clamped to maxbits with the classic overflow repair on the
+ * per-length counts (the approach of zlib's gen_bitlen), longest codes to the rarest symbols. */
+BG_HD void bg_huff_lengths(const uint32_t *keys, uint32_t m, uint32_t maxbits, uint32_t *w, uint16_t *par,
+                           uint32_t *blc /* u32[16] scratch */, uint8_t *lens)
+{
+    if (m == 0) { lens[0] = 1; lens[1] = 1; return; }
+    if (m == 1) {
+        uint32_t s = keys[0] & 511u;
+        lens[s] = 1;
+        lens[s ? 0 : 1] = 1;
+        return;
+    }
+    for (uint32_t i = 0; i < m; i++) w[i] = keys[i] >> 9;
+    uint32_t a = 0, b = m, e = m;
+    while (e < 2 * m - 1) {
+        uint32_t x0, x1;
+        if (a < m && (b >= e || w[a] <= w[b])) x0 = a++; else x0 = b++;
+        if (a < m && (b >= e || w[a] <= w[b])) x1 = a++; else x1 = b++;
+        w[e] = w[x0] + w[x1];
+        par[x0] = (uint16_t)e;
+        par[x1] = (uint16_t)e;
+        e++;
+    }
+    for (uint32_t i = 0; i <= maxbits; i++) blc[i] = 0;
+    int overflow = 0;
+    w[e - 1] = 0;
+    for (uint32_t i = e - 1; i-- > 0;) {
+        uint32_t d = w[par[i]] + 1;
+        if (d > maxbits) { d = maxbits; overflow++; }
+        w[i] = d;
+        if (i < m) blc[d]++;
+    }
+    while (overflow > 0) {
+        uint32_t bits = maxbits - 1;
+        while (blc[bits] == 0) bits--;
+        blc[bits]--;
+        blc[bits + 1] += 2;
+        blc[maxbits]--;
+        overflow -= 2;
+    }
+    uint32_t i = 0;
+    for (uint32_t bits = maxbits; bits >= 1; bits--)
+        for (uint32_t k = blc[bits]; k > 0; k--)
+            lens[keys[i++] & 511u] = (uint8_t)bits;
+}
+
+/* canonical, bit-reversed codewords; scratch = u32[36] */
+BG_HD void bg_huff_codes(const uint8_t *lens, uint32_t nsym, uint32_t maxbits, uint32_t *scratch, uint16_t *codes)
+{
+    uint32_t *count = scratch, *next = scratch + 18;
+    for (uint32_t i = 0; i <= maxbits; i++) count[i] = 0;
+    for (uint32_t s = 0; s < nsym; s++) count[lens[s]]++;
+    count[0] = 0;
+    uint32_t code = 0;
+    for (uint32_t l = 1; l <= maxbits; l++) {
+        code = (code + count[l - 1]) << 1;
+        next[l] = code;
+    }
+    for (uint32_t s = 0; s < nsym; s++) {
+        uint32_t l = lens[s];
+        codes[s] = l ? (uint16_t)bg_brev(next[l]++, (int)l) : 0;
+    }
+}
+
+/* run-length items over litlen+offset lengths (RFC 1951 3.2.7); returns item count, fills pfreq */
+BG_HD uint32_t bg_header_items(const uint8_t *llen, uint32_t nl, const uint8_t *dlen, uint32_t nd, uint16_t *items,
+                               uint32_t *pfreq)
+{
+    for (uint32_t i = 0; i < 19; i++) pfreq[i] = 0;
+    const uint32_t total = nl + nd;
+    uint32_t ni = 0, i = 0;
+    while (i < total) {
+        uint32_t v = i < nl ? llen[i] : dlen[i - nl];
+        uint32_t j = i + 1;
+        while (j < total && (j < nl ? llen[j] : dlen[j - nl]) == v) j++;
+        uint32_t run = j - i;
+        if (v == 0) {
+            while (run >= 11) {
+                uint32_t r = run > 138 ? 138 : run;
+                items[ni++] = (uint16_t)(18 | ((r - 11) << 5));
+                pfreq[18]++;
+                run -= r;
+            }
+            if (run >= 3) {
+                items[ni++] = (uint16_t)(17 | ((run - 3) << 5));
+                pfreq[17]++;
+                run = 0;
+            }
+        } else {
+            items[ni++] = (uint16_t)v;
+            pfreq[v]++;
+            run--;
+            while (run >= 3) {
+                uint32_t r = run > 6 ? 6 : run;
+                items[ni++] = (uint16_t)(16 | ((r - 3) << 5));
+                pfreq[16]++;
+                run -= r;
+            }
+        }
+        while (run > 0) { items[ni++] = (uint16_t)v; pfreq[v]++; run--; }
+        i = j;
+    }
+    return ni;
+}
+
+/* precode length order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15 (RFC 1951 3.2.7), 5 bits each */
+BG_HD uint32_t bg_precode_order(uint32_t i)
+{
+    const uint64_t lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 |
+                        10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+    const uint64_t hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+    return (uint32_t)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31u);
+}
+
+/* phase 13: thread 0 builds the litlen lengths, thread 32 the distance lengths */
+BG_HD void bg_phase_huff(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    uint8_t *rb = c.regb;
+    if (t == 0) {
+        const uint32_t *keys = (const uint32_t *)(rb + BG_B_KEYS);
+        uint8_t *llen = rb + BG_B_LLEN;
+        for (uint32_t i = 0; i < 288; i++) llen[i] = 0;
+        uint32_t m = 0;
+        while (m < 288 && keys[m] != 0xFFFFFFFFu) m++;
+        bg_huff_lengths(keys, m, 15, (uint32_t *)(rb + BG_B_TREEW), (uint16_t *)(rb + BG_B_TREEP),
+                        (uint32_t *)(rb + BG_B_SCRATCH), llen);
+    }
+    if (t == 32 % T) {
+        uint32_t *dkeys = (uint32_t *)(rb + BG_B_DKEYS);
+        uint8_t *dlen = rb + BG_B_DLEN;
+        for (uint32_t i = 0; i < 32; i++) dlen[i] = 0;
+        uint32_t m = bg_small_keys((const uint32_t *)(rb + BG_B_DFREQ), 30, dkeys);
+        bg_huff_lengths(dkeys, m, 15, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP),
+                        (uint32_t *)(rb + BG_B_SCRATCH) + 32, dlen);
+    }
+}
+
+/* phase 14 (thread 0): header items, precode, exact costs, block type, final code tables */
+BG_HD void bg_phase_decide(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    if (t != 0) return;
+    uint8_t *rb = c.regb;
+    const uint32_t n = c.n;
+    uint32_t *lfreq = (uint32_t *)(rb + BG_B_LFREQ), *dfreq = (uint32_t *)(rb + BG_B_DFREQ);
+    uint32_t *pfreq = (uint32_t *)(rb + BG_B_PFREQ);
+    uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN, *plen = rb + BG_B_PLEN;
+    uint16_t *lcode = (uint16_t *)(rb + BG_B_LCODE), *dcode = (uint16_t *)(rb + BG_B_DCODE);
+    uint16_t *pcode = (uint16_t *)(rb + BG_B_PCODE), *items = (uint16_t *)(rb + BG_B_ITEMS);
+    uint32_t *scratch = (uint32_t *)(rb + BG_B_SCRATCH);
+
+    uint32_t nl = 286, nd = 30;
+    while (nl > 257 && llen[nl - 1] == 0) nl--;
+    while (nd > 1 && dlen[nd - 1] == 0) nd--;
+    uint32_t ni = bg_header_items(llen, nl, dlen, nd, items, pfreq);
+    uint32_t *pkeys = (uint32_t *)(rb + BG_B_PKEYS);
+    for (uint32_t i = 0; i < 19; i++) plen[i] = 0;
+    uint32_t pm = bg_small_keys(pfreq, 19, pkeys);
+    bg_huff_lengths(pkeys, pm, 7, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP), scratch, plen);
+    uint32_t np = 19;
+    while (np > 4 && plen[bg_precode_order(np - 1)] == 0) np--;
+
+    /* exact bit costs */
+    uint32_t extra = 0, dyn_syms = 0, sta_syms = 0;
+    for (uint32_t s = 0; s < 286; s++) {
+        uint32_t f = lfreq[s];
+        if (!f) continue;
+        dyn_syms += f * llen[s];
+        sta_syms += f * bg_static_llen(s);
+        if (s > 256) extra += f * bg_len_slot_extra_bits(s - 257);
+    }
+    for (uint32_t s = 0; s < 30; s++) {
+        uint32_t f = dfreq[s];
+        if (!f) continue;
+        dyn_syms += f * dlen[s];
+        sta_syms += f * 5;
+        extra += f * bg_off_slot_extra_bits(s);
+    }
+    uint32_t hdr = 3 + 5 + 5 + 4 + 3 * np;
+    for (uint32_t i = 0; i < ni; i++) {
+        uint32_t sym = items[i] & 31u;
+        hdr += plen[sym] + (sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0);
+    }
+    const uint32_t dyn_bits = hdr + dyn_syms + extra;
+    const uint32_t sta_bits = 3 + sta_syms + extra;
+    const uint32_t nstored = n ? (n + 65534u) / 65535u : 1u;
+    const uint32_t sto_bits = 8 * (n + 5 * nstored);
+
+    uint32_t btype, hdrbits, tokbits;
+    if (n != 0 && ((int)n <= c.prm.passthrough || (sto_bits <= sta_bits && sto_bits <= dyn_bits))) {
+        btype = 0; hdrbits = 0; tokbits = 0;
+        c.scal[BG_S_PAYLOAD] = n + 5 * nstored;
+    } else if (sta_bits <= dyn_bits) {
+        btype = 1; hdrbits = 3; tokbits = sta_bits - 3;
+        for (uint32_t s = 0; s < 288; s++) llen[s] = (uint8_t)bg_static_llen(s);
+        for (uint32_t s = 0; s < 32; s++) dlen[s] = 5;
+        c.scal[BG_S_PAYLOAD] = (sta_bits + 7) >> 3;
+    } else {
+        btype = 2; hdrbits = hdr; tokbits = dyn_bits - hdr;
+        c.scal[BG_S_PAYLOAD] = (dyn_bits + 7) >> 3;
+    }
+    if (btype) {
+        bg_huff_codes(llen, 288, 15, scratch, lcode);
+        bg_huff_codes(dlen, 32, 15, scratch, dcode);
+        if (btype == 2) bg_huff_codes(plen, 19, 7, scratch, pcode);
+    }
+    c.scal[BG_S_BTYPE] = btype;
+    c.scal[BG_S_HDRBITS] = hdrbits;
+    c.scal[BG_S_TOKBITS] = tokbits;   /* includes the end-of-block symbol */
+    c.scal[BG_S_NITEMS] = ni;
+    c.scal[BG_S_NL] = nl;
+    c.scal[BG_S_ND] = nd;
+    c.scal[BG_S_NP] = np;
+    c.scal[BG_S_STATUS] = (18u + c.scal[BG_S_PAYLOAD] + 8u > BG_SLOT_BYTES) ? 1u : 0u;
+}
+
+/* phase 15: bits per chunk with the final code */
+BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    uint8_t *rb = c.regb;
+    const uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN;
+    const uint16_t *entry = (const uint16_t *)(rb + BG_B_ENTRY);
+    uint32_t *cbits = (uint32_t *)(rb + BG_B_CBITS);
+    const bool coded = c.scal[BG_S_BTYPE] != 0;
+    for (uint32_t ch = t; ch < BG_MAX_CHUNKS; ch += T) {
+        uint32_t bits = 0;
+        uint32_t p = ch * BG_CHUNK < n ? entry[ch] : BG_NOPOS;
+        if (coded && p != BG_NOPOS) {
+            p += ch * BG_CHUNK;
+            uint32_t end = ch * BG_CHUNK + BG_CHUNK;
+            if (end > n) end = n;
+            while (p < end) {
+                uint32_t sc = c.stepcode[p];
+                if (sc == 0) {
+                    bits += llen[bg_ld8(c.dataw, p)];
+                    p++;
+                } else {
+                    uint32_t len = sc == 255 ? (c.R[p] >> 16) : sc + 2, nb, ex;
+                    bits += llen[257 + bg_len_slot(len, &nb, &ex)] + nb;
+                    bits += dlen[bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex)] + nb;
+                    p += len;
+                }
+            }
+        }
+        cbits[ch] = bits;
+    }
+}
+
+/* (between 15 and 16 the driver turns cbits[] into its exclusive prefix sum) */
+
+/* phase 16: zero the output words this block will OR into */
+BG_HD void bg_phase_zero_out(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint32_t bytes = 18 + c.scal[BG_S_PAYLOAD] + 8;
+    if (bytes > BG_SLOT_BYTES) bytes = BG_SLOT_BYTES;
+    uint32_t words = (bytes + 3) >> 2;
+    for (uint32_t i = t; i < words; i += T)
+        c.out[i] = 0;
+}
+
+struct BgWriter {
+    uint32_t *out;
+    uint32_t word;
+    uint64_t acc;
+    uint32_t nacc;
+    bool shared;   /* the word being filled may also be written by a neighbour: OR it */
+};
+
+BG_HD void bg_w_init(BgWriter &w, uint32_t *out, uint32_t bitpos)
+{
+    w.out = out;
+    w.word = bitpos >> 5;
+    w.nacc = bitpos & 31u;
+    w.acc = 0;
+    w.shared = true;
+}
+
+BG_HD void bg_w_put(BgWriter &w, uint32_t val, uint32_t nbits)
+{
+    w.acc |= (uint64_t)val << w.nacc;
+    w.nacc += nbits;
+    if (w.nacc >= 32) {
+        if (w.shared) bg_or32(&w.out[w.word], (uint32_t)w.acc);
+        else w.out[w.word] = (uint32_t)w.acc;
+        w.shared = false;
+        w.word++;
+        w.acc >>= 32;
+        w.nacc -= 32;
+    }
+}
+
+BG_HD void bg_w_flush(BgWriter &w)
+{
+    if (w.nacc > 0 && (uint32_t)w.acc != 0)
+        bg_or32(&w.out[w.word], (uint32_t)w.acc);
+}
+
+/* BGZF framing: 18-byte header with BSIZE, then CRC32 + ISIZE after the payload (bgzf_compress.c:191-196) */
+BG_HD void bg_emit_frame(const BgCtx &c)
+{
+    const uint32_t payload = c.scal[BG_S_PAYLOAD];
+    const uint32_t total = 18 + payload + 8;
+    BgWriter w;
+    bg_w_init(w, c.out, 0);
+    bg_w_put(w, 0x04088b1fu, 32);          /* 1f 8b 08 04 */
+    bg_w_put(w, 0u, 32);                   /* MTIME */
+    bg_w_put(w, 0x0006ff00u, 32);          /* XFL 00, OS ff, XLEN 0006 */
+    bg_w_put(w, 0x00024342u, 32);          /* 'B' 'C' SLEN 0002 */
+    bg_w_put(w, (total - 1) & 0xffffu, 16);
+    bg_w_flush(w);
+    bg_w_init(w, c.out, (18 + payload) * 8);
+    bg_w_put(w, c.scal[BG_S_CRC], 32);
+    bg_w_put(w, c.n, 32);
+    bg_w_flush(w);
+}
+
+/* phase 17: write everything.  thread 0: frame + block header (+EOB); chunk threads: tokens;
+ * stored blocks: all threads copy words. */
+BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    if (c.scal[BG_S_STATUS]) return;
+    const uint32_t n = c.n;
+    uint8_t *rb = c.regb;
+    const uint32_t btype = c.scal[BG_S_BTYPE];
+    const uint32_t base = 18 * 8;
+    if (btype == 0) {
+        /* stored: [01|00] LEN NLEN raw..., at most two stored blocks (n <= 65536) */
+        const uint32_t first = n > 65535u ? 65535u : n;
+        if (t == 0) {
+            bg_emit_frame(c);
+            BgWriter w;
+            bg_w_init(w, c.out, base);
+            bg_w_put(w, n > 65535u ? 0u : 1u, 8);
+            bg_w_put(w, first | ((~first & 0xffffu) << 16), 32);
+            bg_w_flush(w);
+            if (n > 65535u) {
+                uint32_t rest = n - 65535u;
+                bg_w_init(w, c.out, base + (5 + 65535u) * 8);
+                bg_w_put(w, 1u, 8);
+                bg_w_put(w, rest | ((~rest & 0xffffu) << 16), 32);
+                bg_w_flush(w);
+            }
+        }
+        /* raw bytes: payload byte i lands at slot byte 23+i (+5 more after the first 65535).
+         * Output words whose four source bytes all lie in the first stored block are plain stores
+         * of an unaligned read; the few bytes at either edge are OR-ed in one by one. */
+        const uint32_t wend = (first + 23u) >> 2;              /* first word that is not "full" */
+        for (uint32_t wd = 6 + t; wd < wend; wd += T)
+            c.out[wd] = bg_ld32(c.dataw, 4 * wd - 23);
+        const uint32_t s1 = wend > 6 ? 4 * wend - 23 : 1;      /* first source byte past the full words */
+        if (t < 16) {
+            uint32_t src = t == 0 ? 0 : s1 + (t - 1);
+            if (src < n) {
+                uint32_t dst = 23 + src + (src >= 65535u ? 5 : 0);
+                bg_or32(&c.out[dst >> 2], bg_ld8(c.dataw, src) << (8 * (dst & 3)));
+            }
+        }
+        return;
+    }
+    const uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN, *plen = rb + BG_B_PLEN;
+    const uint16_t *lcode = (const uint16_t *)(rb + BG_B_LCODE), *dcode = (const uint16_t *)(rb + BG_B_DCODE);
+    const uint16_t *pcode = (const uint16_t *)(rb + BG_B_PCODE), *items = (const uint16_t *)(rb + BG_B_ITEMS);
+    const uint16_t *entry = (const uint16_t *)(rb + BG_B_ENTRY);
+    const uint32_t *cbits = (const uint32_t *)(rb + BG_B_CBITS);
+    const uint32_t hdrbits = c.scal[BG_S_HDRBITS];
+    if (t == 0) {
+        bg_emit_frame(c);
+        BgWriter w;
+        bg_w_init(w, c.out, base);
+        bg_w_put(w, 1u | (btype << 1), 3);
+        if (btype == 2) {
+            const uint32_t nl = c.scal[BG_S_NL], nd = c.scal[BG_S_ND], np = c.scal[BG_S_NP];
+            bg_w_put(w, (nl - 257) | ((nd - 1) << 5) | ((np - 4) << 10), 14);
+            for (uint32_t i = 0; i < np; i++)
+                bg_w_put(w, plen[bg_precode_order(i)], 3);
+            const uint32_t ni = c.scal[BG_S_NITEMS];
+            for (uint32_t i = 0; i < ni; i++) {
+                uint32_t sym = items[i] & 31u, ex = items[i] >> 5;
+                bg_w_put(w, pcode[sym], plen[sym]);
+                if (sym >= 16) bg_w_put(w, ex, sym == 16 ? 2 : sym == 17 ? 3 : 7);
+            }
+        }
+        bg_w_flush(w);
+        /* end-of-block symbol closes the token stream */
+        bg_w_init(w, c.out, base + hdrbits + c.scal[BG_S_TOKBITS] - llen[256]);
+        bg_w_put(w, lcode[256], llen[256]);
+        bg_w_flush(w);
+    }
+    for (uint32_t ch = t; ch * BG_CHUNK < n; ch += T) {
+        uint32_t p = entry[ch];
+        if (p == BG_NOPOS) continue;
+        p += ch * BG_CHUNK;
+        uint32_t end = ch * BG_CHUNK + BG_CHUNK;
+        if (end > n) end = n;
+        BgWriter w;
+        bg_w_init(w, c.out, base + hdrbits + cbits[ch]);
+        while (p < end) {
+            uint32_t sc = c.stepcode[p];
+            if (sc == 0) {
+                uint32_t b = bg_ld8(c.dataw, p);
+                bg_w_put(w, lcode[b], llen[b]);
+                p++;
+            } else {
+                uint32_t len = sc == 255 ? (c.R[p] >> 16) : sc + 2, nb, ex;
+                uint32_t ls = 257 + bg_len_slot(len, &nb, &ex);
+                bg_w_put(w, (uint32_t)lcode[ls] | (ex << llen[ls]), llen[ls] + nb);
+                uint32_t ds = bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex);
+                bg_w_put(w, (uint32_t)dcode[ds] | (ex << dlen[ds]), dlen[ds] + nb);
+                p += len;
+            }
+        }
+        bg_w_flush(w);
+    }
+}
+
+#endif /* BGZF_BLOCK_H */

@@ -1,0 +1,514 @@
+/*
+ * bgzf_inflate.cu — sm_100a BGZF inflate kernels.
+ *
+ *   bgzf_inflate_kernel : one CTA (= one warp) per BGZF member, ~9 KiB of shared memory each, so ~24 members
+ *       decode concurrently per SM.  All 32 lanes run the bit reader in lock-step (uniform control flow,
+ *       broadcast LUT reads); the compressed bytes arrive as coalesced 128-byte chunks, one word per lane,
+ *       and are handed to the reader with __shfl_sync; back-references are copied by all lanes.
+ *       Table-driven Huffman decode from shared-memory LUTs: 10-bit root + sub-tables for the litlen code,
+ *       8-bit root + sub-tables for the offset code, 7-bit precode table.
+ *   bgzf_index_* : finds the members of a device-resident BGZF stream in parallel (signature scan, ordered
+ *       compaction, BSIZE chain validation, exclusive scan of ISIZE) — the device form of the applet's
+ *       header walk.
+ *
+ * Replaces in the reference: applet/7bgzf.c:295-365 (_decompress), :81-131 (_read_gz_header),
+ * lib/zlibutil.c:82-93,194-204 (auto_inflate -> libdeflate_inflate), lib/libdeflate/deflate_decompress.c:721-1004
+ * (build_decode_table) and decompress_template.h:44-772 (the decode loop).  Any valid DEFLATE stream is
+ * accepted (stored / static / dynamic, several blocks per member); malformed input yields a per-member
+ * error code, never an out-of-bounds write.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bgzf_block.h"
+#include "bgzf_kernels.h"
+
+#define INF_LROOT 10
+#define INF_DROOT 8
+#define INF_LTAB (1024 + 352)   /* litlen root + sub-tables (valid codes need <= 1334) */
+#define INF_DTAB (256 + 160)    /* offset root + sub-tables (valid codes need <= 402) */
+#define INF_PTAB 128
+#define INF_WARPS_PER_CTA 1
+
+/* decode-table entry: [3:0] bits to consume, [7:4] extra-bit count, [10:8] kind, [15:11] sub-table bits,
+ * [31:16] value (literal / base length / base offset / sub-table start).  0 = invalid. */
+#define K_LIT 1u
+#define K_BASE 2u
+#define K_EOB 3u
+#define K_SUB 4u
+#define ENT(nb, xb, kind, sb, val) ((uint32_t)(nb) | ((uint32_t)(xb) << 4) | ((uint32_t)(kind) << 8) | ((uint32_t)(sb) << 11) | ((uint32_t)(val) << 16))
+
+/* per-member error codes (status[]) */
+#define INF_OK 0u
+#define INF_E_HEADER 1u     /* not a BGZF member header */
+#define INF_E_BTYPE 2u      /* reserved block type */
+#define INF_E_CODE 3u       /* over-subscribed / unusable Huffman code */
+#define INF_E_SYMBOL 4u     /* invalid codeword in the data */
+#define INF_E_DIST 5u       /* offset reaches before the start of the member */
+#define INF_E_OVERRUN 6u    /* more output than ISIZE / input exhausted */
+#define INF_E_STORED 7u     /* LEN != ~NLEN */
+#define INF_E_SHORT 8u      /* output shorter than ISIZE */
+
+struct InfSmem {
+    uint32_t ltab[INF_LTAB];
+    uint32_t dtab[INF_DTAB];
+    uint32_t ptab[INF_PTAB];
+    uint32_t offs[16];
+    uint8_t lens[320 + 16];
+};
+
+struct BitReader {
+    const uint32_t *base;   /* word-aligned start */
+    uint32_t nwords;        /* words that may be read */
+    uint32_t chunk;         /* this lane's word of the current 32-word chunk */
+    uint32_t wpos;          /* index of the next word to hand out */
+    uint64_t bb;            /* bit buffer */
+    uint32_t bc;            /* valid bits */
+    uint32_t lane;
+};
+
+__device__ __forceinline__ void br_load_chunk(BitReader &r)
+{
+    const uint32_t idx = (r.wpos & ~31u) + r.lane;
+    r.chunk = idx < r.nwords ? __ldg(r.base + idx) : 0u;
+}
+
+__device__ __forceinline__ void br_init(BitReader &r, const uint8_t *p, const uint8_t *end, uint32_t lane)
+{
+    const uint32_t mis = (uint32_t)((uintptr_t)p & 3u);
+    r.base = (const uint32_t *)(p - mis);
+    r.nwords = (uint32_t)(((end - (p - mis)) + 3) >> 2);
+    r.lane = lane;
+    r.wpos = 0;
+    br_load_chunk(r);
+    const uint32_t w0 = __shfl_sync(0xffffffffu, r.chunk, 0);
+    r.wpos = 1;
+    r.bb = (uint64_t)(w0 >> (8 * mis));
+    r.bc = 32 - 8 * mis;
+}
+
+/* make sure at least 33 bits are buffered */
+__device__ __forceinline__ void br_refill(BitReader &r)
+{
+    if (r.bc <= 32) {
+        if ((r.wpos & 31u) == 0) br_load_chunk(r);
+        const uint32_t w = __shfl_sync(0xffffffffu, r.chunk, r.wpos & 31u);
+        r.wpos++;
+        r.bb |= (uint64_t)w << r.bc;
+        r.bc += 32;
+    }
+}
+__device__ __forceinline__ uint32_t br_peek(const BitReader &r, uint32_t n) { return (uint32_t)r.bb & ((1u << n) - 1u); }
+__device__ __forceinline__ void br_drop(BitReader &r, uint32_t n) { r.bb >>= n; r.bc -= n; }
+__device__ __forceinline__ uint32_t br_take(BitReader &r, uint32_t n)
+{
+    uint32_t v = br_peek(r, n);
+    br_drop(r, n);
+    return v;
+}
+/* bytes consumed so far, counting whole buffered bytes as unconsumed */
+__device__ __forceinline__ bool br_overrun(const BitReader &r) { return r.wpos > r.nwords + 2; }
+
+__device__ __forceinline__ uint32_t litlen_entry(uint32_t sym, uint32_t nb)
+{
+    if (sym < 256) return ENT(nb, 0, K_LIT, 0, sym);
+    if (sym == 256) return ENT(nb, 0, K_EOB, 0, 0);
+    if (sym > 285) return 0;
+    const uint32_t s = sym - 257;
+    uint32_t xb = bg_len_slot_extra_bits(s);
+    uint32_t base = s < 8 ? 3 + s : s == 28 ? 258 : 3 + ((4 + (s & 3)) << xb);
+    return ENT(nb, xb, K_BASE, 0, base);
+}
+__device__ __forceinline__ uint32_t offset_entry(uint32_t sym, uint32_t nb)
+{
+    if (sym > 29) return 0;
+    uint32_t xb = bg_off_slot_extra_bits(sym);
+    uint32_t base = sym < 4 ? 1 + sym : 1 + ((2 + (sym & 1)) << xb);
+    return ENT(nb, xb, K_BASE, 0, base);
+}
+
+/*
+ * Build a root+sub-table decoder for the canonical code given by lens[0..nsym) (warp-cooperative).
+ * kind: 0 litlen, 1 offset, 2 precode.  Returns false for an over-subscribed code or table overflow.
+ * Incomplete codes are accepted; their unused codewords decode as "invalid".
+ */
+__device__ bool build_table(const uint8_t *lens, uint32_t nsym, uint32_t root, uint32_t *tab, uint32_t cap, int kind,
+                            uint32_t *offs, uint32_t lane)
+{
+    /* 1. per-length counts: lane l counts codewords of length l */
+    uint32_t cnt = 0;
+    if (lane >= 1 && lane <= 15)
+        for (uint32_t s = 0; s < nsym; s++) cnt += (lens[s] == lane);
+    /* 2. first code per length, Kraft check, longest length (uniform, via shuffles) */
+    uint32_t code = 0, maxlen = 0, prevcnt = 0;
+    int left = 1;
+    bool bad = false;
+    uint32_t myfirst = 0;
+    for (uint32_t l = 1; l <= 15; l++) {
+        const uint32_t cl = __shfl_sync(0xffffffffu, cnt, l);
+        code = (code + prevcnt) << 1;
+        if (lane == l) myfirst = code;
+        prevcnt = cl;
+        left = (left << 1) - (int)cl;
+        if (left < 0) bad = true;
+        if (cl) maxlen = l;
+    }
+    if (bad) return false;
+    if (lane >= 1 && lane <= 15) offs[lane] = myfirst;
+    for (uint32_t i = lane; i < cap; i += 32) tab[i] = 0;
+    __syncwarp();
+    if (maxlen == 0) return true;   /* no codewords at all: every lookup is invalid */
+
+    /* 3. pass 1: short codes fill the root; long codes leave the longest length seen under their root prefix */
+    for (uint32_t b0 = 0; b0 < nsym; b0 += 32) {
+        const uint32_t sym = b0 + lane;
+        const uint32_t L = sym < nsym ? lens[sym] : 0u;
+        const unsigned grp = __match_any_sync(0xffffffffu, L);
+        const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+        const uint32_t first = offs[L & 15u];
+        __syncwarp();
+        if (L && rank == 0) offs[L] = first + __popc(grp);
+        __syncwarp();
+        if (L) {
+            const uint32_t rev = __brev(first + rank) >> (32 - L);
+            if (L <= root) {
+                const uint32_t e = kind == 0 ? litlen_entry(sym, L) : kind == 1 ? offset_entry(sym, L) : ENT(L, 0, K_LIT, 0, sym);
+                for (uint32_t i = rev; i < (1u << root); i += (1u << L)) tab[i] = e;
+            } else {
+                atomicMax(&tab[rev & ((1u << root) - 1u)], L);
+            }
+        }
+    }
+    __syncwarp();
+    if (maxlen <= root) return true;
+
+    /* 4. allocate sub-tables in root-index order (warp scan over the markers) */
+    uint32_t next = 1u << root;
+    for (uint32_t b0 = 0; b0 < (1u << root); b0 += 32) {
+        const uint32_t v = tab[b0 + lane];
+        const bool marker = v > root && v <= 15;   /* valid entries are >= 256 */
+        const uint32_t sz = marker ? 1u << (v - root) : 0u;
+        uint32_t inc = sz;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        if (marker) tab[b0 + lane] = ENT(root, 0, K_SUB, v - root, next + inc - sz);
+        next += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (next > cap) return false;
+    __syncwarp();
+    /* restore the canonical first codes consumed in pass 1 */
+    if (lane >= 1 && lane <= 15) offs[lane] = myfirst;
+    __syncwarp();
+
+    /* 5. pass 2: long codes fill their sub-tables */
+    for (uint32_t b0 = 0; b0 < nsym; b0 += 32) {
+        const uint32_t sym = b0 + lane;
+        const uint32_t L = sym < nsym ? lens[sym] : 0u;
+        const unsigned grp = __match_any_sync(0xffffffffu, L);
+        const uint32_t rank = __popc(grp & ((1u << lane) - 1u));
+        const uint32_t first = offs[L & 15u];
+        __syncwarp();
+        if (L && rank == 0) offs[L] = first + __popc(grp);
+        __syncwarp();
+        if (L > root) {
+            const uint32_t rev = __brev(first + rank) >> (32 - L);
+            const uint32_t pe = tab[rev & ((1u << root) - 1u)];
+            const uint32_t sb = (pe >> 11) & 31u, start = pe >> 16;
+            const uint32_t e = kind == 0 ? litlen_entry(sym, L - root) : offset_entry(sym, L - root);
+            for (uint32_t i = rev >> root; i < (1u << sb); i += (1u << (L - root))) tab[start + i] = e;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+__device__ __forceinline__ uint32_t lookup(const uint32_t *tab, uint32_t root, BitReader &r)
+{
+    uint32_t e = tab[br_peek(r, root)];
+    if (((e >> 8) & 7u) == K_SUB) {
+        br_drop(r, root);
+        e = tab[(e >> 16) + br_peek(r, (e >> 11) & 31u)];
+    }
+    br_drop(r, e & 15u);
+    return e;
+}
+
+__global__ void __launch_bounds__(32 * INF_WARPS_PER_CTA)
+bgzf_inflate_kernel(BgzfInflateArgs a)
+{
+    __shared__ InfSmem sm;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = blockIdx.x;
+    if (m >= a.nblocks) return;
+
+    const uint8_t *mem = a.in + a.in_off[m];
+    uint32_t err = INF_OK;
+    /* header: 1f 8b 08 04 .... XLEN=6 'B' 'C' 02 00 BSIZE */
+    const bool hdr_ok = mem[0] == 0x1f && mem[1] == 0x8b && mem[2] == 8 && (mem[3] & 4) && mem[10] == 6 && mem[11] == 0 &&
+                        mem[12] == 'B' && mem[13] == 'C' && mem[14] == 2 && mem[15] == 0;
+    if (!hdr_ok) {
+        if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
+        return;
+    }
+    const uint32_t msize = ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
+    const uint8_t *trailer = mem + msize - 8;
+    const uint32_t isize = (uint32_t)trailer[4] | ((uint32_t)trailer[5] << 8) | ((uint32_t)trailer[6] << 16) | ((uint32_t)trailer[7] << 24);
+    uint8_t *out = a.out + a.out_off[m];
+    if (msize < 28 || isize > 65536u) {
+        if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
+        return;
+    }
+
+    BitReader r;
+    br_init(r, mem + 18, trailer, lane);
+    uint32_t pos = 0;
+    bool last = false;
+    while (!last && err == INF_OK) {
+        br_refill(r);
+        last = br_take(r, 1);
+        const uint32_t btype = br_take(r, 2);
+        if (btype == 0) {
+            /* stored: drop to a byte boundary, LEN, NLEN, raw bytes */
+            br_drop(r, r.bc & 7u);
+            br_refill(r);
+            const uint32_t len = br_take(r, 16);
+            br_refill(r);
+            const uint32_t nlen = br_take(r, 16);
+            if ((len ^ nlen) != 0xffffu) { err = INF_E_STORED; break; }
+            if (pos + len > isize) { err = INF_E_OVERRUN; break; }
+            /* the raw bytes start (bc/8) bytes before the next unread word */
+            const uint8_t *raw = (const uint8_t *)(r.base + r.wpos) - (r.bc >> 3);
+            if (raw + len > trailer) { err = INF_E_OVERRUN; break; }
+            for (uint32_t i = lane; i < len; i += 32) out[pos + i] = raw[i];
+            pos += len;
+            __syncwarp();
+            if (!last) br_init(r, raw + len, trailer, lane);
+            continue;
+        }
+        if (btype == 3) { err = INF_E_BTYPE; break; }
+        if (btype == 1) {
+            for (uint32_t i = lane; i < 288; i += 32) sm.lens[i] = (uint8_t)bg_static_llen(i);
+            sm.lens[288 + lane] = 5;
+            __syncwarp();
+            if (!build_table(sm.lens, 288, INF_LROOT, sm.ltab, INF_LTAB, 0, sm.offs, lane) ||
+                !build_table(sm.lens + 288, 32, INF_DROOT, sm.dtab, INF_DTAB, 1, sm.offs, lane)) { err = INF_E_CODE; break; }
+        } else {
+            br_refill(r);
+            const uint32_t nl = br_take(r, 5) + 257, nd = br_take(r, 5) + 1, np = br_take(r, 4) + 4;
+            if (nl > 286 || nd > 30) { err = INF_E_CODE; break; }
+            if (lane < 19) sm.lens[lane] = 0;
+            __syncwarp();
+            for (uint32_t i = 0; i < np; i++) {
+                br_refill(r);
+                const uint32_t v = br_take(r, 3);
+                if (lane == 0) sm.lens[bg_precode_order(i)] = (uint8_t)v;
+            }
+            __syncwarp();
+            if (!build_table(sm.lens, 19, 7, sm.ptab, INF_PTAB, 2, sm.offs, lane)) { err = INF_E_CODE; break; }
+            /* code lengths for litlen + offset, run-length coded */
+            uint32_t i = 0, prevlen = 0;
+            const uint32_t total = nl + nd;
+            while (i < total) {
+                br_refill(r);
+                const uint32_t e = sm.ptab[br_peek(r, 7)];
+                if (e == 0) { err = INF_E_SYMBOL; break; }
+                br_drop(r, e & 15u);
+                const uint32_t sym = e >> 16;
+                uint32_t rep, val;
+                if (sym < 16) { rep = 1; val = sym; prevlen = sym; }
+                else if (sym == 16) { if (i == 0) { err = INF_E_CODE; break; } rep = 3 + br_take(r, 2); val = prevlen; }
+                else if (sym == 17) { rep = 3 + br_take(r, 3); val = 0; prevlen = 0; }
+                else { rep = 11 + br_take(r, 7); val = 0; prevlen = 0; }
+                if (i + rep > total) { err = INF_E_CODE; break; }
+                for (uint32_t k = lane; k < rep; k += 32) sm.lens[i + k] = (uint8_t)val;
+                i += rep;
+            }
+            if (err) break;
+            __syncwarp();
+            /* the offset lengths follow the litlen lengths; move them to a 16-byte-friendly spot for the builder */
+            if (!build_table(sm.lens, nl, INF_LROOT, sm.ltab, INF_LTAB, 0, sm.offs, lane) ||
+                !build_table(sm.lens + nl, nd, INF_DROOT, sm.dtab, INF_DTAB, 1, sm.offs, lane)) { err = INF_E_CODE; break; }
+        }
+        /* ---- the decode loop ---- */
+        for (;;) {
+            br_refill(r);
+            const uint32_t e = lookup(sm.ltab, INF_LROOT, r);
+            const uint32_t kind = (e >> 8) & 7u;
+            if (kind == K_LIT) {
+                if (pos >= isize) { err = INF_E_OVERRUN; break; }
+                if (lane == 0) out[pos] = (uint8_t)(e >> 16);
+                pos++;
+                continue;
+            }
+            if (kind == K_EOB) break;
+            if (kind != K_BASE) { err = INF_E_SYMBOL; break; }
+            const uint32_t len = (e >> 16) + br_take(r, (e >> 4) & 15u);
+            br_refill(r);
+            const uint32_t d = lookup(sm.dtab, INF_DROOT, r);
+            if (((d >> 8) & 7u) != K_BASE) { err = INF_E_SYMBOL; break; }
+            const uint32_t dist = (d >> 16) + br_take(r, (d >> 4) & 15u);
+            if (dist > pos) { err = INF_E_DIST; break; }
+            if (pos + len > isize) { err = INF_E_OVERRUN; break; }
+            if (br_overrun(r)) { err = INF_E_OVERRUN; break; }
+            __syncwarp();   /* earlier stores of this warp are visible to all its lanes */
+            const uint8_t *srcp = out + pos - dist;
+            if (dist >= len) {
+                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(srcp + k);
+            } else if (dist == 1) {
+                const uint8_t v = __ldcg(srcp);
+                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = v;
+            } else {
+                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(srcp + (k % dist));
+            }
+            pos += len;
+        }
+        if (br_overrun(r) && err == INF_OK) err = INF_E_OVERRUN;
+    }
+    if (err == INF_OK && pos != isize) err = INF_E_SHORT;
+    if (lane == 0) {
+        a.status[m] = err;
+        if (err) atomicOr(a.err_flag, 1u);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* member index of a device-resident stream                                                         */
+
+#define IDX_TILE 32768u
+#define IDX_THREADS 256u
+#define IDX_PER_THREAD (IDX_TILE / IDX_THREADS)
+
+__device__ __forceinline__ bool is_member_start(const uint8_t *p, uint64_t i, uint64_t n)
+{
+    if (i + 28 > n) return false;
+    const uint8_t *q = p + i;
+    return q[0] == 0x1f && q[1] == 0x8b && q[2] == 0x08 && q[3] == 0x04 && q[10] == 0x06 && q[11] == 0 && q[12] == 'B' &&
+           q[13] == 'C' && q[14] == 2 && q[15] == 0;
+}
+
+/* 128-bit candidate mask for the 128 positions [base, base+128) owned by one thread */
+__device__ __forceinline__ void scan_positions(const uint8_t *in, uint64_t n, uint64_t base, bool vec_ok, uint32_t mask[4])
+{
+    mask[0] = mask[1] = mask[2] = mask[3] = 0;
+    for (uint32_t k = 0; k < IDX_PER_THREAD / 16; k++) {
+        const uint64_t off = base + 16u * k;
+        if (off >= n) break;
+        uint32_t hit = 0;   /* bit j: byte j of this 16-byte group is 0x1f */
+        if (vec_ok && off + 16 <= n) {
+            const uint4 v = __ldg((const uint4 *)(in + off));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t x = w[q] ^ 0x1f1f1f1fu;
+                const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;   /* may over-report; verified below */
+                if (z) hit |= 0xfu << (4 * q);
+            }
+        } else {
+            hit = 0xffffu;
+        }
+        while (hit) {
+            const uint32_t j = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const uint64_t i = off + j;
+            if (i < n && in[i] == 0x1f && is_member_start(in, i, n)) {
+                const uint32_t bit = 16u * k + j;
+                mask[bit >> 5] |= 1u << (bit & 31u);
+            }
+        }
+    }
+}
+
+/* pass 0 (write == 0): candidates per tile.  pass 1: ordered list of candidate offsets. */
+__global__ void __launch_bounds__(IDX_THREADS)
+bgzf_index_scan_kernel(const uint8_t *in, uint64_t n, uint32_t *tile_count, const uint64_t *tile_off, uint64_t *in_off,
+                       uint32_t max_blocks, int write)
+{
+    __shared__ uint32_t wsum[IDX_THREADS / 32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * IDX_TILE + (uint64_t)t * IDX_PER_THREAD;
+    uint32_t mask[4];
+    scan_positions(in, n, base, ((uintptr_t)in & 15u) == 0, mask);
+    const uint32_t cnt = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+    uint32_t inc = cnt;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += y;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < IDX_THREADS / 32; w++) {
+        if (w < warp) before += wsum[w];
+        total += wsum[w];
+    }
+    if (!write) {
+        if (t == 0) tile_count[blockIdx.x] = total;
+        return;
+    }
+    uint64_t slot = tile_off[blockIdx.x] + before + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t mm = mask[q];
+        while (mm) {
+            const uint32_t j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            if (slot < max_blocks) in_off[slot] = base + 32u * q + j;
+            slot++;
+        }
+    }
+}
+
+/* validates the BSIZE chain and collects ISIZE per member */
+__global__ void bgzf_index_finish_kernel(const uint8_t *in, uint64_t n, const uint64_t *in_off, const uint64_t *count,
+                                         uint32_t max_blocks, uint32_t *isize, uint32_t *status)
+{
+    const uint64_t nm = *count;
+    if (nm > max_blocks || nm == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, nm == 0 ? 1u : 2u);
+        return;
+    }
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nm; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = in_off[k];
+        const uint64_t next = o + ((uint32_t)in[o + 16] | ((uint32_t)in[o + 17] << 8)) + 1u;
+        const uint64_t expect = k + 1 < nm ? in_off[k + 1] : n;
+        if ((k == 0 && o != 0) || next != expect || next > n) {
+            atomicOr(status, 1u);
+            isize[k] = 0;
+            continue;
+        }
+        const uint8_t *tr = in + next - 4;
+        isize[k] = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        if (isize[k] > 65536u) atomicOr(status, 1u);
+    }
+}
+
+extern "C" cudaError_t bgzf_launch_inflate(const BgzfInflateArgs *a, cudaStream_t stream)
+{
+    if (a->nblocks == 0) return cudaSuccess;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    bgzf_inflate_kernel<<<a->nblocks, 32 * INF_WARPS_PER_CTA, 0, stream>>>(*a);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, uint64_t *in_off, uint64_t *out_off, uint32_t max_blocks,
+                                         uint32_t *tile_count, uint64_t *tile_off, uint32_t *isize, uint64_t *nmembers,
+                                         uint64_t *out_bytes, uint32_t *status, cudaStream_t stream)
+{
+    const uint32_t tiles = (uint32_t)((in_bytes + IDX_TILE - 1) / IDX_TILE);
+    if (tiles == 0) return cudaErrorInvalidValue;
+    bgzf_index_scan_kernel<<<tiles, IDX_THREADS, 0, stream>>>(in, in_bytes, tile_count, nullptr, nullptr, max_blocks, 0);
+    bgzf_launch_scan(tile_count, tile_off, tiles, nullptr, nullptr, nmembers, stream);
+    bgzf_index_scan_kernel<<<tiles, IDX_THREADS, 0, stream>>>(in, in_bytes, tile_count, tile_off, in_off, max_blocks, 1);
+    bgzf_index_finish_kernel<<<64, 256, 0, stream>>>(in, in_bytes, in_off, nmembers, max_blocks, isize, status);
+    /* out_off = exclusive scan of ISIZE over the members found (count read on the device) */
+    bgzf_launch_scan(isize, out_off, max_blocks, nmembers, nullptr, out_bytes, stream);
+    return cudaGetLastError();
+}
+
+extern "C" size_t bgzf_index_tiles(uint64_t in_bytes) { return (size_t)((in_bytes + IDX_TILE - 1) / IDX_TILE); }

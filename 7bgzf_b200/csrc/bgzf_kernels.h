@@ -1,0 +1,59 @@
+/* bgzf_kernels.h — internal launch interface between the C-ABI shim (b200bgzf_api.cu) and the kernels. */
+#ifndef BGZF_KERNELS_H
+#define BGZF_KERNELS_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bgzf_block.h"
+
+#define BGZF_SCRATCH_WORDS (65536u + 32u)   /* per-CTA match scratch (u32 per position) */
+#define BGZF_PROF_SLOTS 16
+
+struct BgzfCompressArgs {
+    const uint8_t *in;         /* device: payload bytes */
+    const uint64_t *in_off;    /* device: per-block byte offset into `in`, or NULL for fixed-size blocks */
+    const uint32_t *in_len;    /* device: per-block length (with in_off) */
+    uint64_t in_bytes;         /* fixed-size mode: total bytes */
+    uint32_t block_size;       /* fixed-size mode: payload bytes per block (<= 65536) */
+    uint32_t nblocks;
+    BgParams prm;              /* search effort, from bg_level_params(level) on the host */
+    uint8_t *slots;            /* device: nblocks * 65536 (+16) bytes */
+    uint32_t *out_len;         /* device: member size per block (0 on failure) */
+    uint32_t *status;          /* device: 0 ok, 1 member would exceed 65536 bytes */
+    uint32_t *err_flag;        /* device: OR of all per-block status words */
+    uint32_t *scratch;         /* device: grid * BGZF_SCRATCH_WORDS */
+    const uint32_t *crctab;    /* device u32[256] */
+    const uint32_t *crcpow;    /* device u32[1024] */
+    unsigned long long *prof;  /* device u64[BGZF_PROF_SLOTS] cycle counters, or NULL */
+};
+
+struct BgzfInflateArgs {
+    const uint8_t *in;         /* device: BGZF stream */
+    const uint64_t *in_off;    /* device: byte offset of each member */
+    const uint64_t *out_off;   /* device: byte offset of each member's payload in `out` */
+    uint32_t nblocks;
+    uint8_t *out;              /* device */
+    uint32_t *status;          /* device: 0 ok, else error code per member */
+    uint32_t *err_flag;        /* device: set to non-zero when any member fails */
+    int verify_crc;
+    const uint32_t *crctab;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+size_t bgzf_compress_smem_bytes(void);
+cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid, cudaStream_t stream);
+cudaError_t bgzf_launch_scan(const uint32_t *len, uint64_t *off, uint32_t nmax, const uint64_t *count_dev,
+                             const uint64_t *base_dev, uint64_t *total_out, cudaStream_t stream);
+cudaError_t bgzf_launch_compact(const uint8_t *slots, const uint32_t *len, uint64_t *off, uint32_t nblocks, uint8_t *out,
+                                uint64_t *total, int append_eof, cudaStream_t stream);
+size_t bgzf_index_tiles(uint64_t in_bytes);
+cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, uint64_t *in_off, uint64_t *out_off, uint32_t max_blocks,
+                              uint32_t *tile_count, uint64_t *tile_off, uint32_t *isize, uint64_t *nmembers,
+                              uint64_t *out_bytes, uint32_t *status, cudaStream_t stream);
+cudaError_t bgzf_launch_inflate(const BgzfInflateArgs *a, cudaStream_t stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

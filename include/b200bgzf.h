@@ -1,0 +1,103 @@
+/*
+ * b200bgzf.h — C ABI of the B200-native BGZF codec (lib7bgzf_b200.so / 7bgzf.so).
+ *
+ * This is the drop-in boundary for the one hot path of cielavenir/7bgzf: per-64 KiB-block BGZF compress
+ * (libdeflate level class 1..12) and BGZF inflate.  Plain pointers and sizes only; every entry point states
+ * the reference interface it stands in for (paths relative to the reference tree).
+ *
+ * There is NO CPU fallback: every compress/inflate call runs the sm_100a kernels and fails with
+ * B200BGZF_E_CUDA when no usable GPU (or the CUDA runtime) is present.
+ */
+#ifndef B200BGZF_H
+#define B200BGZF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BGZF_BLOCK_SIZE 0xff00u      /* htslib BGZF_BLOCK_SIZE; applet/7bgzf.c:146-147 */
+#define B200BGZF_MAX_BLOCK_SIZE 0x10000u /* htslib BGZF_MAX_BLOCK_SIZE = largest member and largest payload */
+#define B200BGZF_EOF_BYTES 28u           /* bgzf_compress.c:43-49 */
+
+/* return codes.  0 and 1 and -1 keep the meaning they have in bgzf_compress.c:39-198 */
+#define B200BGZF_OK 0
+#define B200BGZF_E_NOFIT 1      /* a member would not fit its capacity (reference: "libdeflate_deflate 1", returns 1) */
+#define B200BGZF_E_ARG (-1)     /* bad argument / capacity below the fixed minimum (reference returns -1) */
+#define B200BGZF_E_CUDA (-2)    /* no device, out of device memory, launch failure */
+#define B200BGZF_E_FORMAT (-3)  /* input is not BGZF / corrupt DEFLATE data */
+#define B200BGZF_E_NOSPACE (-4) /* output buffer too small */
+#define B200BGZF_E_CRC (-5)     /* CRC32 or ISIZE mismatch (only with B200BGZF_VERIFY) */
+
+#define B200BGZF_APPEND_EOF 1u  /* compress: finish the stream with the 28-byte EOF member (applet/7bgzf.c:283-289) */
+#define B200BGZF_VERIFY 2u      /* inflate: check CRC32 and ISIZE of every member (the reference does not: 7bgzf.c:350-354) */
+
+typedef struct b200bgzf_ctx b200bgzf_ctx;
+
+/* One context = one GPU, its streams, pinned staging and device workspaces.  device < 0: current device.
+ * Replaces the per-call libdeflate_alloc_compressor/free of lib/zlibutil.c:186-188 with process-lifetime pools. */
+int b200bgzf_create(b200bgzf_ctx **ctx, int device);
+void b200bgzf_destroy(b200bgzf_ctx *ctx);
+const char *b200bgzf_strerror(int code);
+/* last CUDA error text seen by this context (empty string if none) */
+const char *b200bgzf_last_error(const b200bgzf_ctx *ctx);
+
+/* Worst-case size of the BGZF stream for in_bytes of payload cut into block_size blocks (+EOF). */
+size_t b200bgzf_compress_bound(size_t in_bytes, uint32_t block_size);
+
+/*
+ * Compress a contiguous buffer into a contiguous BGZF stream; block b carries payload bytes
+ * [b*block_size, min((b+1)*block_size, in_bytes)).  This is the applet's _compress() loop
+ * (applet/7bgzf.c:133-293: read block, libdeflate_deflate, frame, write in order) as one batched call.
+ *   *_device: d_in/d_out are device pointers (d_in 16-byte aligned for the TMA path), `stream` is a
+ *             cudaStream_t passed as void* (NULL: the context's stream).  Synchronises before returning.
+ *   *_host:   host pointers (pinned memory copies fastest); pipelined H2D / kernels / D2H.
+ * level: 1..12 (libdeflate classes, lib/libdeflate/deflate_compress.c:3921-4007).
+ */
+int b200bgzf_compress_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes, uint32_t block_size, int level,
+                             void *d_out, size_t out_cap, size_t *out_bytes, unsigned flags, void *stream);
+int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                           size_t out_cap, size_t *out_bytes, unsigned flags);
+
+/*
+ * Compress nblocks independent payloads (src[i], slen[i] <= 65536) into dst[i]; dlen[i] holds the capacity on
+ * entry and the member size on return; status[i] gets the per-block code of bgzf_compress().  This is the
+ * batch form of bgzf_compress.c:39-198 that the LD_PRELOAD hook funnels concurrent callers into.
+ */
+int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, const uint32_t *slen, void *const *dst,
+                                  size_t *dlen, int *status, uint32_t nblocks, int level);
+
+/*
+ * Inflate a BGZF stream (any sequence of BGZF members, EOF markers included) — the applet's _decompress()
+ * (applet/7bgzf.c:295-365) with zlibutil_auto_inflate (lib/zlibutil.c:82-93) as the per-member decoder.
+ * The *_size helper walks the member headers on the host (7bgzf.c:81-131) and returns the member count and the
+ * total ISIZE so the caller can size the output.
+ */
+int b200bgzf_inflate_size_host(const void *in, size_t in_bytes, size_t *out_bytes, size_t *nmembers);
+int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes, void *d_out, size_t out_cap,
+                            size_t *out_bytes, unsigned flags, void *stream);
+int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
+                          unsigned flags);
+
+/* Per-phase cycle counters of the compress kernel (development aid; n <= 16). Resets them when reset != 0. */
+int b200bgzf_profile(b200bgzf_ctx *ctx, int enable, unsigned long long *cycles, int n, int reset);
+/* number of kernel launches issued by this context so far */
+unsigned long long b200bgzf_launch_count(const b200bgzf_ctx *ctx);
+
+/*
+ * The htslib hook (exported from 7bgzf.so only).  Same signature and return conventions as the reference's
+ * bgzf_compress.c:39: 0 ok; -1 if *dlen < 28 for slen == 0 or *dlen < 26; 1 (+ "libdeflate_deflate 1" on
+ * stderr) when the member does not fit; `level` is ignored, BGZF_METHOD=<name><digits> selects the level.
+ */
+int bgzf_compress(void *dst, size_t *dlen, const void *src, size_t slen, int level);
+
+/* BGZF_METHOD parser used by the hook (bgzf_compress.c:53-113).  Returns 0 and the level (1..12) to use,
+ * or -1 if the digits are out of range.  Every method name maps onto this codec; unset/zlib -> 6. */
+int b200bgzf_parse_method(const char *spec, int *level, char *method_name, size_t method_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

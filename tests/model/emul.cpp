@@ -1,0 +1,138 @@
+// CPU thread-emulator for the block encoder in 7bgzf_b200/csrc/bgzf_block.h.
+// TEST/DEVELOPMENT INFRASTRUCTURE: it runs the very phase functions the CUDA kernel runs, one "thread" at a
+// time, so the algorithm can be checked (and race-checked, by permuting the thread order) without a GPU.
+// The product never links this.
+//
+//   emul compress <level> <in> <out.bgz> [order]   order: 0 forward, 1 reverse, 2 shuffled
+//   library: int bgemul_compress_block(const uint8_t* src, uint32_t n, int level, int order, uint8_t* dst /*65536*/, uint32_t* dlen)
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+#include "../../7bgzf_b200/csrc/bgzf_block.h"
+#include "../../7bgzf_b200/csrc/bgzf_tables.h"
+
+namespace {
+struct Emu {
+    std::vector<uint32_t> dataw, regA, regB, R, out, crcpow;
+    uint8_t litflag[256];
+    uint32_t crctab[256];
+    uint32_t scal[BG_S_COUNT];
+    Emu() : dataw(BG_DATA_BYTES / 4), regA(131072 / 4), regB(32768 / 4), R(BG_MAX_BLOCK + 8), out(BG_SLOT_BYTES / 4), crcpow(BG_THREADS)
+    {
+        bg_make_crc_table(crctab);
+        bg_make_crc_pow(crcpow.data(), BG_THREADS);
+    }
+};
+
+typedef void (*phase_fn)(const BgCtx &, uint32_t, uint32_t);
+
+void run(phase_fn f, const BgCtx &c, int order, uint32_t seed)
+{
+    const uint32_t T = BG_THREADS;
+    std::vector<uint32_t> idx(T);
+    std::iota(idx.begin(), idx.end(), 0u);
+    if (order == 1) std::reverse(idx.begin(), idx.end());
+    if (order == 2) {
+        uint32_t s = seed * 2654435761u + 12345u;
+        for (uint32_t i = T - 1; i > 0; i--) { s = s * 1664525u + 1013904223u; std::swap(idx[i], idx[(s >> 8) % (i + 1)]); }
+    }
+    for (uint32_t t : idx) f(c, t, T);
+}
+}  // namespace
+
+extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, int order, uint8_t *dst, uint32_t *dlen)
+{
+    static Emu *e = new Emu();
+    if (n > BG_MAX_BLOCK) return -1;
+    // poison what the kernel would find uninitialised
+    std::fill(e->regA.begin(), e->regA.end(), 0xA5A5A5A5u);
+    std::fill(e->regB.begin(), e->regB.end(), 0x5A5A5A5Au);
+    std::fill(e->R.begin(), e->R.end(), 0xDEADBEEFu);
+    std::fill(e->out.begin(), e->out.end(), 0xFFFFFFFFu);
+    std::fill(e->dataw.begin(), e->dataw.end(), 0xEEEEEEEEu);
+    memcpy(e->dataw.data(), src, n);
+    BgCtx c;
+    c.dataw = e->dataw.data();
+    c.prev = (uint16_t *)e->regA.data();
+    c.stepcode = (uint8_t *)e->regA.data();
+    c.jump8 = c.stepcode + 65536;
+    c.offarr = (uint16_t *)c.jump8;
+    c.head = (uint16_t *)e->regB.data();
+    c.regb = (uint8_t *)e->regB.data();
+    c.litflag = e->litflag;
+    c.crctab = e->crctab;
+    c.scal = e->scal;
+    c.R = e->R.data();
+    c.out = e->out.data();
+    c.crcpow = e->crcpow.data();
+    c.n = n;
+    c.prm = bg_level_params(level);
+    uint32_t k = 0;
+    run(bg_phase_init, c, order, k++);
+    run(bg_phase_scan, c, order, k++);
+    run(bg_phase_count, c, order, k++);
+    run(bg_phase_settle, c, order, k++);
+    run(bg_phase_hash, c, order, k++);
+    bg_build_sequential(c);
+    run(bg_phase_search, c, order, k++);
+    run(bg_phase_accept, c, order, k++);
+    run(bg_phase_jump, c, order, k++);
+    run(bg_phase_walk, c, order, k++);
+    if (c.scal[BG_S_WALKEND] != n) { fprintf(stderr, "emul: walk ended at %u, n=%u\n", c.scal[BG_S_WALKEND], n); return -2; }
+    run(bg_phase_clear_freq, c, order, k++);
+    run(bg_phase_tally, c, order, k++);
+    run(bg_phase_lkeys, c, order, k++);
+    {   // twin of the kernel's bitonic sort
+        uint32_t *keys = (uint32_t *)(c.regb + BG_B_KEYS);
+        std::sort(keys, keys + 512);
+    }
+    run(bg_phase_huff, c, order, k++);
+    run(bg_phase_decide, c, order, k++);
+    run(bg_phase_sizes, c, order, k++);
+    {   // twin of the kernel's block-wide exclusive scan
+        uint32_t *cb = (uint32_t *)(c.regb + BG_B_CBITS), acc = 0;
+        for (uint32_t i = 0; i < BG_MAX_CHUNKS; i++) { uint32_t v = cb[i]; cb[i] = acc; acc += v; }
+        if (c.scal[BG_S_BTYPE] && acc + ((uint8_t *)(c.regb + BG_B_LLEN))[256] != c.scal[BG_S_TOKBITS]) {
+            fprintf(stderr, "emul: token bits %u + eob != %u\n", acc, c.scal[BG_S_TOKBITS]);
+            return -3;
+        }
+    }
+    if (c.scal[BG_S_STATUS]) return 1;
+    run(bg_phase_zero_out, c, order, k++);
+    run(bg_phase_emit, c, order, k++);
+    uint32_t total = 18 + c.scal[BG_S_PAYLOAD] + 8;
+    memcpy(dst, e->out.data(), total);
+    *dlen = total;
+    return 0;
+}
+
+#ifdef EMUL_MAIN
+int main(int argc, char **argv)
+{
+    if (argc < 5) { fprintf(stderr, "usage: emul compress <level> <in> <out> [order] [blocksize]\n"); return 2; }
+    int level = atoi(argv[2]), order = argc > 5 ? atoi(argv[5]) : 0;
+    uint32_t bs = argc > 6 ? (uint32_t)strtoul(argv[6], 0, 0) : 0xff00u;
+    FILE *f = fopen(argv[3], "rb");
+    if (!f) { perror(argv[3]); return 1; }
+    std::vector<uint8_t> in;
+    { uint8_t buf[65536]; size_t r; while ((r = fread(buf, 1, sizeof buf, f)) > 0) in.insert(in.end(), buf, buf + r); }
+    fclose(f);
+    FILE *o = fopen(argv[4], "wb");
+    uint8_t dst[65536];
+    size_t total = 0;
+    for (size_t off = 0; off < in.size(); off += bs) {
+        uint32_t n = (uint32_t)std::min<size_t>(bs, in.size() - off), dl = 0;
+        int r = bgemul_compress_block(in.data() + off, n, level, order, dst, &dl);
+        if (r) { fprintf(stderr, "block at %zu: error %d\n", off, r); return 1; }
+        fwrite(dst, 1, dl, o);
+        total += dl;
+    }
+    { uint32_t dl = 0; bgemul_compress_block(in.data(), 0, level, order, dst, &dl); fwrite(dst, 1, dl, o); total += dl; }
+    fclose(o);
+    fprintf(stderr, "in=%zu out=%zu ratio=%.4f\n", in.size(), total, in.size() ? (double)total / in.size() : 0.0);
+    return 0;
+}
+#endif
