@@ -65,6 +65,8 @@ struct BitReader {
     uint64_t bb;            /* bit buffer */
     uint32_t bc;            /* valid bits */
     uint32_t lane;
+    uint32_t skip;          /* bits of the first word that precede the start */
+    uint32_t avail;         /* real input bits from the start to the end of the DEFLATE data */
 };
 
 __device__ __forceinline__ void br_load_chunk(BitReader &r)
@@ -79,6 +81,8 @@ __device__ __forceinline__ void br_init(BitReader &r, const uint8_t *p, const ui
     r.base = (const uint32_t *)(p - mis);
     r.nwords = (uint32_t)(((end - (p - mis)) + 3) >> 2);
     r.lane = lane;
+    r.skip = 8 * mis;
+    r.avail = (uint32_t)(end - p) * 8u;
     r.wpos = 0;
     br_load_chunk(r);
     const uint32_t w0 = __shfl_sync(0xffffffffu, r.chunk, 0);
@@ -106,14 +110,15 @@ __device__ __forceinline__ uint32_t br_take(BitReader &r, uint32_t n)
     br_drop(r, n);
     return v;
 }
-/* bytes consumed so far, counting whole buffered bytes as unconsumed */
-__device__ __forceinline__ bool br_overrun(const BitReader &r) { return r.wpos > r.nwords + 2; }
+/* true once more bits were consumed than the member holds (the reference's overread check,
+ * decompress_template.h: "overread_count <= bitsleft>>3") */
+__device__ __forceinline__ bool br_overrun(const BitReader &r) { return r.wpos * 32u - r.skip - r.bc > r.avail; }
 
 __device__ __forceinline__ uint32_t litlen_entry(uint32_t sym, uint32_t nb)
 {
     if (sym < 256) return ENT(nb, 0, K_LIT, 0, sym);
     if (sym == 256) return ENT(nb, 0, K_EOB, 0, 0);
-    if (sym > 285) return 0;
+    if (sym > 285) sym = 285;   /* 286/287 decode as length 258, as in the reference's litlen_decode_results */
     const uint32_t s = sym - 257;
     uint32_t xb = bg_len_slot_extra_bits(s);
     uint32_t base = s < 8 ? 3 + s : s == 28 ? 258 : 3 + ((4 + (s & 3)) << xb);
@@ -121,7 +126,7 @@ __device__ __forceinline__ uint32_t litlen_entry(uint32_t sym, uint32_t nb)
 }
 __device__ __forceinline__ uint32_t offset_entry(uint32_t sym, uint32_t nb)
 {
-    if (sym > 29) return 0;
+    if (sym > 29) sym = 29;     /* 30/31 decode like 29, as in the reference's offset_decode_results */
     uint32_t xb = bg_off_slot_extra_bits(sym);
     uint32_t base = sym < 4 ? 1 + sym : 1 + ((2 + (sym & 1)) << xb);
     return ENT(nb, xb, K_BASE, 0, base);
@@ -130,7 +135,7 @@ __device__ __forceinline__ uint32_t offset_entry(uint32_t sym, uint32_t nb)
 /*
  * Build a root+sub-table decoder for the canonical code given by lens[0..nsym) (warp-cooperative).
  * kind: 0 litlen, 1 offset, 2 precode.  Returns false for an over-subscribed code or table overflow.
- * Incomplete codes are accepted; their unused codewords decode as "invalid".
+ * Incomplete codes follow the reference's rule (only the empty code and a lone 1-bit codeword are valid).
  */
 __device__ bool build_table(const uint8_t *lens, uint32_t nsym, uint32_t root, uint32_t *tab, uint32_t cap, int kind,
                             uint32_t *offs, uint32_t lane)
@@ -154,10 +159,23 @@ __device__ bool build_table(const uint8_t *lens, uint32_t nsym, uint32_t root, u
         if (cl) maxlen = l;
     }
     if (bad) return false;
+    if (left > 0) {
+        /* incomplete code: the reference (deflate_decompress.c:799-853) accepts only the empty code and a lone
+         * 1-bit codeword, and lets both bit values decode to that symbol */
+        const uint32_t c1 = __shfl_sync(0xffffffffu, cnt, 1);
+        uint32_t sym = 0;
+        if (maxlen != 0) {
+            if (maxlen != 1 || c1 != 1) return false;
+            for (uint32_t s = 0; s < nsym; s++) if (lens[s] == 1) sym = s;
+        }
+        const uint32_t e = kind == 0 ? litlen_entry(sym, 1) : kind == 1 ? offset_entry(sym, 1) : ENT(1, 0, K_LIT, 0, sym);
+        for (uint32_t i = lane; i < (1u << root); i += 32) tab[i] = e;
+        __syncwarp();
+        return true;
+    }
     if (lane >= 1 && lane <= 15) offs[lane] = myfirst;
     for (uint32_t i = lane; i < cap; i += 32) tab[i] = 0;
     __syncwarp();
-    if (maxlen == 0) return true;   /* no codewords at all: every lookup is invalid */
 
     /* 3. pass 1: short codes fill the root; long codes leave the longest length seen under their root prefix */
     for (uint32_t b0 = 0; b0 < nsym; b0 += 32) {
@@ -297,7 +315,6 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
         } else {
             br_refill(r);
             const uint32_t nl = br_take(r, 5) + 257, nd = br_take(r, 5) + 1, np = br_take(r, 4) + 4;
-            if (nl > 286 || nd > 30) { err = INF_E_CODE; break; }
             if (lane < 19) sm.lens[lane] = 0;
             __syncwarp();
             for (uint32_t i = 0; i < np; i++) {

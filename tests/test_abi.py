@@ -1,0 +1,100 @@
+"""CPU: the C-ABI boundary — the shared objects load, export exactly what include/b200bgzf.h declares (and
+nothing unprefixed besides bgzf_compress), and fail loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import b200bgzf
+import helpers as H
+
+ROOT = H.ROOT
+HAVE_GPU = os.path.exists("/dev/nvidia0")
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "b200bgzf.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200bgzf_\w+|bgzf_compress)\s*\(", hdr)))
+
+
+def _exported(path):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+
+
+def test_built():
+    for p in (b200bgzf.LIB_PATH, b200bgzf.HOOK_PATH, b200bgzf.APPLET_PATH):
+        assert os.path.exists(p), f"{p} missing: run make"
+
+
+def test_library_exports_match_header():
+    decl = _declared()
+    assert "bgzf_compress" in decl and len(decl) >= 14
+    assert _exported(b200bgzf.HOOK_PATH) == decl                       # 7bgzf.so: the hook + the prefixed API, nothing else
+    assert _exported(b200bgzf.LIB_PATH) == [d for d in decl if d != "bgzf_compress"]
+    lib = b200bgzf.load()
+    for name in b200bgzf.EXPORTS:
+        assert hasattr(lib, name)
+
+
+def test_no_foreign_symbols_interposed():
+    # the reference .so exports 600+ symbols (deflate, inflate, crc32, main, finish ...); ours must not
+    names = _exported(b200bgzf.HOOK_PATH)
+    for bad in ("deflate", "inflate", "crc32", "main", "finish", "libdeflate_deflate_compress"):
+        assert bad not in names
+
+
+def test_parse_method_matches_reference_levels():
+    lib = b200bgzf.load()
+    lvl, olvl = ctypes.c_int(), ctypes.c_int()
+    name = ctypes.create_string_buffer(32)
+    for spec in (None, b"", b"libdeflate", b"LIBDEFLATE12", b"libdeflate1", b"zlib", b"zlib9", b"slz", b"7-zip", b"igzip3", b"bogus7", b"zopfli", b"miniz2"):
+        assert lib.b200bgzf_parse_method(spec, ctypes.byref(lvl), name, 32) == 0
+        H.oracle().oracle_parse_method(spec, ctypes.byref(olvl))
+        assert lvl.value == max(1, olvl.value), spec          # same level the reference's parser yields
+    assert lib.b200bgzf_parse_method(b"libdeflate13", ctypes.byref(lvl), name, 32) == -1   # reference: NULL deref
+    assert lib.b200bgzf_parse_method(b"libdeflate", ctypes.byref(lvl), name, 32) == 0 and name.value == b"libdeflate"
+
+
+def test_bound_and_errors():
+    lib = b200bgzf.load()
+    assert lib.b200bgzf_compress_bound(0, 0xFF00) == 28
+    assert lib.b200bgzf_compress_bound(65280, 0xFF00) >= 65311 + 28
+    assert lib.b200bgzf_compress_bound(10, 0x10001) == 0
+    assert b"fit" in lib.b200bgzf_strerror(1)
+
+
+def test_hook_paths_that_need_no_gpu():
+    hook = ctypes.CDLL(b200bgzf.HOOK_PATH)
+    hook.bgzf_compress.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    dst = ctypes.create_string_buffer(64)
+    n = ctypes.c_size_t(64)
+    assert hook.bgzf_compress(dst, ctypes.byref(n), b"", 0, 6) == 0 and n.value == 28 and dst.raw[:28] == H.EOF_BLOCK
+    n = ctypes.c_size_t(27)
+    assert hook.bgzf_compress(dst, ctypes.byref(n), b"", 0, 6) == -1 and n.value == 27
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="this checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(b200bgzf.B200BgzfError):
+        b200bgzf.Codec()
+    r = subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6"], input=b"hello", capture_output=True)
+    assert r.returncode != 0 and r.stdout == b"" and b"cannot initialise the GPU codec" in r.stderr
+    # the hook must not quietly compress on the CPU either
+    code = ("import ctypes,sys; h=ctypes.CDLL(sys.argv[1]); d=ctypes.create_string_buffer(65536); n=ctypes.c_size_t(65536);"
+            "h.bgzf_compress.argtypes=[ctypes.c_char_p,ctypes.POINTER(ctypes.c_size_t),ctypes.c_char_p,ctypes.c_size_t,ctypes.c_int];"
+            "print(h.bgzf_compress(d,ctypes.byref(n),b'x'*1000,1000,6), n.value)")
+    r = subprocess.run(["python", "-c", code, b200bgzf.HOOK_PATH], capture_output=True, text=True, env=dict(os.environ, BGZF_METHOD="libdeflate6"))
+    assert r.stdout.split() == ["-1", "65536"]
+
+
+def test_applet_cli_contract():
+    r = subprocess.run([b200bgzf.APPLET_PATH], input=b"", capture_output=True)
+    assert r.returncode == 1 and b"Usage" in r.stderr                    # no method, no -d  (7bgzf.c:467-479)
+    r = subprocess.run([b200bgzf.APPLET_PATH, "-l6", "-z"], input=b"", capture_output=True)
+    assert r.returncode == 1                                             # two methods
+    r = subprocess.run([b200bgzf.APPLET_PATH, "-d", "-l6"], input=b"", capture_output=True)
+    assert r.returncode == 1                                             # method together with -d

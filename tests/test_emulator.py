@@ -1,0 +1,92 @@
+"""CPU: the block-encoder algorithm (7bgzf_b200/csrc/bgzf_block.h, the code the CUDA kernel runs) executed by
+the thread-emulator.  Checks what parity means for compress: streams decode through the oracle, the
+reference decoder and zlib; CRC32/ISIZE/BSIZE exact; size within 3 % of the reference at the matching
+level; identical bytes for every thread schedule (race check) and block size."""
+import json
+import os
+import struct
+import zlib
+
+import pytest
+
+import helpers as H
+
+KA = json.load(open(os.path.join(H.GOLDEN, "known_answers.json")))
+needs_ref = pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
+
+EDGE = {
+    "empty": b"", "A": b"A", "AB": b"AB", "rep": b"abcabcabcabcabc", "zeros65280": bytes(65280), "zeros65536": bytes(65536),
+    "noise65280": H.lcg_noise(65280), "acgt": H.acgt(65280), "n31": H.lcg_noise(31), "n32": H.lcg_noise(32),
+    "text": (b"the quick brown fox jumps over the lazy dog. " * 2000)[:65280], "x700": b"x" * 700, "n600": H.lcg_noise(600),
+    "ragged": H.synth("sam", 70000)[:65535], "one_past": H.synth("fastq", 65281),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+@pytest.mark.parametrize("level", [1, 6, 9, 12])
+def test_edge_blocks_decode_and_frame(name, level):
+    payload = EDGE[name]
+    block = 0x10000 if len(payload) > H.BLOCK else H.BLOCK
+    stream = H.emul_stream(payload, level, block)
+    assert stream.endswith(H.EOF_BLOCK)
+    assert H.gunzip(stream) == payload
+    rc, out, nm = H.oracle_decompress(stream)
+    assert rc == 0 and out == payload
+    for off, size, isize, crc in H.members(stream)[:-1]:
+        assert size <= 65536 and isize == len(payload) and crc == zlib.crc32(payload)
+        assert stream[off : off + 16] == bytes.fromhex("1f8b08040000000000ff060042430200")
+
+
+def test_reference_known_sizes_for_degenerate_inputs():
+    # inputs where the encoder has no freedom must give the reference's exact size
+    for name in ("A", "zeros65280", "zeros65536", "noise65280"):
+        payload = EDGE[name]
+        rc, m = H.emul_block(payload, 6)
+        assert rc == 0 and len(m) == KA[f"{name}_L6"]["size"], name
+    rc, m = H.emul_block(EDGE["A"], 6)
+    assert m.hex().startswith(KA["A_L6"]["head"])            # stored passthrough, byte for byte
+    assert abs(len(H.emul_block(EDGE["acgt"], 6)[1]) - KA["acgt65280_L6"]["size"]) <= 4
+    rc, _ = H.emul_block(H.lcg_noise(65536), 6)             # cannot fit 65536 bytes: reference returns 1
+    assert rc == 1 and KA["noise65536_L6"]["rc"] == 1
+
+
+def test_schedule_independence_is_bit_exact():
+    data = H.synth("fastq", 3 * H.BLOCK) + H.lcg_noise(3000) + bytes(5000)
+    a = H.emul_stream(data, 6, order=0)
+    assert a == H.emul_stream(data, 6, order=1) == H.emul_stream(data, 6, order=2)
+
+
+@pytest.mark.parametrize("kind", ["fastq", "sam"])
+@pytest.mark.parametrize("level,ref_level", [(1, 1), (6, 6), (9, 9)])
+def test_size_within_tolerance_of_golden_reference(kind, level, ref_level):
+    """2 blocks against the committed reference sizes (works without oracle/_ref)"""
+    data = H.synth(kind, 2 * H.BLOCK)
+    if f"{kind}_L{ref_level}_sizes" not in KA:
+        pytest.skip("no golden sizes at this level")
+    mine = sum(m[1] for m in H.members(H.emul_stream(data, level, eof=False)))
+    ref = sum(KA[f"{kind}_L{ref_level}_sizes"])
+    assert mine <= 1.03 * ref, (mine, ref)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["fastq", "sam"])
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_size_and_decode_against_compiled_reference(kind, level):
+    data = H.synth(kind, 4 << 20)
+    mine = H.emul_stream(data, level)
+    ref_stream, ref_sizes, _ = H.Ref(level).compress_stream(data)
+    assert len(mine) - 28 <= 1.03 * sum(ref_sizes), (len(mine), sum(ref_sizes))
+    rc, out, _ = H.Ref(level).inflate_stream(mine)        # the reference's own libdeflate decoder
+    assert rc == 0 and out == data
+    # CRC32 / ISIZE equal what the reference writes for the same payloads
+    for (o1, s1, i1, c1), (o2, s2, i2, c2) in zip(H.members(mine)[:-1], H.members(ref_stream)):
+        assert (i1, c1) == (i2, c2)
+
+
+@needs_ref
+def test_reference_applet_decodes_our_stream(tmp_path):
+    import subprocess
+    data = H.synth("sam", 1 << 20)
+    stream = H.emul_stream(data, 6)
+    r = subprocess.run([H.REF_7BGZF, "-d"], input=stream, capture_output=True)
+    assert r.returncode == 0 and r.stdout == data

@@ -1,0 +1,247 @@
+"""GPU (B200): the parity tests proper.  Everything goes through the C ABI (lib7bgzf_b200.so / 7bgzf.so / the
+7bgzf applet); the oracle (emulator of the block algorithm, oracle/liboracle.so, oracle/_ref) is only the checker."""
+import ctypes
+import json
+import os
+import struct
+import subprocess
+import threading
+import zlib
+
+import pytest
+
+import b200bgzf
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+KA = json.load(open(os.path.join(H.GOLDEN, "known_answers.json")))
+MAL = json.load(open(os.path.join(H.GOLDEN, "malformed.json")))
+
+
+@pytest.fixture(scope="module")
+def codec():
+    c = b200bgzf.Codec(0)       # raises if the CUDA library / device is missing: no fallback
+    yield c
+    c.close()
+
+
+EDGE = {
+    "empty": b"", "A": b"A", "AB": b"AB", "zeros65280": bytes(65280), "noise65280": H.lcg_noise(65280), "acgt": H.acgt(65280),
+    "n31": H.lcg_noise(31), "n32": H.lcg_noise(32), "x700": b"x" * 700, "text": (b"the quick brown fox jumps over the lazy dog. " * 2000)[:65280],
+    "ragged": H.synth("sam", 3 * H.BLOCK + 17), "short_tail": H.synth("fastq", H.BLOCK + 5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+@pytest.mark.parametrize("level", [1, 6, 12])
+def test_edge_inputs_bit_exact_vs_emulator_and_decode(codec, name, level):
+    data = EDGE[name]
+    got = codec.compress(data, level)
+    assert got == H.emul_stream(data, level)                  # same bytes as the CPU run of the same algorithm
+    assert H.gunzip(got) == data
+    rc, out, _ = H.oracle_decompress(got)
+    assert rc == 0 and out == data
+    assert codec.inflate(got) == data
+
+
+def test_known_answers_of_the_reference(codec):
+    for name, payload in (("A", b"A"), ("zeros65280", bytes(65280)), ("noise65280", H.lcg_noise(65280))):
+        members, st = codec.compress_blocks([payload], 6)
+        assert st == [0] and len(members[0]) == KA[f"{name}_L6"]["size"]
+        crc, isize = struct.unpack("<II", members[0][-8:])
+        assert "%08x" % crc == KA[f"{name}_L6"]["crc"] and isize == len(payload)
+    members, _ = codec.compress_blocks([b"A"], 6)
+    assert members[0].hex().startswith(KA["A_L6"]["head"])
+    # 65536 payload bytes: zeros fit, noise cannot (reference returns 1 and leaves *dlen alone)
+    members, st = codec.compress_blocks([bytes(65536), H.lcg_noise(65536)], 6)
+    assert st == [0, 1] and len(members[0]) == KA["zeros65536_L6"]["size"] and members[1] is None
+    assert H.gunzip(members[0]) == bytes(65536)
+    # capacity conventions
+    members, st = codec.compress_blocks([H.lcg_noise(1000)], 6, caps=[30])
+    assert st == [1]
+
+
+@pytest.mark.parametrize("kind", ["fastq", "sam"])
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_stream_parity_size_crc_and_reference_decoder(codec, kind, level):
+    data = H.synth(kind, 8 << 20)
+    got = codec.compress(data, level)
+    assert got[: 20 * 16384].startswith(H.emul_stream(data[: 4 * H.BLOCK], level, eof=False))
+    mem = H.members(got)
+    assert got.endswith(H.EOF_BLOCK) and len(mem) == (len(data) + H.BLOCK - 1) // H.BLOCK + 1
+    for i, (off, size, isize, crc) in enumerate(mem[:-1]):
+        blk = data[i * H.BLOCK : (i + 1) * H.BLOCK]
+        assert isize == len(blk) and crc == zlib.crc32(blk) and size <= 65536
+    assert H.gunzip(got) == data
+    if H.have_ref():
+        ref = H.Ref(level)
+        rc, out, _ = ref.inflate_stream(got)                       # the reference's own libdeflate decoder
+        assert rc == 0 and out == data
+        _, ref_sizes, _ = ref.compress_stream(data, keep=False)
+        assert len(got) - 28 <= 1.03 * sum(ref_sizes), (len(got), sum(ref_sizes))
+
+
+def test_reference_applet_decodes_gpu_stream(codec):
+    if not os.path.exists(H.REF_7BGZF):
+        pytest.skip("oracle/_ref not built")
+    data = H.synth("sam", 2 << 20)
+    r = subprocess.run([H.REF_7BGZF, "-d"], input=codec.compress(data, 6), capture_output=True)
+    assert r.returncode == 0 and r.stdout == data
+
+
+def test_deterministic_across_runs_batches_and_paths(codec):
+    data = H.synth("fastq", 3 << 20)
+    a = codec.compress(data, 6)
+    assert a == codec.compress(data, 6)
+    # block-list path (the hook's) == bulk path, block by block
+    blocks = [data[o : o + H.BLOCK] for o in range(0, len(data), H.BLOCK)]
+    members, st = codec.compress_blocks(blocks[:7], 6)
+    assert st == [0] * 7 and b"".join(members) == a[: sum(len(m) for m in members)]
+    # sharding by contiguous block ranges (what 2/4/8 GPUs do) concatenates to the same stream
+    import shard
+    for world in (2, 4):
+        parts = [codec.compress(data[slice(*shard.byte_range(len(data), H.BLOCK, r, world))], 6, eof=False) for r in range(world)]
+        assert b"".join(parts) + H.EOF_BLOCK == a
+
+
+@pytest.mark.parametrize("kind", ["fastq", "sam"])
+@pytest.mark.parametrize("level", [1, 6, 12])
+def test_inflate_reference_golden_streams_bit_exact(codec, kind, level):
+    stream = open(os.path.join(H.GOLDEN, f"ref_{kind}_L{level}.bgz"), "rb").read()
+    assert codec.inflate(stream + H.EOF_BLOCK) == H.synth(kind, 2 * H.BLOCK)
+
+
+def test_inflate_large_reference_or_zlib_stream(codec):
+    data = H.synth("fastq", 6 << 20) + H.lcg_noise(200000) + bytes(300000)
+    if H.have_ref():
+        stream, _, _ = H.Ref(6).compress_stream(data)
+    else:
+        stream = b"".join(H.zlib_member(data[o : o + H.BLOCK]) for o in range(0, len(data), H.BLOCK))
+    out = codec.inflate(stream + H.EOF_BLOCK)
+    assert out == data
+    rc, oout, _ = H.oracle_decompress(stream)
+    assert rc == 0 and oout == out
+
+
+def test_inflate_zlib_members_all_block_types(codec):
+    payload = H.synth("sam", 60000)
+    stream = b""
+    for level, strat in ((0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_FIXED), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (9, zlib.Z_FILTERED)):
+        stream += H.zlib_member(payload, level, strat)
+    # a member with several deflate blocks (sync flushes), and tiny members
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    raw = b"".join(co.compress(payload[o : o + 7000]) + co.flush(zlib.Z_FULL_FLUSH) for o in range(0, 56000, 7000)) + co.flush()
+    stream += bytes.fromhex("1f8b08040000000000ff060042430200") + struct.pack("<H", len(raw) + 25) + raw + struct.pack("<II", zlib.crc32(payload[:56000]), 56000)
+    stream += H.zlib_member(b"") + H.zlib_member(b"x") + H.EOF_BLOCK
+    assert codec.inflate(stream) == payload * 6 + payload[:56000] + b"x"
+
+
+def test_malformed_members_same_verdict_as_reference_decoder(codec):
+    good = 0
+    for c in MAL["cases"]:
+        m = bytes.fromhex(c["hex"])
+        try:
+            out = codec.inflate(m)
+            accepted = True
+        except b200bgzf.B200BgzfError as e:
+            assert e.code == -3
+            accepted = False
+        assert accepted == (c["ref_rc"] == 0), c["ref_rc"]
+        if accepted:
+            assert "%08x" % zlib.crc32(out) == c["ref_out_crc"]
+            good += 1
+    assert good > 5
+    with pytest.raises(b200bgzf.B200BgzfError):
+        codec.inflate(b"\x1f\x8b\x08\x00" + bytes(40))          # plain gzip is "not BGZF or corrupted" (7bgzf.c:313-316)
+
+
+def test_device_resident_api_roundtrip(codec):
+    import torch
+    data = H.synth("sam", 5 * H.BLOCK + 999)
+    src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    dst = torch.empty(codec.bound(len(data)), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    n = codec.compress_device(src.data_ptr(), len(data), dst.data_ptr(), dst.numel(), 6, stream=s)
+    comp = bytes(dst[:n].cpu().numpy())
+    assert comp == H.emul_stream(data, 6)
+    back = torch.empty(len(data) + 64, dtype=torch.uint8, device="cuda")
+    m = codec.inflate_device(dst.data_ptr(), n, back.data_ptr(), back.numel(), stream=s)
+    assert m == len(data) and bytes(back[:m].cpu().numpy()) == data
+    # corrupt the BSIZE chain: must be reported as not-BGZF
+    bad = dst.clone()
+    bad[16] = (int(bad[16]) + 1) % 256
+    with pytest.raises(b200bgzf.B200BgzfError):
+        codec.inflate_device(bad.data_ptr(), n, back.data_ptr(), back.numel(), stream=s)
+
+
+def test_hook_from_many_threads(codec):
+    hook = ctypes.CDLL(b200bgzf.HOOK_PATH)
+    hook.bgzf_compress.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    data = H.synth("sam", 64 * H.BLOCK)
+    blocks = [data[o : o + H.BLOCK] for o in range(0, len(data), H.BLOCK)]
+    out = [None] * len(blocks)
+
+    def work(tid):
+        dst = ctypes.create_string_buffer(65536)
+        for i in range(tid, len(blocks), 8):
+            n = ctypes.c_size_t(65536)
+            assert hook.bgzf_compress(dst, ctypes.byref(n), blocks[i], len(blocks[i]), 9) == 0
+            out[i] = dst.raw[: n.value]
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    level = 6  # BGZF_METHOD unset -> the reference's default (zlib 6) -> level 6; htslib's level argument is ignored
+    assert b"".join(out) + H.EOF_BLOCK == codec.compress(data, level)
+    dst = ctypes.create_string_buffer(64)
+    n = ctypes.c_size_t(30)
+    assert hook.bgzf_compress(dst, ctypes.byref(n), H.lcg_noise(1000), 1000, 6) == 1 and n.value == 30
+    n = ctypes.c_size_t(25)
+    assert hook.bgzf_compress(dst, ctypes.byref(n), b"hello", 5, 6) == -1
+
+
+def test_applet_roundtrip_and_stderr_contract():
+    data = H.synth("fastq", 3 << 20)
+    r = subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6", "-@", "4"], input=data, capture_output=True)
+    assert r.returncode == 0
+    err = r.stderr.decode()
+    assert "compression level = 6 (libdeflate)" in err and " done." in err and "ellapsed time:" in err
+    assert r.stdout == H.emul_stream(data, 6)
+    d = subprocess.run([b200bgzf.APPLET_PATH, "-d"], input=r.stdout, capture_output=True)
+    assert d.returncode == 0 and d.stdout == data
+    if os.path.exists(H.REF_7BGZF):
+        ref = subprocess.run([H.REF_7BGZF, "-c", "-l6", "-@", "4"], input=data, capture_output=True)
+        d2 = subprocess.run([b200bgzf.APPLET_PATH, "-d"], input=ref.stdout, capture_output=True)
+        assert d2.returncode == 0 and d2.stdout == data            # our applet inflates the reference applet's stream
+        assert len(r.stdout) <= 1.03 * len(ref.stdout)
+    bad = subprocess.run([b200bgzf.APPLET_PATH, "-d"], input=b"this is not bgzf at all, not even close........", capture_output=True)
+    assert bad.returncode != 0 and b"not BGZF or corrupted" in bad.stderr
+
+
+def test_full_size_properties_1gib(codec):
+    """BASELINE configs[0]/[1] size: 1 GiB FASTQ-like.  Size-independent properties: round trip through our
+    inflate, ISIZE sum, per-block CRC32 against zlib on a sample, combined CRC of the whole payload."""
+    import numpy as np
+    import torch
+    n = 1 << 30
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    H._gen().b200gen_fill(0, 1, host.data_ptr(), n)
+    out = torch.empty(codec.bound(n), dtype=torch.uint8, pin_memory=True)
+    clen = codec.compress_into(host.data_ptr(), n, out.data_ptr(), out.numel(), 6)
+    assert 0.20 * n < clen < 0.26 * n                                   # reference libdeflate6 ratio on this corpus: 0.2406
+    view = out.numpy()[:clen]
+    back = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    m = codec.inflate_into(out.data_ptr(), clen, back.data_ptr(), n)
+    assert m == n and torch.equal(back, host)
+    # trailer fields of a sample of members + checksum of checksums
+    raw = view.tobytes()
+    mem = H.members(raw)
+    assert len(mem) == (n + H.BLOCK - 1) // H.BLOCK + 1 and sum(x[2] for x in mem) == n
+    hb = host.numpy()
+    crc_all = 0
+    o = H.oracle()
+    for i, (off, size, isize, crc) in enumerate(mem[:-1]):
+        if i % 257 == 0:
+            assert crc == zlib.crc32(hb[i * H.BLOCK : i * H.BLOCK + isize].tobytes())
+        crc_all = o.oracle_crc32_combine(crc_all, crc, isize)
+    assert crc_all == zlib.crc32(hb)
