@@ -67,10 +67,14 @@ refh *refh_open(const char *so_path, int level)
     if (!h->compress || !h->dec) { dlclose(h->dl); free(h); return NULL; }
     /* latch the level */
     snprintf(env, sizeof env, "libdeflate%d", level);
+    const char *old = getenv("BGZF_METHOD");
+    char *saved = old ? strdup(old) : NULL;
     setenv("BGZF_METHOD", env, 1);
     uint8_t dst[256];
     size_t dl = sizeof dst;
     h->compress(dst, &dl, "latch-the-method", 16, 0);
+    if (saved) { setenv("BGZF_METHOD", saved, 1); free(saved); }
+    else unsetenv("BGZF_METHOD");
     return h;
 }
 

@@ -174,30 +174,51 @@ def test_device_resident_api_roundtrip(codec):
         codec.inflate_device(bad.data_ptr(), n, back.data_ptr(), back.numel(), stream=s)
 
 
-def test_hook_from_many_threads(codec):
-    hook = ctypes.CDLL(b200bgzf.HOOK_PATH)
-    hook.bgzf_compress.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+HOOK_DRIVER = r"""
+import ctypes, sys, threading
+sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
+import helpers as H
+hook = ctypes.CDLL(sys.argv[1])
+hook.bgzf_compress.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+data = H.synth("sam", 64 * H.BLOCK)
+blocks = [data[o : o + H.BLOCK] for o in range(0, len(data), H.BLOCK)]
+out = [None] * len(blocks)
+def work(tid):
+    dst = ctypes.create_string_buffer(65536)
+    for i in range(tid, len(blocks), 8):
+        n = ctypes.c_size_t(65536)
+        assert hook.bgzf_compress(dst, ctypes.byref(n), blocks[i], len(blocks[i]), 9) == 0      # htslib's level is ignored
+        out[i] = dst.raw[: n.value]
+th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+[t.start() for t in th]; [t.join() for t in th]
+dst = ctypes.create_string_buffer(64)
+n = ctypes.c_size_t(30); r1 = hook.bgzf_compress(dst, ctypes.byref(n), H.lcg_noise(1000), 1000, 6); k1 = n.value
+n = ctypes.c_size_t(25); r2 = hook.bgzf_compress(dst, ctypes.byref(n), b"hello", 5, 6)
+n = ctypes.c_size_t(64); r3 = hook.bgzf_compress(dst, ctypes.byref(n), b"", 0, 6); k3 = n.value
+sys.stdout.buffer.write(b"".join(out))
+sys.stderr.write("RC %d %d %d %d %d\n" % (r1, k1, r2, r3, k3))
+"""
+
+
+def test_hook_from_many_threads(codec, tmp_path):
+    """LD_PRELOAD object: 8 concurrent callers (htslib's pool), BGZF_METHOD from the environment, reference return codes"""
     data = H.synth("sam", 64 * H.BLOCK)
-    blocks = [data[o : o + H.BLOCK] for o in range(0, len(data), H.BLOCK)]
-    out = [None] * len(blocks)
-
-    def work(tid):
-        dst = ctypes.create_string_buffer(65536)
-        for i in range(tid, len(blocks), 8):
-            n = ctypes.c_size_t(65536)
-            assert hook.bgzf_compress(dst, ctypes.byref(n), blocks[i], len(blocks[i]), 9) == 0
-            out[i] = dst.raw[: n.value]
-
-    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    level = 6  # BGZF_METHOD unset -> the reference's default (zlib 6) -> level 6; htslib's level argument is ignored
-    assert b"".join(out) + H.EOF_BLOCK == codec.compress(data, level)
-    dst = ctypes.create_string_buffer(64)
-    n = ctypes.c_size_t(30)
-    assert hook.bgzf_compress(dst, ctypes.byref(n), H.lcg_noise(1000), 1000, 6) == 1 and n.value == 30
-    n = ctypes.c_size_t(25)
-    assert hook.bgzf_compress(dst, ctypes.byref(n), b"hello", 5, 6) == -1
+    for method, level in (("libdeflate5", 5), ("LibDeflate", 6), (None, 6)):
+        env = dict(os.environ)
+        env.pop("BGZF_METHOD", None)
+        if method:
+            env["BGZF_METHOD"] = method
+        r = subprocess.run(["python", "-c", HOOK_DRIVER, b200bgzf.HOOK_PATH, os.path.join(H.ROOT, "tests"), os.path.join(H.ROOT, "7bgzf_b200")],
+                           capture_output=True, env=env)
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout + H.EOF_BLOCK == codec.compress(data, level)
+        tail = [l for l in r.stderr.decode().splitlines() if l.startswith("RC ")][-1].split()[1:]
+        assert tail == ["1", "30", "-1", "0", "28"]           # does-not-fit -> 1 (*dlen untouched); cap < 26 -> -1; slen 0 -> EOF block
+        assert "libdeflate_deflate 1" in r.stderr.decode()     # the reference's stderr line for the does-not-fit case
+    env = dict(os.environ, BGZF_METHOD="libdeflate13")
+    r = subprocess.run(["python", "-c", HOOK_DRIVER, b200bgzf.HOOK_PATH, os.path.join(H.ROOT, "tests"), os.path.join(H.ROOT, "7bgzf_b200")],
+                       capture_output=True, env=env)
+    assert r.returncode != 0                                   # out-of-range level: every call fails with -1, nothing crashes
 
 
 def test_applet_roundtrip_and_stderr_contract():
