@@ -40,9 +40,12 @@
 #define BG_HASH_BITS 14
 #define BG_HASH_SIZE (1u << BG_HASH_BITS)
 #define BG_NOPOS 0xFFFFu
-#define BG_CHUNK 64u          /* parse/emit granule: one thread per chunk */
+#define BG_CHUNK 68u          /* parse/emit granule: one thread per chunk; 17 words => conflict-free lane stride */
 #define BG_THREADS 1024u
-#define BG_MAX_CHUNKS (BG_MAX_BLOCK / BG_CHUNK)
+#define BG_MAX_CHUNKS 1024u    /* array size; ceil(65536/68) = 964 chunks are ever live */
+#define BG_SUPER 32u           /* chunks per super-chunk in the hierarchical walk */
+#define BG_SUPER_POS (BG_SUPER * BG_CHUNK)
+#define BG_MAX_TOKEN 258u
 #define BG_SLOT_BYTES 65536u  /* one output slot = the largest legal BGZF member */
 #define BG_CRC_WORDS 17u      /* CRC slice per thread, in 32-bit words (odd => conflict-free smem striding) */
 #define BG_MIN_LOOKUP 4       /* shortest match the chain search can return */
@@ -69,6 +72,8 @@
 #define BG_B_DTREEW 15584   /* u32[64]   */
 #define BG_B_DTREEP 15840   /* u16[64]   */
 #define BG_B_END 15968
+#define BG_B_SENTRY 16000     /* u32[32]   where the parse enters each super-chunk */
+#define BG_B_XTAB 16384       /* u16[31*258] super-chunk exit offset for every possible entry offset */
 
 /* scalars kept in the always-live misc area (u32 each) */
 enum {
@@ -344,43 +349,94 @@ BG_HD void bg_build_sequential(const BgCtx &c)
     }
 }
 
-/* phase 6: all-position search */
-BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
+/* phase 6: all-position search.
+ * For position p: follow the chain of earlier positions with the same hash (nearest first, at most `depth`
+ * of them, offsets <= 32768), keep the longest match (first found wins ties, i.e. the nearest), stop at
+ * `nice` or at the end of the block.  A candidate is examined only if the 4 bytes ending just past the best
+ * length so far agree (they must, for it to be longer).
+ *
+ * It is written as a per-lane state machine: one call of bg_search_step() does exactly one 4-byte comparison
+ * (a tail check or an extension word), so the 32 lanes of a warp stay converged while each works through its
+ * own candidates and positions at its own pace. */
+struct BgSearch {
+    uint32_t p, q, maxl, best, boff, l, ptail;
+    int depth;
+    bool ext;
+};
+
+/* false: nothing to search at p (result 0) */
+BG_HD bool bg_search_begin(const BgCtx &c, BgSearch &s, uint32_t p)
 {
-    const uint32_t n = c.n;
-    uint32_t maxl = n - p;
+    uint32_t maxl = c.n - p;
     if (maxl > 258) maxl = 258;
-    if (maxl < (uint32_t)BG_MIN_LOOKUP) return 0;
-    uint32_t q = c.prev[p];
-    if (q == BG_NOPOS) return 0;
+    if (maxl < (uint32_t)BG_MIN_LOOKUP) return false;
+    const uint32_t q = c.prev[p];
+    if (q == BG_NOPOS || p - q > 32768u) return false;
+    s.p = p;
+    s.q = q;
+    s.maxl = maxl;
+    s.best = 3;
+    s.boff = 0;
+    s.l = 0;
+    s.depth = c.prm.depth;
+    s.ext = false;
+    s.ptail = bg_ld32(c.dataw, p);
+    return true;
+}
+
+/* true: position finished, result in s.best / s.boff */
+BG_HD bool bg_search_step(const BgCtx &c, BgSearch &s)
+{
     const uint32_t *dw = c.dataw;
-    const uint32_t wp = bg_ld32(dw, p);
-    uint32_t best = 3, boff = 0, wtail = 0;
-    int depth = c.prm.depth;
-    const uint32_t nice = (uint32_t)c.prm.nice;
-    for (;;) {
-        uint32_t dist = p - q;
-        if (dist > 32768u) break;
-        if (bg_ld32(dw, q) == wp && (best == 3 || bg_ld32(dw, q + best - 3) == wtail)) {
-            uint32_t l = 4;
-            while (l < maxl) {
-                uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
-                if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
-                l += 4;
-            }
-            if (l > maxl) l = maxl;
-            if (l > best) {
-                best = l;
-                boff = dist;
-                if (l >= nice || l == maxl) break;
-                wtail = bg_ld32(dw, p + best - 3);
+    const uint32_t o = s.ext ? s.l : s.best - 3;
+    const uint32_t wq = bg_ld32(dw, s.q + o);
+    const uint32_t wp = s.ext ? bg_ld32(dw, s.p + o) : s.ptail;
+    const uint32_t x = wq ^ wp;
+    bool advance;
+    if (!s.ext) {
+        advance = x != 0;
+        if (!advance) {
+            s.ext = true;                      /* tail agrees: measure the whole match */
+            s.l = s.best > 3 ? 0 : 4;          /* (with no match yet the tail is bytes 0..3: already compared) */
+        }
+    } else {
+        uint32_t len = 0;
+        bool end = true;
+        if (x == 0) {
+            s.l += 4;
+            if (s.l >= s.maxl) len = s.maxl; else end = false;
+        } else {
+            len = s.l + ((uint32_t)bg_ctz(x) >> 3);
+            if (len > s.maxl) len = s.maxl;
+        }
+        advance = end;
+        if (end) {
+            s.ext = false;
+            if (len > s.best) {
+                s.best = len;
+                s.boff = s.p - s.q;
+                if (len >= (uint32_t)c.prm.nice || len == s.maxl) return true;
+                s.ptail = bg_ld32(dw, s.p + len - 3);
             }
         }
-        if (--depth <= 0) break;
-        q = c.prev[q];
-        if (q == BG_NOPOS) break;
     }
-    return best > 3 ? (best << 16) | boff : 0;
+    if (advance) {
+        if (--s.depth <= 0) return true;
+        const uint32_t q = c.prev[s.q];
+        if (q == BG_NOPOS || s.p - q > 32768u) return true;
+        s.q = q;
+    }
+    return false;
+}
+
+BG_HD uint32_t bg_search_result(const BgSearch &s) { return s.best > 3 ? (s.best << 16) | s.boff : 0; }
+
+BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
+{
+    BgSearch s;
+    if (!bg_search_begin(c, s, p)) return 0;
+    while (!bg_search_step(c, s)) {}
+    return bg_search_result(s);
 }
 
 BG_HD void bg_phase_search(const BgCtx &c, uint32_t t, uint32_t T)
@@ -456,20 +512,23 @@ BG_HD void bg_phase_jump(const BgCtx &c, uint32_t t, uint32_t T)
     }
 }
 
-/* phase 9 (thread 0): walk chunk to chunk, recording where the parse enters each chunk */
-BG_HD void bg_phase_walk(const BgCtx &c, uint32_t t, uint32_t T)
+/* phase 9: where does the parse enter each chunk?  Done in three short phases instead of one 1000-step walk:
+ *   9a (all threads)  for every super-chunk (32 chunks) and every offset 0..257 at which a parse can enter it,
+ *                     where does that parse leave it                                     -> xtab
+ *   9b (thread 0)     chain the <= 31 super-chunks from position 0                        -> sentry
+ *   9c (one thread per super-chunk) walk its 32 chunks from the true entry               -> entry */
+BG_HD uint32_t bg_walk_chunks(const BgCtx &c, uint32_t e, uint32_t ch0, uint32_t ch1, uint16_t *entry)
 {
-    (void)T;
-    if (t != 0) return;
     const uint32_t n = c.n;
-    uint16_t *entry = (uint16_t *)(c.regb + BG_B_ENTRY);
-    uint32_t e = 0;
-    for (uint32_t ch = 0; ch * BG_CHUNK < n; ch++) {
+    for (uint32_t ch = ch0; ch < ch1 && ch * BG_CHUNK < n; ch++) {
         uint32_t end = ch * BG_CHUNK + BG_CHUNK;
         if (end > n) end = n;
-        if (e >= end) { entry[ch] = BG_NOPOS; continue; }
-        entry[ch] = (uint16_t)(e - ch * BG_CHUNK);   /* chunk-relative: 65535 is a legal position */
-        uint32_t j = c.jump8[e];
+        if (e >= end) {
+            if (entry) entry[ch] = BG_NOPOS;
+            continue;
+        }
+        if (entry) entry[ch] = (uint16_t)(e - ch * BG_CHUNK);   /* chunk-relative: 65535 is a legal position */
+        const uint32_t j = c.jump8[e];
         if (j == 255) {
             uint32_t q = e;
             while (q < end) q += bg_step(c, q);
@@ -478,7 +537,52 @@ BG_HD void bg_phase_walk(const BgCtx &c, uint32_t t, uint32_t T)
             e = end + j;
         }
     }
+    return e;
+}
+
+BG_HD void bg_phase_walk_a(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    const uint32_t nsuper = (n + BG_SUPER_POS - 1) / BG_SUPER_POS;
+    uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
+    for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) {
+        const uint32_t sc = w / BG_MAX_TOKEN, k = w - sc * BG_MAX_TOKEN;
+        uint32_t send = (sc + 1) * BG_SUPER_POS;
+        if (send > n) send = n;
+        uint32_t e = sc * BG_SUPER_POS + k;
+        if (e < send) e = bg_walk_chunks(c, e, sc * BG_SUPER, (sc + 1) * BG_SUPER, (uint16_t *)0);
+        xtab[w] = (uint16_t)(e >= send ? e - send : 0);
+    }
+}
+
+BG_HD void bg_phase_walk_b(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    if (t != 0) return;
+    const uint32_t n = c.n;
+    const uint32_t nsuper = (n + BG_SUPER_POS - 1) / BG_SUPER_POS;
+    const uint16_t *xtab = (const uint16_t *)(c.regb + BG_B_XTAB);
+    uint32_t *sentry = (uint32_t *)(c.regb + BG_B_SENTRY);
+    uint32_t e = 0;
+    for (uint32_t sc = 0; sc < nsuper; sc++) {
+        uint32_t send = (sc + 1) * BG_SUPER_POS;
+        if (send > n) send = n;
+        sentry[sc] = e;
+        if (e < send) e = send + xtab[sc * BG_MAX_TOKEN + (e - sc * BG_SUPER_POS)];
+    }
     c.scal[BG_S_WALKEND] = e;   /* must equal n */
+}
+
+BG_HD void bg_phase_walk_c(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    const uint32_t nsuper = (n + BG_SUPER_POS - 1) / BG_SUPER_POS;
+    const uint32_t *sentry = (const uint32_t *)(c.regb + BG_B_SENTRY);
+    uint16_t *entry = (uint16_t *)(c.regb + BG_B_ENTRY);
+    /* spread the walkers over the warps: thread 32*sc of the block handles super-chunk sc */
+    for (uint32_t sc = t / 32; sc < nsuper; sc += (T + 31) / 32)
+        if ((t & 31u) == 0 || T < 32)
+            bg_walk_chunks(c, sentry[sc], sc * BG_SUPER, (sc + 1) * BG_SUPER, entry);
 }
 
 /* phase 10: clear histograms (region B is free now) */

@@ -28,6 +28,7 @@
 #define SM_LITFLAG (SM_CRCTAB + 1024u)
 #define SM_SCAL (SM_LITFLAG + 256u)
 #define SM_MBAR (SM_SCAL + 4u * BG_S_COUNT)
+#define SM_FRONTIER (SM_MBAR + 8u)
 #define SM_SCAN (SM_MBAR + 16u)
 #define SM_TOTAL (SM_SCAN + 4u * 36u)
 
@@ -67,22 +68,78 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-/* ---- warp 0 links the hash chains, 32 positions per step, in position order ---- */
-__device__ __forceinline__ void build_chains_warp(const BgCtx &c, uint32_t lane)
+/* ---- one warp links the hash chains, 32 positions per step, in position order, and publishes how far it got.
+ * Lanes holding the same hash inside a step are found with one ballot per hash bit (constant time; the
+ * match.any instruction serialises over distinct values and cost 400+ cycles per step here). ---- */
+__device__ __forceinline__ void build_chains_warp(const BgCtx &c, uint32_t lane, volatile uint32_t *frontier)
 {
     const uint32_t n = c.n;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t hnext = lane < n ? c.prev[lane] : BG_NOPOS;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t p = base + lane;
-        const uint32_t h = p < n ? c.prev[p] : BG_NOPOS;
-        const unsigned grp = __match_any_sync(0xffffffffu, h);
-        if (h != BG_NOPOS) {
-            const unsigned lower = grp & ((1u << lane) - 1u);
+        const uint32_t h = hnext;
+        hnext = p + 32 < n ? c.prev[p + 32] : BG_NOPOS;      /* next step's hashes: those slots are still hashes */
+        const bool valid = h != BG_NOPOS;
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int k = 0; k < BG_HASH_BITS; k++) {
+            const bool bit = (h >> k) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? b : ~b;
+        }
+        if (valid) {
+            const unsigned lower = peers & lt;
             const uint32_t link = lower ? base + (31u - (uint32_t)__clz(lower)) : (uint32_t)c.head[h];
             c.prev[p] = (uint16_t)link;
-            if ((grp >> lane) == 1u)       /* highest lane holding this hash */
+            if ((peers >> lane) == 1u)       /* highest lane holding this hash */
                 c.head[h] = (uint16_t)p;
         }
         __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            *frontier = base + 32;           /* links of every position below this are final */
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        *frontier = 0xffffffffu;
+    }
+}
+
+/* ---- all-position search: every thread owns positions t, t+1024, ... and works through them with the
+ * state machine of bgzf_block.h, one 4-byte comparison per iteration, so a warp never waits for its slowest
+ * lane except at the very end.  A position is started only once the builder has linked everything up to it. ---- */
+__device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t, volatile const uint32_t *frontier)
+{
+    const uint32_t n = c.n;
+    uint32_t p = t, fr = 0;
+    bool have = false, exhausted = p >= n;
+    BgSearch s;
+    s.p = s.q = s.maxl = s.best = s.boff = s.l = s.ptail = 0;
+    s.depth = 0;
+    s.ext = false;
+    for (;;) {
+        if (!have && !exhausted) {
+            if (fr <= p) fr = *frontier;
+            if (fr > p) {
+                if (bg_search_begin(c, s, p)) {
+                    have = true;
+                } else {
+                    c.R[p] = 0;
+                    p += BG_THREADS;
+                    exhausted = p >= n;
+                }
+            }
+        }
+        if (have && bg_search_step(c, s)) {
+            c.R[p] = bg_search_result(s);
+            have = false;
+            p += BG_THREADS;
+            exhausted = p >= n;
+        }
+        if (__all_sync(0xffffffffu, exhausted && !have)) break;
     }
 }
 
@@ -147,6 +204,7 @@ bgzf_compress_kernel(BgzfCompressArgs a)
     const uint32_t t = threadIdx.x, T = BG_THREADS;
     uint64_t *mbar = (uint64_t *)(smem + SM_MBAR);
     uint32_t *scan_scratch = (uint32_t *)(smem + SM_SCAN);
+    volatile uint32_t *frontier = (volatile uint32_t *)(smem + SM_FRONTIER);
     unsigned long long *prof = a.prof;
     long long tprev_ = prof ? clock64() : 0;
 
@@ -218,10 +276,15 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bg_phase_hash(c, t, T);
         __syncthreads();
         PROF_MARK(2);
-        if (t < 32) build_chains_warp(c, t);
+        const long long tbuild_ = prof ? clock64() : 0;
+        /* chain build (warp 31, which the scheduler favours) overlapped with the search (everyone) */
+        if (t == 0) *frontier = 0;
         __syncthreads();
-        PROF_MARK(3);
-        bg_phase_search(c, t, T);
+        if (t >= BG_THREADS - 32) {
+            build_chains_warp(c, t & 31u, frontier);
+            if (prof && t == BG_THREADS - 32) atomicAdd(&prof[10], (unsigned long long)(clock64() - tbuild_));
+        }
+        search_positions(c, t, frontier);
         __syncthreads();
         PROF_MARK(4);
         bg_phase_accept(c, t, T);
@@ -229,8 +292,12 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bg_phase_jump(c, t, T);
         __syncthreads();
         PROF_MARK(5);
-        bg_phase_walk(c, t, T);
+        bg_phase_walk_a(c, t, T);
         bg_phase_clear_freq(c, t, T);
+        __syncthreads();
+        bg_phase_walk_b(c, t, T);
+        __syncthreads();
+        bg_phase_walk_c(c, t, T);
         __syncthreads();
         PROF_MARK(6);
         bg_phase_tally(c, t, T);

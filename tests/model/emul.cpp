@@ -80,7 +80,9 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     run(bg_phase_search, c, order, k++);
     run(bg_phase_accept, c, order, k++);
     run(bg_phase_jump, c, order, k++);
-    run(bg_phase_walk, c, order, k++);
+    run(bg_phase_walk_a, c, order, k++);
+    run(bg_phase_walk_b, c, order, k++);
+    run(bg_phase_walk_c, c, order, k++);
     if (c.scal[BG_S_WALKEND] != n) { fprintf(stderr, "emul: walk ended at %u, n=%u\n", c.scal[BG_S_WALKEND], n); return -2; }
     run(bg_phase_clear_freq, c, order, k++);
     run(bg_phase_tally, c, order, k++);
