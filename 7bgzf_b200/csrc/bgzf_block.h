@@ -78,7 +78,8 @@
 /* scalars kept in the always-live misc area (u32 each) */
 enum {
     BG_S_NUSED = 0, BG_S_MINLEN, BG_S_HBYTES, BG_S_CRC, BG_S_NITEMS, BG_S_NL, BG_S_ND, BG_S_NP,
-    BG_S_BTYPE, BG_S_HDRBITS, BG_S_TOKBITS, BG_S_PAYLOAD, BG_S_STATUS, BG_S_NLKEYS, BG_S_NDKEYS, BG_S_WALKEND,
+    BG_S_BTYPE, BG_S_HDRBITS, BG_S_TOKBITS, BG_S_PAYLOAD, BG_S_STATUS, BG_S_DYNSYMS, BG_S_STASYMS, BG_S_WALKEND,
+    BG_S_EXTRA, BG_S_DYNHDR,
     BG_S_COUNT = 32
 };
 
@@ -87,21 +88,23 @@ struct BgParams {
     int nice;         /* stop searching at this length */
     int lazy;         /* 0 greedy, 1 one-ahead, 2 two-ahead */
     int passthrough;  /* inputs this short are stored (reference: 55 - 4*level) */
+    int hlong;        /* hash window (bytes) when short matches do not pay (few distinct literals): 8 or 5 */
 };
 
 /* level 1..12 -> search effort; the classes follow libdeflate_alloc_compressor_ex (deflate_compress.c:3921-4007):
- * 1-4 greedy, 5-7 lazy, 8-9 lazy2, 10-12 deepest setting of this codec. */
+ * 1-4 greedy, 5-7 lazy, 8-12 lazy2.  The numbers are this codec's own: on low-entropy text (FASTQ/SAM) an 8-byte
+ * hash with a shallow chain reaches the reference's level-6 size (+1 %) at a fraction of the candidate visits. */
 BG_HD BgParams bg_level_params(int level)
 {
     BgParams p;
-    const int depth[13] = { 0, 2, 4, 6, 8, 10, 16, 32, 64, 128, 256, 384, 512 };
-    const int nice[13] = { 0, 32, 32, 48, 64, 64, 65, 130, 258, 258, 258, 258, 258 };
     if (level < 1) level = 1;
     if (level > 12) level = 12;
-    p.depth = depth[level];
-    p.nice = nice[level];
+    p.depth = level <= 4 ? level : level == 5 ? 6 : level == 6 ? 8 : level == 7 ? 16 : level == 8 ? 64 : level == 9 ? 128
+            : level == 10 ? 256 : level == 11 ? 384 : 512;
+    p.nice = level <= 2 ? 32 : level == 3 ? 48 : level <= 5 ? 64 : level == 6 ? 65 : level == 7 ? 130 : 258;
     p.lazy = level <= 4 ? 0 : level <= 7 ? 1 : 2;
     p.passthrough = 55 - 4 * level;
+    p.hlong = level <= 7 ? 8 : 5;
     return p;
 }
 
@@ -316,9 +319,9 @@ BG_HD void bg_phase_settle(const BgCtx &c, uint32_t t, uint32_t T)
     for (uint32_t p = n & ~3u; p < n; p++)
         r = bg_crc_byte(c.crctab, r, bg_ld8(c.dataw, p));
     c.scal[BG_S_CRC] = ~r;
-    uint32_t ml = bg_min_match_len(c.scal[BG_S_NUSED], c.prm.depth, n);
-    c.scal[BG_S_MINLEN] = ml;
-    c.scal[BG_S_HBYTES] = ml >= 5 ? 5 : 4;
+    c.scal[BG_S_MINLEN] = bg_min_match_len(c.scal[BG_S_NUSED], c.prm.depth, n);
+    /* hash width follows the literal census alone (not the depth cap): cheap literals => only long matches pay */
+    c.scal[BG_S_HBYTES] = bg_min_match_len(c.scal[BG_S_NUSED], 1000, n) >= 5 ? (uint32_t)c.prm.hlong : 4u;
 }
 
 /* phase 4: hash every position that has a full hash window into prev[] */
@@ -328,6 +331,8 @@ BG_HD uint32_t bg_hash(const uint32_t *dataw, uint32_t p, uint32_t hbytes)
     uint32_t h = v * 0x1E35A7BDu;
     if (hbytes == 5)
         h ^= bg_ld8(dataw, p + 4) * 0x9E3779B1u;
+    else if (hbytes == 8)
+        h ^= bg_ld32(dataw, p + 4) * 0x9E3779B1u;
     return h >> (32 - BG_HASH_BITS);
 }
 
@@ -385,8 +390,15 @@ BG_HD bool bg_search_begin(const BgCtx &c, BgSearch &s, uint32_t p)
 }
 
 /* true: position finished, result in s.best / s.boff */
+#ifdef BG_STATS
+static unsigned long long bg_stat_steps, bg_stat_tail, bg_stat_pos;
+#endif
 BG_HD bool bg_search_step(const BgCtx &c, BgSearch &s)
 {
+#ifdef BG_STATS
+    bg_stat_steps++;
+    if (!s.ext) bg_stat_tail++;
+#endif
     const uint32_t *dw = c.dataw;
     const uint32_t o = s.ext ? s.l : s.best - 3;
     const uint32_t wq = bg_ld32(dw, s.q + o);
@@ -431,7 +443,44 @@ BG_HD bool bg_search_step(const BgCtx &c, BgSearch &s)
 
 BG_HD uint32_t bg_search_result(const BgSearch &s) { return s.best > 3 ? (s.best << 16) | s.boff : 0; }
 
+/* the same search as a plain loop (what the kernel runs: cheaper per candidate than the step machine) */
 BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
+{
+    const uint32_t n = c.n;
+    uint32_t maxl = n - p;
+    if (maxl > 258) maxl = 258;
+    if (maxl < (uint32_t)BG_MIN_LOOKUP) return 0;
+    uint32_t q = c.prev[p];
+    if (q == BG_NOPOS || p - q > 32768u) return 0;
+    const uint32_t *dw = c.dataw;
+    uint32_t best = 3, boff = 0, ptail = bg_ld32(dw, p);
+    int depth = c.prm.depth;
+    const uint32_t nice = (uint32_t)c.prm.nice;
+    for (;;) {
+        if (bg_ld32(dw, q + best - 3) == ptail) {
+            uint32_t l = best > 3 ? 0 : 4;
+            while (l < maxl) {
+                const uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
+                if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
+                l += 4;
+            }
+            if (l > maxl) l = maxl;
+            if (l > best) {
+                best = l;
+                boff = p - q;
+                if (l >= nice || l == maxl) break;
+                ptail = bg_ld32(dw, p + best - 3);
+            }
+        }
+        if (--depth <= 0) break;
+        q = c.prev[q];
+        if (q == BG_NOPOS || p - q > 32768u) break;
+    }
+    return best > 3 ? (best << 16) | boff : 0;
+}
+
+/* step-machine twin (kept for the emulator's cross-check of both formulations) */
+BG_HD uint32_t bg_search_one_steps(const BgCtx &c, uint32_t p)
 {
     BgSearch s;
     if (!bg_search_begin(c, s, p)) return 0;
@@ -786,83 +835,166 @@ BG_HD void bg_phase_huff(const BgCtx &c, uint32_t t, uint32_t T)
     }
 }
 
-/* phase 14 (thread 0): header items, precode, exact costs, block type, final code tables */
-BG_HD void bg_phase_decide(const BgCtx &c, uint32_t t, uint32_t T)
+/* phase 14a: thread 0 runs the header pipeline (trim, run-length items, precode, header bits) while one thread
+ * per symbol adds up the exact symbol costs of the dynamic and the static code */
+BG_HD void bg_phase_decide_a(const BgCtx &c, uint32_t t, uint32_t T)
 {
     (void)T;
-    if (t != 0) return;
     uint8_t *rb = c.regb;
-    const uint32_t n = c.n;
-    uint32_t *lfreq = (uint32_t *)(rb + BG_B_LFREQ), *dfreq = (uint32_t *)(rb + BG_B_DFREQ);
+    const uint32_t *lfreq = (const uint32_t *)(rb + BG_B_LFREQ), *dfreq = (const uint32_t *)(rb + BG_B_DFREQ);
+    const uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN;
+    uint32_t dyn = 0, sta = 0, extra = 0;
+    if (t < 286) {
+        const uint32_t f = lfreq[t];
+        dyn = f * llen[t];
+        sta = f * bg_static_llen(t);
+        if (t > 256) extra = f * bg_len_slot_extra_bits(t - 257);
+    } else if (t < 316) {
+        const uint32_t sym = t - 286, f = dfreq[sym];
+        dyn = f * dlen[sym];
+        sta = f * 5;
+        extra = f * bg_off_slot_extra_bits(sym);
+    }
+#if defined(__CUDA_ARCH__)
+    dyn = __reduce_add_sync(0xffffffffu, dyn);
+    sta = __reduce_add_sync(0xffffffffu, sta);
+    extra = __reduce_add_sync(0xffffffffu, extra);
+    if ((t & 31u) == 0 && t < 320) {
+        atomicAdd(&c.scal[BG_S_DYNSYMS], dyn);
+        atomicAdd(&c.scal[BG_S_STASYMS], sta);
+        atomicAdd(&c.scal[BG_S_EXTRA], extra);
+    }
+#else
+    c.scal[BG_S_DYNSYMS] += dyn;
+    c.scal[BG_S_STASYMS] += sta;
+    c.scal[BG_S_EXTRA] += extra;
+#endif
+    if (t != 0) return;
     uint32_t *pfreq = (uint32_t *)(rb + BG_B_PFREQ);
-    uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN, *plen = rb + BG_B_PLEN;
-    uint16_t *lcode = (uint16_t *)(rb + BG_B_LCODE), *dcode = (uint16_t *)(rb + BG_B_DCODE);
-    uint16_t *pcode = (uint16_t *)(rb + BG_B_PCODE), *items = (uint16_t *)(rb + BG_B_ITEMS);
+    uint8_t *plen = rb + BG_B_PLEN;
+    uint16_t *items = (uint16_t *)(rb + BG_B_ITEMS);
     uint32_t *scratch = (uint32_t *)(rb + BG_B_SCRATCH);
-
     uint32_t nl = 286, nd = 30;
     while (nl > 257 && llen[nl - 1] == 0) nl--;
     while (nd > 1 && dlen[nd - 1] == 0) nd--;
-    uint32_t ni = bg_header_items(llen, nl, dlen, nd, items, pfreq);
+    const uint32_t ni = bg_header_items(llen, nl, dlen, nd, items, pfreq);
     uint32_t *pkeys = (uint32_t *)(rb + BG_B_PKEYS);
     for (uint32_t i = 0; i < 19; i++) plen[i] = 0;
-    uint32_t pm = bg_small_keys(pfreq, 19, pkeys);
+    const uint32_t pm = bg_small_keys(pfreq, 19, pkeys);
     bg_huff_lengths(pkeys, pm, 7, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP), scratch, plen);
     uint32_t np = 19;
     while (np > 4 && plen[bg_precode_order(np - 1)] == 0) np--;
-
-    /* exact bit costs */
-    uint32_t extra = 0, dyn_syms = 0, sta_syms = 0;
-    for (uint32_t s = 0; s < 286; s++) {
-        uint32_t f = lfreq[s];
-        if (!f) continue;
-        dyn_syms += f * llen[s];
-        sta_syms += f * bg_static_llen(s);
-        if (s > 256) extra += f * bg_len_slot_extra_bits(s - 257);
-    }
-    for (uint32_t s = 0; s < 30; s++) {
-        uint32_t f = dfreq[s];
-        if (!f) continue;
-        dyn_syms += f * dlen[s];
-        sta_syms += f * 5;
-        extra += f * bg_off_slot_extra_bits(s);
-    }
     uint32_t hdr = 3 + 5 + 5 + 4 + 3 * np;
-    for (uint32_t i = 0; i < ni; i++) {
-        uint32_t sym = items[i] & 31u;
-        hdr += plen[sym] + (sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0);
-    }
-    const uint32_t dyn_bits = hdr + dyn_syms + extra;
-    const uint32_t sta_bits = 3 + sta_syms + extra;
-    const uint32_t nstored = n ? (n + 65534u) / 65535u : 1u;
-    const uint32_t sto_bits = 8 * (n + 5 * nstored);
-
-    uint32_t btype, hdrbits, tokbits;
-    if (n != 0 && ((int)n <= c.prm.passthrough || (sto_bits <= sta_bits && sto_bits <= dyn_bits))) {
-        btype = 0; hdrbits = 0; tokbits = 0;
-        c.scal[BG_S_PAYLOAD] = n + 5 * nstored;
-    } else if (sta_bits <= dyn_bits) {
-        btype = 1; hdrbits = 3; tokbits = sta_bits - 3;
-        for (uint32_t s = 0; s < 288; s++) llen[s] = (uint8_t)bg_static_llen(s);
-        for (uint32_t s = 0; s < 32; s++) dlen[s] = 5;
-        c.scal[BG_S_PAYLOAD] = (sta_bits + 7) >> 3;
-    } else {
-        btype = 2; hdrbits = hdr; tokbits = dyn_bits - hdr;
-        c.scal[BG_S_PAYLOAD] = (dyn_bits + 7) >> 3;
-    }
-    if (btype) {
-        bg_huff_codes(llen, 288, 15, scratch, lcode);
-        bg_huff_codes(dlen, 32, 15, scratch, dcode);
-        if (btype == 2) bg_huff_codes(plen, 19, 7, scratch, pcode);
-    }
-    c.scal[BG_S_BTYPE] = btype;
-    c.scal[BG_S_HDRBITS] = hdrbits;
-    c.scal[BG_S_TOKBITS] = tokbits;   /* includes the end-of-block symbol */
+    for (uint32_t i = 0; i < 19; i++)
+        hdr += pfreq[i] * (plen[i] + (i == 16 ? 2u : i == 17 ? 3u : i == 18 ? 7u : 0u));
+    c.scal[BG_S_DYNHDR] = hdr;
     c.scal[BG_S_NITEMS] = ni;
     c.scal[BG_S_NL] = nl;
     c.scal[BG_S_ND] = nd;
     c.scal[BG_S_NP] = np;
-    c.scal[BG_S_STATUS] = (18u + c.scal[BG_S_PAYLOAD] + 8u > BG_SLOT_BYTES) ? 1u : 0u;
+}
+
+/* block type from the exact costs: every thread evaluates the same few scalars */
+BG_HD uint32_t bg_block_type(const BgCtx &c, uint32_t *hdrbits, uint32_t *tokbits, uint32_t *payload)
+{
+    const uint32_t n = c.n;
+    const uint32_t hdr = c.scal[BG_S_DYNHDR], extra = c.scal[BG_S_EXTRA];
+    const uint32_t dyn_bits = hdr + c.scal[BG_S_DYNSYMS] + extra;
+    const uint32_t sta_bits = 3 + c.scal[BG_S_STASYMS] + extra;
+    const uint32_t nstored = n ? (n + 65534u) / 65535u : 1u;
+    const uint32_t sto_bits = 8 * (n + 5 * nstored);
+    if (n != 0 && ((int)n <= c.prm.passthrough || (sto_bits <= sta_bits && sto_bits <= dyn_bits))) {
+        *hdrbits = 0; *tokbits = 0; *payload = n + 5 * nstored;
+        return 0;
+    }
+    if (sta_bits <= dyn_bits) {
+        *hdrbits = 3; *tokbits = sta_bits - 3; *payload = (sta_bits + 7) >> 3;
+        return 1;
+    }
+    *hdrbits = hdr; *tokbits = dyn_bits - hdr; *payload = (dyn_bits + 7) >> 3;
+    return 2;
+}
+
+/* per-length counters / first codes of the three alphabets live in dead sort-key space */
+#define BG_B_LCOUNT BG_B_KEYS            /* u32[16] litlen, u32[16] offset, u32[16] precode: counts per length */
+#define BG_B_LFIRST (BG_B_KEYS + 192)    /* u32[16] x 3: first canonical codeword per length */
+
+/* phase 14b: settle the block type; a static block swaps in the fixed code lengths; clear the counters */
+BG_HD void bg_phase_decide_b(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    uint8_t *rb = c.regb;
+    uint32_t hdrbits, tokbits, payload;
+    const uint32_t btype = bg_block_type(c, &hdrbits, &tokbits, &payload);
+    if (btype == 1) {
+        if (t < 288) rb[BG_B_LLEN + t] = (uint8_t)bg_static_llen(t);
+        if (t < 32) rb[BG_B_DLEN + t] = 5;
+    }
+    if (t < 96) ((uint32_t *)(rb + BG_B_LCOUNT))[t] = 0;
+    if (t == 0) {
+        c.scal[BG_S_BTYPE] = btype;
+        c.scal[BG_S_HDRBITS] = hdrbits;
+        c.scal[BG_S_TOKBITS] = tokbits;   /* includes the end-of-block symbol */
+        c.scal[BG_S_PAYLOAD] = payload;
+        c.scal[BG_S_STATUS] = (18u + payload + 8u > BG_SLOT_BYTES) ? 1u : 0u;
+    }
+}
+
+/* which (alphabet, symbol) does thread t own: 0..287 litlen, 288..319 offset, 320..338 precode */
+BG_HD bool bg_code_slot(const BgCtx &c, uint32_t t, uint32_t *alpha, uint32_t *sym, const uint8_t **lens, uint16_t **codes)
+{
+    uint8_t *rb = c.regb;
+    if (t < 288) { *alpha = 0; *sym = t; *lens = rb + BG_B_LLEN; *codes = (uint16_t *)(rb + BG_B_LCODE); return true; }
+    if (t < 320) { *alpha = 1; *sym = t - 288; *lens = rb + BG_B_DLEN; *codes = (uint16_t *)(rb + BG_B_DCODE); return true; }
+    if (t < 339) { *alpha = 2; *sym = t - 320; *lens = rb + BG_B_PLEN; *codes = (uint16_t *)(rb + BG_B_PCODE); return true; }
+    return false;
+}
+
+/* phase 14c: count codewords per length (one thread per symbol) */
+BG_HD void bg_phase_codes_a(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    uint32_t alpha, sym;
+    const uint8_t *lens;
+    uint16_t *codes;
+    if (c.scal[BG_S_BTYPE] == 0 || !bg_code_slot(c, t, &alpha, &sym, &lens, &codes)) return;
+    const uint32_t l = lens[sym];
+    if (l) bg_add32((uint32_t *)(c.regb + BG_B_LCOUNT) + 16 * alpha + l, 1);
+}
+
+/* phase 14d: first canonical codeword of every length (threads 0, 32, 64: one alphabet each) */
+BG_HD void bg_phase_codes_b(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    if (c.scal[BG_S_BTYPE] == 0) return;
+    for (uint32_t alpha = 0; alpha < 3; alpha++) {
+        if (t != (32 * alpha) % T) continue;
+        const uint32_t *count = (const uint32_t *)(c.regb + BG_B_LCOUNT) + 16 * alpha;
+        uint32_t *first = (uint32_t *)(c.regb + BG_B_LFIRST) + 16 * alpha;
+        uint32_t code = 0, prevcount = 0;
+        for (uint32_t l = 1; l <= 15; l++) {
+            code = (code + prevcount) << 1;
+            first[l] = code;
+            prevcount = count[l];
+        }
+    }
+}
+
+/* phase 14e: codeword of symbol s = first[len] + (number of lower symbols with the same length), bit-reversed */
+BG_HD void bg_phase_codes_c(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    uint32_t alpha, sym;
+    const uint8_t *lens;
+    uint16_t *codes;
+    if (c.scal[BG_S_BTYPE] == 0 || !bg_code_slot(c, t, &alpha, &sym, &lens, &codes)) return;
+    const uint32_t l = lens[sym];
+    uint32_t code = 0;
+    if (l) {
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < sym; j++) rank += lens[j] == l;
+        code = bg_brev(((const uint32_t *)(c.regb + BG_B_LFIRST))[16 * alpha + l] + rank, (int)l);
+    }
+    codes[sym] = (uint16_t)code;
 }
 
 /* phase 15: bits per chunk with the final code */

@@ -68,79 +68,102 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-/* ---- one warp links the hash chains, 32 positions per step, in position order, and publishes how far it got.
- * Lanes holding the same hash inside a step are found with one ballot per hash bit (constant time; the
- * match.any instruction serialises over distinct values and cost 400+ cycles per step here). ---- */
-__device__ __forceinline__ void build_chains_warp(const BgCtx &c, uint32_t lane, volatile uint32_t *frontier)
+/* ---- hash chains: prev[p] = nearest earlier position with p's hash (exactly what a sequential insert gives).
+ * Two phases, so that only a thin loop stays sequential:
+ *   A (all warps)  per group of 32 consecutive positions, find the lanes that share a hash with one ballot per
+ *                  hash bit (match.any serialises over distinct values: 400+ cycles per group here).  A lane
+ *                  with a lower peer gets its final link at once; the lowest lane of each peer set keeps its
+ *                  hash and notes (hi[] byte, in the L2-resident scratch) which lane is the highest peer.
+ *   B (warp 0)     walks the groups in order: every noted lane reads head[hash] as its link and stores the
+ *                  highest peer's position as the new head.  ~12 instructions per group. ---- */
+__device__ __forceinline__ unsigned hash_peers(uint32_t h, bool valid)
 {
-    const uint32_t n = c.n;
-    const unsigned lt = (1u << lane) - 1u;
-    uint32_t hnext = lane < n ? c.prev[lane] : BG_NOPOS;
-    for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t p = base + lane;
-        const uint32_t h = hnext;
-        hnext = p + 32 < n ? c.prev[p + 32] : BG_NOPOS;      /* next step's hashes: those slots are still hashes */
-        const bool valid = h != BG_NOPOS;
-        unsigned peers = __ballot_sync(0xffffffffu, valid);
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-        for (int k = 0; k < BG_HASH_BITS; k++) {
-            const bool bit = (h >> k) & 1u;
-            const unsigned b = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? b : ~b;
-        }
-        if (valid) {
-            const unsigned lower = peers & lt;
-            const uint32_t link = lower ? base + (31u - (uint32_t)__clz(lower)) : (uint32_t)c.head[h];
-            c.prev[p] = (uint16_t)link;
-            if ((peers >> lane) == 1u)       /* highest lane holding this hash */
-                c.head[h] = (uint16_t)p;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            *frontier = base + 32;           /* links of every position below this are final */
-        }
+    for (int k = 0; k < BG_HASH_BITS; k++) {
+        const uint32_t bit = (h >> k) & 1u;
+        const unsigned b = __ballot_sync(0xffffffffu, bit != 0);
+        peers &= b ^ (bit - 1u);
     }
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        *frontier = 0xffffffffu;
-    }
+    return peers;
 }
 
-/* ---- all-position search: every thread owns positions t, t+1024, ... and works through them with the
- * state machine of bgzf_block.h, one 4-byte comparison per iteration, so a warp never waits for its slowest
- * lane except at the very end.  A position is started only once the builder has linked everything up to it. ---- */
-__device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t, volatile const uint32_t *frontier)
+/* notes layout: tile = 16 consecutive groups (512 positions); tile i holds 32 lanes x 16 bytes, so that in phase
+ * B each lane fetches the notes of its next 16 groups with one coalesced 16-byte load, a whole tile ahead. */
+__device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, uint32_t t)
 {
-    const uint32_t n = c.n;
-    uint32_t p = t, fr = 0;
-    bool have = false, exhausted = p >= n;
-    BgSearch s;
-    s.p = s.q = s.maxl = s.best = s.boff = s.l = s.ptail = 0;
-    s.depth = 0;
-    s.ext = false;
-    for (;;) {
-        if (!have && !exhausted) {
-            if (fr <= p) fr = *frontier;
-            if (fr > p) {
-                if (bg_search_begin(c, s, p)) {
-                    have = true;
+    const uint32_t n = c.n, lane = t & 31u, warp = t >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t ntiles = (n + 511u) >> 9;
+    for (uint32_t tile = warp; tile < ntiles; tile += BG_THREADS / 32) {
+        uint32_t w[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
+#pragma unroll
+        for (uint32_t g = 0; g < 16; g++) {
+            const uint32_t base = tile * 512u + g * 32u;
+            if (base >= n) break;               /* uniform for the warp */
+            const uint32_t p = base + lane;
+            const uint32_t h = p < n ? c.prev[p] : BG_NOPOS;
+            const bool valid = h != BG_NOPOS;
+            const unsigned peers = hash_peers(h, valid);
+            if (valid) {
+                const unsigned lower = peers & lt;
+                if (lower) {
+                    c.prev[p] = (uint16_t)(base + (31u - (uint32_t)__clz(lower)));
                 } else {
-                    c.R[p] = 0;
-                    p += BG_THREADS;
-                    exhausted = p >= n;
+                    const uint32_t note = 31u - (uint32_t)__clz(peers);   /* lane of the highest position with this hash */
+                    w[g >> 2] = (w[g >> 2] & ~(0xffu << (8 * (g & 3)))) | (note << (8 * (g & 3)));
                 }
             }
         }
-        if (have && bg_search_step(c, s)) {
-            c.R[p] = bg_search_result(s);
-            have = false;
-            p += BG_THREADS;
-            exhausted = p >= n;
-        }
-        if (__all_sync(0xffffffffu, exhausted && !have)) break;
+        notes[tile * 32u + lane] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+/* Phase B, one warp.  Shared-memory instructions of a warp execute in program order, so the head-table updates of
+ * consecutive groups need no barrier between them (the accesses are volatile so the compiler keeps their order);
+ * the loop is then bound by issue rate, not by the load->store round trip of every group. */
+__device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *notes, uint32_t lane)
+{
+    const uint32_t n = c.n;
+    const uint32_t ntiles = (n + 511u) >> 9;
+    volatile uint16_t *vhead = c.head;
+    volatile uint16_t *vprev = c.prev;
+    const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    uint4 n1 = ntiles > 0 ? __ldcg(notes + lane) : none;
+    uint4 n2 = ntiles > 1 ? __ldcg(notes + 32u + lane) : none;
+    for (uint32_t tile = 0; tile < ntiles; tile++) {
+        const uint4 cur = n1;
+        n1 = n2;
+        if (tile + 2 < ntiles) n2 = __ldcg(notes + (tile + 2) * 32u + lane);     /* two tiles (32 groups) ahead */
+        const uint32_t w[4] = { cur.x, cur.y, cur.z, cur.w };
+        /* the hash slots of this tile's leaders are untouched until their group is processed: fetch them all now */
+        uint32_t hs[16];
+#pragma unroll
+        for (uint32_t g = 0; g < 16; g++) {
+            const uint32_t p = tile * 512u + g * 32u + lane;
+            const uint32_t note = (w[g >> 2] >> (8 * (g & 3))) & 0xffu;
+            hs[g] = (note != 0xffu && p < n) ? (uint32_t)vprev[p] : 0xffffffffu;
+        }
+#pragma unroll
+        for (uint32_t g = 0; g < 16; g++) {
+            const uint32_t base = tile * 512u + g * 32u;
+            const uint32_t h = hs[g];
+            if (h != 0xffffffffu) {
+                const uint32_t note = (w[g >> 2] >> (8 * (g & 3))) & 31u;
+                const uint16_t old = vhead[h];
+                vhead[h] = (uint16_t)(base + note);
+                vprev[base + lane] = old;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* ---- all-position search: thread t takes positions t, t+1024, ... ---- */
+__device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
+{
+    for (uint32_t p = t; p < c.n; p += BG_THREADS)
+        c.R[p] = bg_search_one(c, p);
 }
 
 /* ---- 512-key bitonic sort in shared memory (ascending); all threads call it ---- */
@@ -204,7 +227,6 @@ bgzf_compress_kernel(BgzfCompressArgs a)
     const uint32_t t = threadIdx.x, T = BG_THREADS;
     uint64_t *mbar = (uint64_t *)(smem + SM_MBAR);
     uint32_t *scan_scratch = (uint32_t *)(smem + SM_SCAN);
-    volatile uint32_t *frontier = (volatile uint32_t *)(smem + SM_FRONTIER);
     unsigned long long *prof = a.prof;
     long long tprev_ = prof ? clock64() : 0;
 
@@ -276,15 +298,14 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bg_phase_hash(c, t, T);
         __syncthreads();
         PROF_MARK(2);
-        const long long tbuild_ = prof ? clock64() : 0;
-        /* chain build (warp 31, which the scheduler favours) overlapped with the search (everyone) */
-        if (t == 0) *frontier = 0;
+        uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build notes live behind the match scratch */
+        build_peers_phase(c, hi, t);
         __syncthreads();
-        if (t >= BG_THREADS - 32) {
-            build_chains_warp(c, t & 31u, frontier);
-            if (prof && t == BG_THREADS - 32) atomicAdd(&prof[10], (unsigned long long)(clock64() - tbuild_));
-        }
-        search_positions(c, t, frontier);
+        PROF_MARK(3);
+        if (t < 32u) build_link_phase(c, hi, t);     /* the other warps wait at the barrier */
+        __syncthreads();
+        PROF_MARK(10);
+        search_positions(c, t);
         __syncthreads();
         PROF_MARK(4);
         bg_phase_accept(c, t, T);
@@ -308,7 +329,15 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bitonic_sort_512((uint32_t *)(c.regb + BG_B_KEYS), t);
         bg_phase_huff(c, t, T);
         __syncthreads();
-        bg_phase_decide(c, t, T);
+        bg_phase_decide_a(c, t, T);
+        __syncthreads();
+        bg_phase_decide_b(c, t, T);
+        __syncthreads();
+        bg_phase_codes_a(c, t, T);
+        __syncthreads();
+        bg_phase_codes_b(c, t, T);
+        __syncthreads();
+        bg_phase_codes_c(c, t, T);
         __syncthreads();
         PROF_MARK(8);
         bg_phase_sizes(c, t, T);

@@ -6,7 +6,7 @@
 
 #include "bgzf_block.h"
 
-#define BGZF_SCRATCH_WORDS (65536u + 32u)   /* per-CTA match scratch (u32 per position) */
+#define BGZF_SCRATCH_WORDS (65536u + 32u + 16384u + 32u)   /* per-CTA scratch: u32 match per position + u8 build notes */
 #define BGZF_PROF_SLOTS 16
 
 struct BgzfCompressArgs {

@@ -92,7 +92,11 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
         std::sort(keys, keys + 512);
     }
     run(bg_phase_huff, c, order, k++);
-    run(bg_phase_decide, c, order, k++);
+    run(bg_phase_decide_a, c, order, k++);
+    run(bg_phase_decide_b, c, order, k++);
+    run(bg_phase_codes_a, c, order, k++);
+    run(bg_phase_codes_b, c, order, k++);
+    run(bg_phase_codes_c, c, order, k++);
     run(bg_phase_sizes, c, order, k++);
     {   // twin of the kernel's block-wide exclusive scan
         uint32_t *cb = (uint32_t *)(c.regb + BG_B_CBITS), acc = 0;
@@ -135,6 +139,9 @@ int main(int argc, char **argv)
     { uint32_t dl = 0; bgemul_compress_block(in.data(), 0, level, order, dst, &dl); fwrite(dst, 1, dl, o); total += dl; }
     fclose(o);
     fprintf(stderr, "in=%zu out=%zu ratio=%.4f\n", in.size(), total, in.size() ? (double)total / in.size() : 0.0);
+#ifdef BG_STATS
+    fprintf(stderr, "search steps/position %.2f (tail checks %.2f)\n", (double)bg_stat_steps / in.size(), (double)bg_stat_tail / in.size());
+#endif
     return 0;
 }
 #endif

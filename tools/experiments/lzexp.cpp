@@ -105,6 +105,7 @@ static size_t compress_block(const uint8_t *in, int n, long *stats) {
     uint64_t hmask = HBYTES >= 8 ? ~0ull : ((1ull << (8 * HBYTES)) - 1);
     auto hash = [&](int p) { uint64_t v; memcpy(&v, in + p, 8); v &= hmask;
         if (HBYTES <= 4) return (uint32_t)(((uint32_t)v * 0x1E35A7BDu) >> (32 - HB));
+        if (HBYTES == 8) return (uint32_t)((((uint32_t)v * 0x1E35A7BDu) ^ ((uint32_t)(v >> 32) * 0x9E3779B1u)) >> (32 - HB));
         return (uint32_t)((v * 0x9E3779B185EBCA87ull) >> (64 - HB)); };
     int last = n - HBYTES; // positions with a full hash
     for (int p = 0; p <= last; p++) { uint32_t h = hash(p); prev[p] = head[h]; head[h] = p; }
