@@ -507,21 +507,25 @@ BG_HD void bg_phase_accept(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t n = c.n, minlen = c.scal[BG_S_MINLEN];
     const int lazy = c.prm.lazy;
     const uint32_t nice = (uint32_t)c.prm.nice;
+    /* R lives in the L2-resident scratch: keep the next round's three loads in flight while deciding this one */
+    uint32_t a0 = t < n ? c.R[t] : 0, a1 = t + 1 < n ? c.R[t + 1] : 0, a2 = (lazy >= 2 && t + 2 < n) ? c.R[t + 2] : 0;
     for (uint32_t p = t; p < n; p += T) {
-        uint32_t r0 = c.R[p];
+        const uint32_t r0 = a0, r1 = a1, r2 = a2;
+        const uint32_t pn = p + T;
+        a0 = pn < n ? c.R[pn] : 0;
+        a1 = pn + 1 < n ? c.R[pn + 1] : 0;
+        a2 = (lazy >= 2 && pn + 2 < n) ? c.R[pn + 2] : 0;
         uint32_t code = 0;
         if (bg_match_ok(r0, minlen)) {
             uint32_t cl = r0 >> 16, co = r0 & 0xffffu;
             bool take = true;
             if (lazy >= 1 && cl < nice && p + 1 < n) {
-                uint32_t r1 = c.R[p + 1];
                 if (bg_match_ok(r1, minlen)) {
                     int nl = (int)(r1 >> 16);
                     if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r1 & 0xffffu)) > 2)
                         take = false;
                 }
                 if (take && lazy >= 2 && p + 2 < n) {
-                    uint32_t r2 = c.R[p + 2];
                     if (bg_match_ok(r2, minlen)) {
                         int nl = (int)(r2 >> 16);
                         if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r2 & 0xffffu)) > 6)
@@ -589,12 +593,40 @@ BG_HD uint32_t bg_walk_chunks(const BgCtx &c, uint32_t e, uint32_t ch0, uint32_t
     return e;
 }
 
+/* 9-: which entry offsets can occur at all?  Offset k into super-chunk sc is possible only if some position in the
+ * 258 before its start steps exactly onto it (or it is the very start of the block).  Typically a few dozen of the 258. */
+BG_HD void bg_phase_walk_mark(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t n = c.n;
+    const uint32_t nsuper = (n + BG_SUPER_POS - 1) / BG_SUPER_POS;
+    uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
+    for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) {
+        const uint32_t sc = w / BG_MAX_TOKEN, back = w - sc * BG_MAX_TOKEN + 1;    /* 1..258 positions before the start */
+        const uint32_t start = sc * BG_SUPER_POS;
+        if (sc == 0) {
+            if (back == 1) xtab[0] = 0xFFFFu;
+            continue;
+        }
+        const uint32_t q = start - back;           /* start >= 2176 > 258 */
+        const uint32_t nx = q + bg_step(c, q);
+        if (nx >= start && nx < start + BG_MAX_TOKEN) xtab[sc * BG_MAX_TOKEN + (nx - start)] = 0xFFFFu;   /* same value from all writers */
+    }
+}
+
+BG_HD void bg_phase_walk_clear(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t nsuper = (c.n + BG_SUPER_POS - 1) / BG_SUPER_POS;
+    uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
+    for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) xtab[w] = 0;
+}
+
 BG_HD void bg_phase_walk_a(const BgCtx &c, uint32_t t, uint32_t T)
 {
     const uint32_t n = c.n;
     const uint32_t nsuper = (n + BG_SUPER_POS - 1) / BG_SUPER_POS;
     uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
     for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) {
+        if (xtab[w] != 0xFFFFu) continue;          /* not a possible entry */
         const uint32_t sc = w / BG_MAX_TOKEN, k = w - sc * BG_MAX_TOKEN;
         uint32_t send = (sc + 1) * BG_SUPER_POS;
         if (send > n) send = n;
@@ -835,9 +867,22 @@ BG_HD void bg_phase_huff(const BgCtx &c, uint32_t t, uint32_t T)
     }
 }
 
-/* phase 14a: thread 0 runs the header pipeline (trim, run-length items, precode, header bits) while one thread
- * per symbol adds up the exact symbol costs of the dynamic and the static code */
-BG_HD void bg_phase_decide_a(const BgCtx &c, uint32_t t, uint32_t T)
+/* phase 14: the dynamic header, in parallel.
+ *   h1  trim trailing zero lengths (atomic max), symbol cost sums of the dynamic and the static code
+ *   h2  one thread per code length: does a run start here?  (ballot words)
+ *   h3  each run start measures its run and counts the run-length items it will emit  -> scan -> offsets
+ *   h4  each run start writes its items and tallies the precode alphabet
+ *   h5  thread 0: precode lengths, HCLEN, header bit count
+ * The items are exactly those of the sequential rule in bg_header_items() (kept below as documentation and
+ * for the emulator's cross-check). */
+#define BG_B_RUNMASK BG_B_SCRATCH      /* u32[12] run-start ballots, one word per 32 code lengths */
+
+BG_HD uint32_t bg_hdr_len_at(const BgCtx &c, uint32_t i, uint32_t nl)
+{
+    return i < nl ? c.regb[BG_B_LLEN + i] : c.regb[BG_B_DLEN + (i - nl)];
+}
+
+BG_HD void bg_phase_hdr1(const BgCtx &c, uint32_t t, uint32_t T)
 {
     (void)T;
     uint8_t *rb = c.regb;
@@ -849,11 +894,25 @@ BG_HD void bg_phase_decide_a(const BgCtx &c, uint32_t t, uint32_t T)
         dyn = f * llen[t];
         sta = f * bg_static_llen(t);
         if (t > 256) extra = f * bg_len_slot_extra_bits(t - 257);
+        if (llen[t]) {
+#if defined(__CUDA_ARCH__)
+            atomicMax(&c.scal[BG_S_NL], t + 1);
+#else
+            if (c.scal[BG_S_NL] < t + 1) c.scal[BG_S_NL] = t + 1;
+#endif
+        }
     } else if (t < 316) {
         const uint32_t sym = t - 286, f = dfreq[sym];
         dyn = f * dlen[sym];
         sta = f * 5;
         extra = f * bg_off_slot_extra_bits(sym);
+        if (dlen[sym]) {
+#if defined(__CUDA_ARCH__)
+            atomicMax(&c.scal[BG_S_ND], sym + 1);
+#else
+            if (c.scal[BG_S_ND] < sym + 1) c.scal[BG_S_ND] = sym + 1;
+#endif
+        }
     }
 #if defined(__CUDA_ARCH__)
     dyn = __reduce_add_sync(0xffffffffu, dyn);
@@ -869,26 +928,132 @@ BG_HD void bg_phase_decide_a(const BgCtx &c, uint32_t t, uint32_t T)
     c.scal[BG_S_STASYMS] += sta;
     c.scal[BG_S_EXTRA] += extra;
 #endif
+    if (t < 20) ((uint32_t *)(rb + BG_B_PFREQ))[t] = 0;
+    if (t < 12) ((uint32_t *)(rb + BG_B_RUNMASK))[t] = 0;
+}
+
+BG_HD void bg_hdr_dims(const BgCtx &c, uint32_t *nl, uint32_t *nd)
+{
+    *nl = c.scal[BG_S_NL] < 257 ? 257 : c.scal[BG_S_NL];
+    *nd = c.scal[BG_S_ND] < 1 ? 1 : c.scal[BG_S_ND];
+}
+
+BG_HD void bg_phase_hdr2(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    uint32_t nl, nd;
+    bg_hdr_dims(c, &nl, &nd);
+    const uint32_t total = nl + nd;
+    bool start = false;
+    if (t < total) start = t == 0 || bg_hdr_len_at(c, t, nl) != bg_hdr_len_at(c, t - 1, nl);
+#if defined(__CUDA_ARCH__)
+    const unsigned m = __ballot_sync(0xffffffffu, start);
+    if ((t & 31u) == 0 && t < 352) ((uint32_t *)(c.regb + BG_B_RUNMASK))[t >> 5] = m;
+#else
+    if (start) ((uint32_t *)(c.regb + BG_B_RUNMASK))[t >> 5] |= 1u << (t & 31u);
+#endif
+}
+
+/* run starting at i: its length, from the ballot words */
+BG_HD uint32_t bg_hdr_run_len(const BgCtx &c, uint32_t i, uint32_t total)
+{
+    const uint32_t *mask = (const uint32_t *)(c.regb + BG_B_RUNMASK);
+    uint32_t w = i >> 5;
+    uint32_t m = mask[w] & ~((2u << (i & 31u)) - 1u);      /* starts above i in the same word */
+    while (m == 0 && (w + 1) * 32 < total) m = mask[++w];
+    const uint32_t next = m ? w * 32 + (uint32_t)bg_ctz(m) : total;
+    return (next < total ? next : total) - i;
+}
+
+/* the sequential rule, as counts: how many items does a run (value v, length r) produce */
+BG_HD uint32_t bg_hdr_run_items(uint32_t v, uint32_t r)
+{
+    if (v == 0) {
+        const uint32_t full = r / 138, rem = r - full * 138;
+        return full + (rem >= 3 ? 1 : rem);
+    }
+    const uint32_t r1 = r - 1, full = r1 / 6, rem = r1 - full * 6;
+    return 1 + full + (rem >= 3 ? 1 : rem);
+}
+
+BG_HD void bg_phase_hdr3(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint32_t nl, nd;
+    bg_hdr_dims(c, &nl, &nd);
+    const uint32_t total = nl + nd;
+    uint32_t *cnt = (uint32_t *)(c.regb + BG_B_CBITS);
+    const uint32_t *mask = (const uint32_t *)(c.regb + BG_B_RUNMASK);
+    for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
+        uint32_t k = 0;
+        if (i < total && ((mask[i >> 5] >> (i & 31u)) & 1u))
+            k = bg_hdr_run_items(bg_hdr_len_at(c, i, nl), bg_hdr_run_len(c, i, total));
+        cnt[i] = k;
+    }
+}
+
+/* (the driver turns cnt[] into its exclusive prefix sum; the grand total is the item count) */
+
+BG_HD void bg_phase_hdr4(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint32_t nl, nd;
+    bg_hdr_dims(c, &nl, &nd);
+    const uint32_t total = nl + nd;
+    const uint32_t *off = (const uint32_t *)(c.regb + BG_B_CBITS);
+    const uint32_t *mask = (const uint32_t *)(c.regb + BG_B_RUNMASK);
+    uint16_t *items = (uint16_t *)(c.regb + BG_B_ITEMS);
+    uint32_t *pfreq = (uint32_t *)(c.regb + BG_B_PFREQ);
+    for (uint32_t i = t; i < total; i += T) {
+        if (!((mask[i >> 5] >> (i & 31u)) & 1u)) continue;
+        const uint32_t v = bg_hdr_len_at(c, i, nl);
+        uint32_t run = bg_hdr_run_len(c, i, total), ni = off[i];
+        if (v == 0) {
+            while (run >= 11) {
+                const uint32_t r = run > 138 ? 138 : run;
+                items[ni++] = (uint16_t)(18 | ((r - 11) << 5));
+                bg_add32(&pfreq[18], 1);
+                run -= r;
+            }
+            if (run >= 3) {
+                items[ni++] = (uint16_t)(17 | ((run - 3) << 5));
+                bg_add32(&pfreq[17], 1);
+                run = 0;
+            }
+        } else {
+            items[ni++] = (uint16_t)v;
+            bg_add32(&pfreq[v], 1);
+            run--;
+            while (run >= 3) {
+                const uint32_t r = run > 6 ? 6 : run;
+                items[ni++] = (uint16_t)(16 | ((r - 3) << 5));
+                bg_add32(&pfreq[16], 1);
+                run -= r;
+            }
+        }
+        if (run) bg_add32(&pfreq[v], run);
+        while (run > 0) { items[ni++] = (uint16_t)v; run--; }
+    }
+}
+
+BG_HD void bg_phase_hdr5(const BgCtx &c, uint32_t t, uint32_t T, uint32_t nitems)
+{
+    (void)T;
     if (t != 0) return;
-    uint32_t *pfreq = (uint32_t *)(rb + BG_B_PFREQ);
+    uint8_t *rb = c.regb;
+    uint32_t nl, nd;
+    bg_hdr_dims(c, &nl, &nd);
+    const uint32_t *pfreq = (const uint32_t *)(rb + BG_B_PFREQ);
     uint8_t *plen = rb + BG_B_PLEN;
-    uint16_t *items = (uint16_t *)(rb + BG_B_ITEMS);
-    uint32_t *scratch = (uint32_t *)(rb + BG_B_SCRATCH);
-    uint32_t nl = 286, nd = 30;
-    while (nl > 257 && llen[nl - 1] == 0) nl--;
-    while (nd > 1 && dlen[nd - 1] == 0) nd--;
-    const uint32_t ni = bg_header_items(llen, nl, dlen, nd, items, pfreq);
     uint32_t *pkeys = (uint32_t *)(rb + BG_B_PKEYS);
     for (uint32_t i = 0; i < 19; i++) plen[i] = 0;
     const uint32_t pm = bg_small_keys(pfreq, 19, pkeys);
-    bg_huff_lengths(pkeys, pm, 7, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP), scratch, plen);
+    bg_huff_lengths(pkeys, pm, 7, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP), (uint32_t *)(rb + BG_B_SCRATCH) + 16, plen);
     uint32_t np = 19;
     while (np > 4 && plen[bg_precode_order(np - 1)] == 0) np--;
     uint32_t hdr = 3 + 5 + 5 + 4 + 3 * np;
     for (uint32_t i = 0; i < 19; i++)
         hdr += pfreq[i] * (plen[i] + (i == 16 ? 2u : i == 17 ? 3u : i == 18 ? 7u : 0u));
     c.scal[BG_S_DYNHDR] = hdr;
-    c.scal[BG_S_NITEMS] = ni;
+    c.scal[BG_S_NITEMS] = nitems;
     c.scal[BG_S_NL] = nl;
     c.scal[BG_S_ND] = nd;
     c.scal[BG_S_NP] = np;

@@ -310,11 +310,16 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         PROF_MARK(4);
         bg_phase_accept(c, t, T);
         __syncthreads();
+        PROF_MARK(15);
         bg_phase_jump(c, t, T);
         __syncthreads();
         PROF_MARK(5);
-        bg_phase_walk_a(c, t, T);
+        bg_phase_walk_clear(c, t, T);
         bg_phase_clear_freq(c, t, T);
+        __syncthreads();
+        bg_phase_walk_mark(c, t, T);
+        __syncthreads();
+        bg_phase_walk_a(c, t, T);
         __syncthreads();
         bg_phase_walk_b(c, t, T);
         __syncthreads();
@@ -327,10 +332,22 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         __syncthreads();
         PROF_MARK(7);
         bitonic_sort_512((uint32_t *)(c.regb + BG_B_KEYS), t);
+        PROF_MARK(11);
         bg_phase_huff(c, t, T);
         __syncthreads();
-        bg_phase_decide_a(c, t, T);
+        PROF_MARK(12);
+        bg_phase_hdr1(c, t, T);
         __syncthreads();
+        bg_phase_hdr2(c, t, T);
+        __syncthreads();
+        bg_phase_hdr3(c, t, T);
+        __syncthreads();
+        const uint32_t nitems = block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_CBITS), scan_scratch, t);
+        bg_phase_hdr4(c, t, T);
+        __syncthreads();
+        bg_phase_hdr5(c, t, T, nitems);
+        __syncthreads();
+        PROF_MARK(13);
         bg_phase_decide_b(c, t, T);
         __syncthreads();
         bg_phase_codes_a(c, t, T);
@@ -345,6 +362,7 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_CBITS), scan_scratch, t);
         bg_phase_zero_out(c, t, T);
         __syncthreads();
+        PROF_MARK(14);
         bg_phase_emit(c, t, T);
         if (t == 0) {
             const uint32_t st = c.scal[BG_S_STATUS];

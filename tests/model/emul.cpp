@@ -80,6 +80,8 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     run(bg_phase_search, c, order, k++);
     run(bg_phase_accept, c, order, k++);
     run(bg_phase_jump, c, order, k++);
+    run(bg_phase_walk_clear, c, order, k++);
+    run(bg_phase_walk_mark, c, order, k++);
     run(bg_phase_walk_a, c, order, k++);
     run(bg_phase_walk_b, c, order, k++);
     run(bg_phase_walk_c, c, order, k++);
@@ -92,7 +94,24 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
         std::sort(keys, keys + 512);
     }
     run(bg_phase_huff, c, order, k++);
-    run(bg_phase_decide_a, c, order, k++);
+    run(bg_phase_hdr1, c, order, k++);
+    run(bg_phase_hdr2, c, order, k++);
+    run(bg_phase_hdr3, c, order, k++);
+    uint32_t nitems = 0;
+    {   // twin of the kernel's block-wide exclusive scan
+        uint32_t *cb = (uint32_t *)(c.regb + BG_B_CBITS);
+        for (uint32_t i = 0; i < BG_MAX_CHUNKS; i++) { uint32_t v = cb[i]; cb[i] = nitems; nitems += v; }
+    }
+    run(bg_phase_hdr4, c, order, k++);
+    for (uint32_t t = 0; t < BG_THREADS; t++) bg_phase_hdr5(c, t, BG_THREADS, nitems);
+    {   // cross-check against the sequential rule
+        static uint16_t ref_items[400]; uint32_t ref_pf[19];
+        uint32_t ni = bg_header_items(c.regb + BG_B_LLEN, c.scal[BG_S_NL], c.regb + BG_B_DLEN, c.scal[BG_S_ND], ref_items, ref_pf);
+        if (ni != nitems || memcmp(ref_items, c.regb + BG_B_ITEMS, ni * 2) || memcmp(ref_pf, c.regb + BG_B_PFREQ, 19 * 4)) {
+            fprintf(stderr, "emul: parallel header items differ from the sequential rule (%u vs %u)\n", nitems, ni);
+            return -4;
+        }
+    }
     run(bg_phase_decide_b, c, order, k++);
     run(bg_phase_codes_a, c, order, k++);
     run(bg_phase_codes_b, c, order, k++);

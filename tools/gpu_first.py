@@ -54,6 +54,7 @@ prof = c.profile(False, True)
 tot = sum(prof[:10]) or 1
 names = ["load", "crc+census", "hash", "build-peers", "search", "accept+jump", "walk", "tally", "huffman", "sizes+emit"]
 nblk = (64 << 20) / 0xff00
-print("cycles/block %.0f  build-link %.0f" % ((tot + prof[10]) / nblk, prof[10] / nblk))
+print("cycles/block %.0f  build-link %.0f" % (sum(prof) / nblk, prof[10] / nblk))
 print("  ".join(f"{n}={p / nblk:.0f}" for n, p in zip(names, prof[:10])))
+print("  detail: sort=%.0f trees=%.0f header=%.0f codes=%.0f | accept=%.0f jump=%.0f | sizes+scan+zero=%.0f emit=%.0f" % tuple(x / nblk for x in (prof[11], prof[12], prof[13], prof[8], prof[15], prof[5], prof[14], prof[9])))
 print("launches", c.launches())
