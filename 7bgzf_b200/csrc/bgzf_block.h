@@ -443,8 +443,8 @@ BG_HD bool bg_search_step(const BgCtx &c, BgSearch &s)
 
 BG_HD uint32_t bg_search_result(const BgSearch &s) { return s.best > 3 ? (s.best << 16) | s.boff : 0; }
 
-/* the same search as a plain loop (what the kernel runs: cheaper per candidate than the step machine) */
-BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
+/* the same search as a plain loop, exact (every candidate fully verified) */
+BG_HD uint32_t bg_search_one_exact(const BgCtx &c, uint32_t p)
 {
     const uint32_t n = c.n;
     uint32_t maxl = n - p;
@@ -477,6 +477,52 @@ BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
         if (q == BG_NOPOS || p - q > 32768u) break;
     }
     return best > 3 ? (best << 16) | boff : 0;
+}
+
+/* What the kernel runs.  Chain members share p's hash, i.e. (collisions aside) its first `skip` bytes, so those
+ * bytes are not compared candidate by candidate: lengths are measured from `skip` on and only the winner's
+ * prefix is verified, once.  In the (rare) event that it does not match, the exact search above decides, so
+ * the result is always the exact one. */
+BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
+{
+    const uint32_t n = c.n;
+    uint32_t maxl = n - p;
+    if (maxl > 258) maxl = 258;
+    const uint32_t skip = c.scal[BG_S_HBYTES] & ~3u;         /* 8 or 4: whole words inside the hash window */
+    if (maxl < skip + 1) return bg_search_one_exact(c, p);   /* block tail: nothing to gain */
+    uint32_t q = c.prev[p];
+    if (q == BG_NOPOS || p - q > 32768u) return 0;
+    const uint32_t *dw = c.dataw;
+    uint32_t best = 0, boff = 0, ptail = 0;
+    int depth = c.prm.depth;
+    const uint32_t nice = (uint32_t)c.prm.nice;
+    for (;;) {
+        uint32_t qn = c.prev[q];                             /* next link: in flight during the comparisons */
+        if (best == 0 || bg_ld32(dw, q + best - 3) == ptail) {
+            uint32_t l = skip;
+            while (l < maxl) {
+                const uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
+                if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
+                l += 4;
+            }
+            if (l > maxl) l = maxl;
+            if (l > best) {
+                best = l;
+                boff = p - q;
+                if (l >= nice || l == maxl) break;
+                ptail = bg_ld32(dw, p + best - 3);
+            }
+        }
+        if (--depth <= 0) break;
+        q = qn;
+        if (q == BG_NOPOS || p - q > 32768u) break;
+    }
+    /* verify the winner's unchecked prefix */
+    const uint32_t qb = p - boff;
+    bool ok = bg_ld32(dw, qb) == bg_ld32(dw, p);
+    if (skip == 8) ok = ok && bg_ld32(dw, qb + 4) == bg_ld32(dw, p + 4);
+    if (!ok) return bg_search_one_exact(c, p);
+    return (best << 16) | boff;
 }
 
 /* step-machine twin (kept for the emulator's cross-check of both formulations) */
