@@ -1,8 +1,9 @@
 /*
  * bgzf_inflate.cu — sm_100a BGZF inflate kernels.
  *
- *   bgzf_inflate_kernel : one CTA (= one warp) per BGZF member, ~9 KiB of shared memory each, so ~24 members
- *       decode concurrently per SM.  All 32 lanes run the bit reader in lock-step (uniform control flow,
+ *   bgzf_inflate_kernel : one CTA (= one warp) per BGZF member, ~10 KiB of shared memory each, so ~22 members
+ *       decode concurrently per SM; the last 2 KiB of output live in a shared-memory window (near back-references
+ *       never leave the SM, output leaves as whole 128-byte lines).  All 32 lanes run the bit reader in lock-step (uniform control flow,
  *       broadcast LUT reads); the compressed bytes arrive as coalesced 128-byte chunks, one word per lane,
  *       and are handed to the reader with __shfl_sync; back-references are copied by all lanes.
  *       Table-driven Huffman decode from shared-memory LUTs: 10-bit root + sub-tables for the litlen code,
@@ -36,6 +37,8 @@
 #define K_BASE 2u
 #define K_EOB 3u
 #define K_SUB 4u
+#define F_LIT 0x8000u    /* literal entry (also set on LIT2) */
+#define F_LIT2 0x4000u   /* two literals: value = lit1 | lit2 << 8, [3:0] total bits, [7:4] bits of the first */
 #define ENT(nb, xb, kind, sb, val) ((uint32_t)(nb) | ((uint32_t)(xb) << 4) | ((uint32_t)(kind) << 8) | ((uint32_t)(sb) << 11) | ((uint32_t)(val) << 16))
 
 /* per-member error codes (status[]) */
@@ -49,30 +52,85 @@
 #define INF_E_STORED 7u     /* LEN != ~NLEN */
 #define INF_E_SHORT 8u      /* output shorter than ISIZE */
 
+#define INF_WIN 2048u            /* bytes of recent output kept in shared memory per member (power of two) */
+
 struct InfSmem {
     uint32_t ltab[INF_LTAB];
-    uint32_t dtab[INF_DTAB];
-    uint32_t ptab[INF_PTAB];
+    uint32_t dtab[INF_DTAB];      /* the precode table (128 entries) borrows the start of this while lengths are read */
     uint32_t offs[16];
     uint8_t lens[320 + 16];
+    uint32_t win[INF_WIN / 4];    /* circular window of the output, indexed by absolute address & (INF_WIN-1) */
 };
 
+/* Output side of the decoder.  Every byte is first written to the shared-memory window (so that near
+ * back-references cost a shared-memory read, not an L2 round trip) and leaves for global memory as whole
+ * 128-byte lines, one 4-byte store per lane, as soon as a line is complete.  `apos` counts bytes from the
+ * 128-byte-aligned address at or below the member's first output byte. */
+struct OutWin {
+    uint8_t *gline;      /* 128-byte aligned global base (gline + apos = address of output byte) */
+    uint8_t *win;
+    uint32_t first;      /* apos of the member's first byte (0..127) */
+    uint32_t apos;       /* apos of the next byte to produce */
+    uint32_t flushed;    /* lines below this index are in global memory */
+    uint32_t lane;
+};
+
+__device__ __forceinline__ void ow_flush_lines(OutWin &o, uint32_t upto_line)
+{
+    /* lines [flushed, upto_line) are complete in the window */
+    for (uint32_t L = o.flushed; L < upto_line; L++) {
+        const uint32_t a = L * 128u + o.lane * 4u;
+        const uint32_t v = *(const uint32_t *)(o.win + (a & (INF_WIN - 1u)));
+        if (a >= o.first) {
+            *(uint32_t *)(o.gline + a) = v;                /* whole word belongs to this member */
+        } else if (a + 4 > o.first) {
+            for (uint32_t k = o.first - a; k < 4; k++) o.gline[a + k] = (uint8_t)(v >> (8 * k));   /* ragged first word */
+        }
+    }
+    o.flushed = upto_line;
+}
+
+__device__ __forceinline__ void ow_advance(OutWin &o, uint32_t nbytes)
+{
+    o.apos += nbytes;
+    const uint32_t complete = o.apos >> 7;
+    if (complete != o.flushed) {
+        __syncwarp();
+        ow_flush_lines(o, complete);
+    }
+}
+
+/* the tail that never completed a line */
+__device__ __forceinline__ void ow_finish(OutWin &o)
+{
+    __syncwarp();
+    const uint32_t base = o.flushed * 128u;
+    for (uint32_t a = (base > o.first ? base : o.first) + o.lane; a < o.apos; a += 32)
+        o.gline[a] = o.win[a & (INF_WIN - 1u)];
+}
+
+/* Bit reader: all 32 lanes hold identical state.  The stream is fetched as coalesced 128-byte chunks (one word per
+ * lane) and handed out with __shfl_sync; the reader keeps two consecutive words in registers and exposes the next
+ * 32 bits of the stream with one funnel shift (no 64-bit arithmetic on the decode path). */
 struct BitReader {
     const uint32_t *base;   /* word-aligned start */
-    uint32_t nwords;        /* words that may be read */
-    uint32_t chunk;         /* this lane's word of the current 32-word chunk */
-    uint32_t wpos;          /* index of the next word to hand out */
-    uint64_t bb;            /* bit buffer */
-    uint32_t bc;            /* valid bits */
+    uint32_t nwords;        /* words that may be read (beyond: zeros) */
+    uint32_t chunk;         /* this lane's word of the chunk that holds word wi+1 */
     uint32_t lane;
+    uint32_t w0, w1;        /* words wi and wi+1 */
+    uint32_t wi;
+    uint32_t bit;           /* next unread bit inside w0, 0..31 */
     uint32_t skip;          /* bits of the first word that precede the start */
     uint32_t avail;         /* real input bits from the start to the end of the DEFLATE data */
 };
 
-__device__ __forceinline__ void br_load_chunk(BitReader &r)
+__device__ __forceinline__ uint32_t br_fetch(BitReader &r, uint32_t idx)
 {
-    const uint32_t idx = (r.wpos & ~31u) + r.lane;
-    r.chunk = idx < r.nwords ? __ldg(r.base + idx) : 0u;
+    if ((idx & 31u) == 0u || idx == 0u) {
+        const uint32_t i = (idx & ~31u) + r.lane;
+        r.chunk = i < r.nwords ? __ldg(r.base + i) : 0u;
+    }
+    return __shfl_sync(0xffffffffu, r.chunk, idx & 31u);
 }
 
 __device__ __forceinline__ void br_init(BitReader &r, const uint8_t *p, const uint8_t *end, uint32_t lane)
@@ -83,40 +141,39 @@ __device__ __forceinline__ void br_init(BitReader &r, const uint8_t *p, const ui
     r.lane = lane;
     r.skip = 8 * mis;
     r.avail = (uint32_t)(end - p) * 8u;
-    r.wpos = 0;
-    br_load_chunk(r);
-    const uint32_t w0 = __shfl_sync(0xffffffffu, r.chunk, 0);
-    r.wpos = 1;
-    r.bb = (uint64_t)(w0 >> (8 * mis));
-    r.bc = 32 - 8 * mis;
+    r.wi = 0;
+    r.bit = r.skip;
+    r.w0 = br_fetch(r, 0);
+    r.w1 = br_fetch(r, 1);
 }
 
-/* make sure at least 33 bits are buffered */
-__device__ __forceinline__ void br_refill(BitReader &r)
+/* the next 32 bits of the stream */
+__device__ __forceinline__ uint32_t br_window(const BitReader &r) { return __funnelshift_r(r.w0, r.w1, r.bit); }
+
+/* n <= 32 */
+__device__ __forceinline__ void br_consume(BitReader &r, uint32_t n)
 {
-    if (r.bc <= 32) {
-        if ((r.wpos & 31u) == 0) br_load_chunk(r);
-        const uint32_t w = __shfl_sync(0xffffffffu, r.chunk, r.wpos & 31u);
-        r.wpos++;
-        r.bb |= (uint64_t)w << r.bc;
-        r.bc += 32;
+    r.bit += n;
+    if (r.bit >= 32u) {
+        r.bit -= 32u;
+        r.w0 = r.w1;
+        r.wi++;
+        r.w1 = br_fetch(r, r.wi + 1);
     }
 }
-__device__ __forceinline__ uint32_t br_peek(const BitReader &r, uint32_t n) { return (uint32_t)r.bb & ((1u << n) - 1u); }
-__device__ __forceinline__ void br_drop(BitReader &r, uint32_t n) { r.bb >>= n; r.bc -= n; }
 __device__ __forceinline__ uint32_t br_take(BitReader &r, uint32_t n)
 {
-    uint32_t v = br_peek(r, n);
-    br_drop(r, n);
+    const uint32_t v = br_window(r) & ((n >= 32u) ? 0xffffffffu : ((1u << n) - 1u));
+    br_consume(r, n);
     return v;
 }
 /* true once more bits were consumed than the member holds (the reference's overread check,
  * decompress_template.h: "overread_count <= bitsleft>>3") */
-__device__ __forceinline__ bool br_overrun(const BitReader &r) { return r.wpos * 32u - r.skip - r.bc > r.avail; }
+__device__ __forceinline__ bool br_overrun(const BitReader &r) { return r.wi * 32u + r.bit - r.skip > r.avail; }
 
 __device__ __forceinline__ uint32_t litlen_entry(uint32_t sym, uint32_t nb)
 {
-    if (sym < 256) return ENT(nb, 0, K_LIT, 0, sym);
+    if (sym < 256) return ENT(nb, 0, K_LIT, 0, sym) | F_LIT;
     if (sym == 256) return ENT(nb, 0, K_EOB, 0, 0);
     if (sym > 285) sym = 285;   /* 286/287 decode as length 258, as in the reference's litlen_decode_results */
     const uint32_t s = sym - 257;
@@ -242,14 +299,37 @@ __device__ bool build_table(const uint8_t *lens, uint32_t nsym, uint32_t root, u
     return true;
 }
 
-__device__ __forceinline__ uint32_t lookup(const uint32_t *tab, uint32_t root, BitReader &r)
+/* Root entries whose literal leaves room for a second literal inside the root index get both: the decoder then
+ * emits two bytes per lookup on literal runs (most of FASTQ/SAM text under a long-match parse is literals).
+ * A paired entry still carries its first literal and that literal's length, so lanes may read entries that
+ * other lanes have already paired. */
+__device__ void pair_literals(uint32_t *tab, uint32_t root, uint32_t lane)
 {
-    uint32_t e = tab[br_peek(r, root)];
-    if (((e >> 8) & 7u) == K_SUB) {
-        br_drop(r, root);
-        e = tab[(e >> 16) + br_peek(r, (e >> 11) & 31u)];
+    for (uint32_t i = lane; i < (1u << root); i += 32) {
+        const uint32_t e1 = tab[i];
+        if (!(e1 & F_LIT)) continue;
+        const uint32_t nb1 = (e1 & F_LIT2) ? ((e1 >> 4) & 15u) : (e1 & 15u);
+        if (nb1 >= root) continue;
+        const uint32_t e2 = tab[i >> nb1];
+        if (!(e2 & F_LIT)) continue;
+        const uint32_t nb2 = (e2 & F_LIT2) ? ((e2 >> 4) & 15u) : (e2 & 15u);
+        if (nb1 + nb2 > root) continue;      /* the second codeword must lie wholly inside the index bits */
+        const uint32_t lit1 = (e1 >> 16) & 0xffu, lit2 = (e2 >> 16) & 0xffu;
+        tab[i] = (nb1 + nb2) | (nb1 << 4) | (K_LIT << 8) | F_LIT | F_LIT2 | ((lit1 | (lit2 << 8)) << 16);
     }
-    br_drop(r, e & 15u);
+    __syncwarp();
+}
+
+/* decode one symbol from the 32-bit window; *nb = codeword bits (root + sub-table part) */
+__device__ __forceinline__ uint32_t lookup(const uint32_t *tab, uint32_t root, uint32_t win, uint32_t *nb)
+{
+    uint32_t e = tab[win & ((1u << root) - 1u)];
+    uint32_t used = 0;
+    if (((e >> 8) & 7u) == K_SUB) {
+        e = tab[(e >> 16) + ((win >> root) & ((1u << ((e >> 11) & 31u)) - 1u))];
+        used = root;
+    }
+    *nb = used + (e & 15u);
     return e;
 }
 
@@ -281,26 +361,32 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
 
     BitReader r;
     br_init(r, mem + 18, trailer, lane);
-    uint32_t pos = 0;
+    OutWin o;
+    o.first = (uint32_t)((uintptr_t)out & 127u);
+    o.gline = out - o.first;
+    o.win = (uint8_t *)sm.win;
+    o.apos = o.first;
+    o.flushed = 0;
+    o.lane = lane;
+    const uint32_t end_apos = o.first + isize;
     bool last = false;
     while (!last && err == INF_OK) {
-        br_refill(r);
         last = br_take(r, 1);
         const uint32_t btype = br_take(r, 2);
         if (btype == 0) {
             /* stored: drop to a byte boundary, LEN, NLEN, raw bytes */
-            br_drop(r, r.bc & 7u);
-            br_refill(r);
+            br_consume(r, (8u - (r.bit & 7u)) & 7u);
             const uint32_t len = br_take(r, 16);
-            br_refill(r);
             const uint32_t nlen = br_take(r, 16);
             if ((len ^ nlen) != 0xffffu) { err = INF_E_STORED; break; }
-            if (pos + len > isize) { err = INF_E_OVERRUN; break; }
-            /* the raw bytes start (bc/8) bytes before the next unread word */
-            const uint8_t *raw = (const uint8_t *)(r.base + r.wpos) - (r.bc >> 3);
+            if (o.apos + len > end_apos) { err = INF_E_OVERRUN; break; }
+            const uint8_t *raw = (const uint8_t *)(r.base + r.wi) + (r.bit >> 3);
             if (raw + len > trailer) { err = INF_E_OVERRUN; break; }
-            for (uint32_t i = lane; i < len; i += 32) out[pos + i] = raw[i];
-            pos += len;
+            for (uint32_t done = 0; done < len; done += 32) {
+                const uint32_t k = done + lane;
+                if (k < len) o.win[(o.apos + lane) & (INF_WIN - 1u)] = raw[k];
+                ow_advance(o, len - done < 32 ? len - done : 32);
+            }
             __syncwarp();
             if (!last) br_init(r, raw + len, trailer, lane);
             continue;
@@ -312,26 +398,24 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
             __syncwarp();
             if (!build_table(sm.lens, 288, INF_LROOT, sm.ltab, INF_LTAB, 0, sm.offs, lane) ||
                 !build_table(sm.lens + 288, 32, INF_DROOT, sm.dtab, INF_DTAB, 1, sm.offs, lane)) { err = INF_E_CODE; break; }
+            pair_literals(sm.ltab, INF_LROOT, lane);
         } else {
-            br_refill(r);
             const uint32_t nl = br_take(r, 5) + 257, nd = br_take(r, 5) + 1, np = br_take(r, 4) + 4;
             if (lane < 19) sm.lens[lane] = 0;
             __syncwarp();
             for (uint32_t i = 0; i < np; i++) {
-                br_refill(r);
                 const uint32_t v = br_take(r, 3);
                 if (lane == 0) sm.lens[bg_precode_order(i)] = (uint8_t)v;
             }
             __syncwarp();
-            if (!build_table(sm.lens, 19, 7, sm.ptab, INF_PTAB, 2, sm.offs, lane)) { err = INF_E_CODE; break; }
+            if (!build_table(sm.lens, 19, 7, sm.dtab, INF_PTAB, 2, sm.offs, lane)) { err = INF_E_CODE; break; }
             /* code lengths for litlen + offset, run-length coded */
             uint32_t i = 0, prevlen = 0;
             const uint32_t total = nl + nd;
             while (i < total) {
-                br_refill(r);
-                const uint32_t e = sm.ptab[br_peek(r, 7)];
+                const uint32_t e = sm.dtab[br_window(r) & 127u];
                 if (e == 0) { err = INF_E_SYMBOL; break; }
-                br_drop(r, e & 15u);
+                br_consume(r, e & 15u);
                 const uint32_t sym = e >> 16;
                 uint32_t rep, val;
                 if (sym < 16) { rep = 1; val = sym; prevlen = sym; }
@@ -347,43 +431,69 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
             /* the offset lengths follow the litlen lengths; move them to a 16-byte-friendly spot for the builder */
             if (!build_table(sm.lens, nl, INF_LROOT, sm.ltab, INF_LTAB, 0, sm.offs, lane) ||
                 !build_table(sm.lens + nl, nd, INF_DROOT, sm.dtab, INF_DTAB, 1, sm.offs, lane)) { err = INF_E_CODE; break; }
+            pair_literals(sm.ltab, INF_LROOT, lane);
         }
         /* ---- the decode loop ---- */
         for (;;) {
-            br_refill(r);
-            const uint32_t e = lookup(sm.ltab, INF_LROOT, r);
-            const uint32_t kind = (e >> 8) & 7u;
-            if (kind == K_LIT) {
-                if (pos >= isize) { err = INF_E_OVERRUN; break; }
-                if (lane == 0) out[pos] = (uint8_t)(e >> 16);
-                pos++;
+            uint32_t win = br_window(r);
+            uint32_t e = sm.ltab[win & ((1u << INF_LROOT) - 1u)];
+            uint32_t nb = e & 15u;
+            if (!(e & F_LIT) && ((e >> 8) & 7u) == K_SUB) {
+                e = sm.ltab[(e >> 16) + ((win >> INF_LROOT) & ((1u << ((e >> 11) & 7u)) - 1u))];
+                nb = INF_LROOT + (e & 15u);
+            }
+            if (e & F_LIT) {
+                if (o.apos >= end_apos) { err = INF_E_OVERRUN; break; }
+                uint32_t cnt = 1;
+                if (e & F_LIT2) {
+                    if (o.apos + 2 <= end_apos) cnt = 2; else nb = (e >> 4) & 15u;
+                }
+                br_consume(r, nb);
+                if (lane < cnt) o.win[(o.apos + lane) & (INF_WIN - 1u)] = (uint8_t)(e >> (16 + 8 * lane));
+                ow_advance(o, cnt);
                 continue;
             }
-            if (kind == K_EOB) break;
+            const uint32_t kind = (e >> 8) & 7u;
+            if (kind == K_EOB) { br_consume(r, nb); break; }
             if (kind != K_BASE) { err = INF_E_SYMBOL; break; }
-            const uint32_t len = (e >> 16) + br_take(r, (e >> 4) & 15u);
-            br_refill(r);
-            const uint32_t d = lookup(sm.dtab, INF_DROOT, r);
+            const uint32_t xb = (e >> 4) & 15u;
+            const uint32_t len = (e >> 16) + ((win >> nb) & ((1u << xb) - 1u));
+            br_consume(r, nb + xb);
+            win = br_window(r);
+            const uint32_t d = lookup(sm.dtab, INF_DROOT, win, &nb);
             if (((d >> 8) & 7u) != K_BASE) { err = INF_E_SYMBOL; break; }
-            const uint32_t dist = (d >> 16) + br_take(r, (d >> 4) & 15u);
-            if (dist > pos) { err = INF_E_DIST; break; }
-            if (pos + len > isize) { err = INF_E_OVERRUN; break; }
-            if (br_overrun(r)) { err = INF_E_OVERRUN; break; }
-            __syncwarp();   /* earlier stores of this warp are visible to all its lanes */
-            const uint8_t *srcp = out + pos - dist;
-            if (dist >= len) {
-                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(srcp + k);
-            } else if (dist == 1) {
-                const uint8_t v = __ldcg(srcp);
-                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = v;
+            const uint32_t dxb = (d >> 4) & 15u;
+            const uint32_t dist = (d >> 16) + ((win >> nb) & ((1u << dxb) - 1u));
+            br_consume(r, nb + dxb);
+            if (dist > o.apos - o.first) { err = INF_E_DIST; break; }
+            if (o.apos + len > end_apos) { err = INF_E_OVERRUN; break; }
+            __syncwarp();   /* earlier window/global stores of this warp are visible to all its lanes */
+            if (dist + len <= INF_WIN) {
+                /* near: the source is still in the window.  Bytes are produced 32 at a time; with an overlapping
+                 * copy (dist < len) byte k repeats byte k mod dist, which is always older than this match. */
+                for (uint32_t done = 0; done < len; done += 32) {
+                    const uint32_t k = done + lane;
+                    if (k < len) {
+                        const uint32_t sk = dist >= len ? k : (dist == 1 ? 0u : k % dist);
+                        const uint8_t v = o.win[(o.apos - done - dist + sk) & (INF_WIN - 1u)];
+                        o.win[(o.apos + lane) & (INF_WIN - 1u)] = v;
+                    }
+                    ow_advance(o, len - done < 32 ? len - done : 32);
+                }
             } else {
-                for (uint32_t k = lane; k < len; k += 32) out[pos + k] = __ldcg(srcp + (k % dist));
+                /* far: dist > INF_WIN - 258, so the source lies in lines that were flushed long ago */
+                const uint8_t *srcp = o.gline + o.apos - dist;
+                for (uint32_t done = 0; done < len; done += 32) {
+                    const uint32_t k = done + lane;
+                    if (k < len) o.win[(o.apos + lane) & (INF_WIN - 1u)] = __ldcg(srcp + k);
+                    ow_advance(o, len - done < 32 ? len - done : 32);
+                }
             }
-            pos += len;
         }
         if (br_overrun(r) && err == INF_OK) err = INF_E_OVERRUN;
     }
-    if (err == INF_OK && pos != isize) err = INF_E_SHORT;
+    ow_finish(o);
+    if (err == INF_OK && o.apos != end_apos) err = INF_E_SHORT;
     if (lane == 0) {
         a.status[m] = err;
         if (err) atomicOr(a.err_flag, 1u);
