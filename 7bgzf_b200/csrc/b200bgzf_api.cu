@@ -34,7 +34,7 @@ struct Lane {
     uint32_t cap_blocks = 0;
     size_t in_cap = 0, out_cap = 0, host_in_cap = 0, host_out_cap = 0, meta_cap = 0;
     uint8_t *d_in = nullptr, *d_slots = nullptr, *d_out = nullptr;
-    uint32_t *d_len = nullptr, *d_status = nullptr, *d_scratch = nullptr;
+    uint32_t *d_len = nullptr, *d_status = nullptr, *d_scratch = nullptr, *d_cand = nullptr;
     uint64_t *d_off = nullptr, *d_inoff = nullptr, *d_outoff = nullptr;
     uint32_t *d_inlen = nullptr;
     uint64_t *d_total = nullptr;   /* [0] running stream size, [1] error flags, [2..3] spare */
@@ -103,7 +103,7 @@ cudaError_t grow(T **p, size_t *cap, size_t need, bool pinned = false)
 void lane_free(Lane &l)
 {
     cudaFree(l.d_in); cudaFree(l.d_slots); cudaFree(l.d_out); cudaFree(l.d_len); cudaFree(l.d_status);
-    cudaFree(l.d_scratch); cudaFree(l.d_off); cudaFree(l.d_inoff); cudaFree(l.d_outoff); cudaFree(l.d_inlen);
+    cudaFree(l.d_scratch); cudaFree(l.d_cand); cudaFree(l.d_off); cudaFree(l.d_inoff); cudaFree(l.d_outoff); cudaFree(l.d_inlen);
     cudaFree(l.d_total);
     if (l.h_total) cudaFreeHost(l.h_total);
     if (l.h_in) cudaFreeHost(l.h_in);
@@ -162,6 +162,10 @@ int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint6
         a.out_len = l.d_len;
         a.status = l.d_status;
         a.scratch = l.d_scratch;
+        if (a.prm.opt_passes > 0) {
+            if (!l.d_cand) CK(cudaMalloc((void **)&l.d_cand, (size_t)l.scratch_ctas * 4u * BG_MAX_BLOCK * sizeof(uint32_t)));
+            a.cand = l.d_cand;
+        }
         a.crctab = ctx->d_crctab;
         a.crcpow = ctx->d_crcpow;
         a.err_flag = (uint32_t *)(l.d_total + 1);

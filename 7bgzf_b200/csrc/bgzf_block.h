@@ -89,10 +89,12 @@ struct BgParams {
     int lazy;         /* 0 greedy, 1 one-ahead, 2 two-ahead */
     int passthrough;  /* inputs this short are stored (reference: 55 - 4*level) */
     int hlong;        /* hash window (bytes) when short matches do not pay (few distinct literals): 8 or 5 */
+    int opt_passes;   /* > 0: near-optimal class (levels 10-12): that many min-cost-path passes after the lazy parse */
 };
 
 /* level 1..12 -> search effort; the classes follow libdeflate_alloc_compressor_ex (deflate_compress.c:3921-4007):
- * 1-4 greedy, 5-7 lazy, 8-12 lazy2.  The numbers are this codec's own: on low-entropy text (FASTQ/SAM) an 8-byte
+ * 1-4 greedy, 5-7 lazy, 8-9 lazy2, 10-12 near-optimal (lazy2 first, then min-cost-path passes over up to four
+ * matches per position, the role of deflate_compress_near_optimal :3593-3850 / deflate_find_min_cost_path :3328-3400).  The numbers are this codec's own: on low-entropy text (FASTQ/SAM) an 8-byte
  * hash with a shallow chain reaches the reference's level-6 size (+1 %) at a fraction of the candidate visits. */
 BG_HD BgParams bg_level_params(int level)
 {
@@ -100,11 +102,12 @@ BG_HD BgParams bg_level_params(int level)
     if (level < 1) level = 1;
     if (level > 12) level = 12;
     p.depth = level <= 4 ? level : level == 5 ? 6 : level == 6 ? 8 : level == 7 ? 16 : level == 8 ? 64 : level == 9 ? 128
-            : level == 10 ? 256 : level == 11 ? 384 : 512;
+            : level == 10 ? 128 : level == 11 ? 256 : 512;
     p.nice = level <= 2 ? 32 : level == 3 ? 48 : level <= 5 ? 64 : level == 6 ? 65 : level == 7 ? 130 : 258;
     p.lazy = level <= 4 ? 0 : level <= 7 ? 1 : 2;
     p.passthrough = 55 - 4 * level;
-    p.hlong = level <= 7 ? 8 : 5;
+    p.hlong = level <= 7 ? 8 : level <= 9 ? 5 : 4;
+    p.opt_passes = level <= 9 ? 0 : level <= 11 ? 3 : 4;
     return p;
 }
 
@@ -120,6 +123,7 @@ struct BgCtx {
     uint32_t *crctab;   /* smem u32[256] */
     uint32_t *scal;     /* smem u32[BG_S_COUNT] */
     uint32_t *R;        /* global scratch u32[BG_MAX_BLOCK+8]: len<<16 | offset per position */
+    uint32_t *cand;     /* global scratch u32[4*BG_MAX_BLOCK] or NULL: up to 4 matches per position (near-optimal class) */
     uint32_t *out;      /* global: this block's output slot, BG_SLOT_BYTES, 16-byte aligned */
     const uint32_t *crcpow; /* global u32[BG_THREADS]: x^(8*4*BG_CRC_WORDS*k) mod P */
     uint32_t n;         /* payload bytes */
@@ -479,6 +483,48 @@ BG_HD uint32_t bg_search_one_exact(const BgCtx &c, uint32_t p)
     return best > 3 ? (best << 16) | boff : 0;
 }
 
+/* near-optimal class: like the exact search, but remembers the last four improvements.  Because the chain runs
+ * from the nearest candidate outwards, lengths and offsets both grow along that list: for any length the
+ * cheapest offset is the entry with the smallest length that still covers it (what bt_matchfinder_get_matches
+ * hands to the reference's optimiser, bt_matchfinder.h:140-340, capped at four entries). */
+BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
+{
+    const uint32_t n = c.n;
+    uint32_t m1 = 0, m2 = 0, m3 = 0, cur = 0;
+    uint32_t maxl = n - p;
+    if (maxl > 258) maxl = 258;
+    uint32_t q = maxl >= (uint32_t)BG_MIN_LOOKUP ? (uint32_t)c.prev[p] : (uint32_t)BG_NOPOS;
+    if (q != BG_NOPOS && p - q <= 32768u) {
+        const uint32_t *dw = c.dataw;
+        uint32_t best = 3, ptail = bg_ld32(dw, p);
+        int depth = c.prm.depth;
+        for (;;) {
+            if (bg_ld32(dw, q + best - 3) == ptail) {
+                uint32_t l = best > 3 ? 0 : 4;
+                while (l < maxl) {
+                    const uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
+                    if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
+                    l += 4;
+                }
+                if (l > maxl) l = maxl;
+                if (l > best) {
+                    best = l;
+                    m3 = m2; m2 = m1; m1 = cur;
+                    cur = (l << 16) | (p - q);
+                    if (l == maxl) break;
+                    ptail = bg_ld32(dw, p + best - 3);
+                }
+            }
+            if (--depth <= 0) break;
+            q = c.prev[q];
+            if (q == BG_NOPOS || p - q > 32768u) break;
+        }
+    }
+    uint32_t *cd = c.cand + 4u * p;
+    cd[0] = cur; cd[1] = m1; cd[2] = m2; cd[3] = m3;
+    return cur;
+}
+
 /* What the kernel runs.  Chain members share p's hash, i.e. (collisions aside) its first `skip` bytes, so those
  * bytes are not compared candidate by candidate: lengths are measured from `skip` on and only the winner's
  * prefix is verified, once.  In the (rare) event that it does not match, the exact search above decides, so
@@ -536,8 +582,97 @@ BG_HD uint32_t bg_search_one_steps(const BgCtx &c, uint32_t p)
 
 BG_HD void bg_phase_search(const BgCtx &c, uint32_t t, uint32_t T)
 {
+    if (c.prm.opt_passes > 0) {
+        for (uint32_t p = t; p < c.n; p += T)
+            c.R[p] = bg_search_one_multi(c, p);
+        return;
+    }
     for (uint32_t p = t; p < c.n; p += T)
         c.R[p] = bg_search_one(c, p);
+}
+
+/* ---- near-optimal class: minimum-cost path ------------------------------------------------------------------ */
+#define BG_DP_OVERLAP 512u        /* a segment's backward pass starts this far past its end, from cost 0 */
+#define BG_DP_RING 512u           /* cost-to-end of the next positions (power of two > 258) */
+#define BG_B_LITCOST BG_B_KEYS            /* u8[256]  bits of literal b                      (sort keys are dead here) */
+#define BG_B_LENCOST (BG_B_KEYS + 256)    /* u8[260]  bits of match length l (symbol + extra) */
+#define BG_B_OFFCOST (BG_B_KEYS + 516)    /* u8[32]   bits of offset slot s (symbol + extra)  */
+
+/* bit costs from the code lengths of the previous parse; unused symbols get a flat guess */
+BG_HD void bg_phase_costs(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    uint8_t *rb = c.regb;
+    const uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN;
+    if (t < 256) rb[BG_B_LITCOST + t] = llen[t] ? llen[t] : 13;
+    if (t >= 3 && t <= 258) {
+        uint32_t nb, ex;
+        const uint32_t sl = bg_len_slot(t, &nb, &ex);
+        rb[BG_B_LENCOST + t] = (uint8_t)((llen[257 + sl] ? llen[257 + sl] : 13) + nb);
+    }
+    if (t < 30) rb[BG_B_OFFCOST + t] = (uint8_t)((dlen[t] ? dlen[t] : 10) + bg_off_slot_extra_bits(t));
+}
+
+/* packed choice: cost << 11 | length << 2 | candidate; the minimum of these picks the cheapest, then the shortest */
+BG_HD uint32_t bg_dp_pack(uint32_t cost, uint32_t len, uint32_t cidx) { return (cost << 11) | (len << 2) | cidx; }
+
+/* One backward step at position p of a segment ending (for this pass) at `e`: best way to code data[p..e).
+ * ring[(q) & 511] holds the cost-to-end of position q for p < q <= p+258.  Sequential formulation. */
+BG_HD uint32_t bg_dp_choose(const BgCtx &c, uint32_t p, uint32_t e, const uint32_t *ring)
+{
+    const uint8_t *rb = c.regb;
+    uint32_t best = bg_dp_pack(rb[BG_B_LITCOST + bg_ld8(c.dataw, p)] + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
+    const uint32_t *cd = c.cand + 4u * p;
+    uint32_t L[4], O[4];
+    for (int k = 0; k < 4; k++) { L[k] = cd[k] >> 16; O[k] = cd[k] & 0xffffu; }
+    uint32_t maxl = e - p;
+    if (L[0] < maxl) maxl = L[0];
+    for (uint32_t l = 3; l <= maxl; l++) {
+        const uint32_t k = l <= L[3] ? 3 : l <= L[2] ? 2 : l <= L[1] ? 1 : 0;
+        uint32_t nb, ex;
+        const uint32_t cost = rb[BG_B_LENCOST + l] + rb[BG_B_OFFCOST + bg_off_slot(O[k], &nb, &ex)] + ring[(p + l) & (BG_DP_RING - 1)];
+        const uint32_t v = bg_dp_pack(cost, l, k);
+        if (v < best) best = v;
+    }
+    return best;
+}
+
+BG_HD void bg_dp_commit(const BgCtx &c, uint32_t p, uint32_t choice)
+{
+    const uint32_t l = (choice >> 2) & 511u, k = choice & 3u;
+    if (l == 1) {
+        c.stepcode[p] = 0;
+    } else {
+        c.stepcode[p] = (uint8_t)(l <= 256 ? l - 2 : 255);
+        c.R[p] = (l << 16) | (c.cand[4u * p + k] & 0xffffu);
+    }
+}
+
+/* segment w of W (one warp each in the kernel): positions [w*S, (w+1)*S) get their decisions; the pass starts
+ * BG_DP_OVERLAP positions later with cost 0 so that the relative costs have settled when it reaches the segment */
+BG_HD void bg_dp_segment_bounds(uint32_t n, uint32_t w, uint32_t W, uint32_t *a, uint32_t *b, uint32_t *e)
+{
+    const uint32_t S = (n + W - 1) / W;
+    *a = w * S < n ? w * S : n;
+    *b = *a + S < n ? *a + S : n;
+    *e = *b + BG_DP_OVERLAP < n ? *b + BG_DP_OVERLAP : n;
+}
+
+/* sequential twin of the kernel's warp-parallel pass (the emulator runs it with one "thread" per segment) */
+BG_HD void bg_phase_dp(const BgCtx &c, uint32_t t, uint32_t T, uint32_t *rings)
+{
+    const uint32_t W = 32;
+    if (t >= W || T < W) return;
+    uint32_t a, b, e;
+    bg_dp_segment_bounds(c.n, t, W, &a, &b, &e);
+    if (a >= b) return;
+    uint32_t *ring = rings + t * BG_DP_RING;
+    ring[e & (BG_DP_RING - 1)] = 0;
+    for (uint32_t p = e; p-- > a;) {
+        const uint32_t choice = bg_dp_choose(c, p, e, ring);
+        ring[p & (BG_DP_RING - 1)] = choice >> 11;
+        if (p < b) bg_dp_commit(c, p, choice);
+    }
 }
 
 /* phase 7: local accept + lazy rule -> stepcode (deflate_compress.c:2664-2670, 2723-2726, 2753-2756 restated

@@ -162,8 +162,63 @@ __device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *no
 /* ---- all-position search: thread t takes positions t, t+1024, ... ---- */
 __device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
 {
+    if (c.prm.opt_passes > 0) {
+        for (uint32_t p = t; p < c.n; p += BG_THREADS)
+            c.R[p] = bg_search_one_multi(c, p);       /* near-optimal class: up to four matches per position */
+        return;
+    }
     for (uint32_t p = t; p < c.n; p += BG_THREADS)
         c.R[p] = bg_search_one(c, p);
+}
+
+/* ---- near-optimal class: one backward min-cost pass, warp w owning segment w.  The candidate lengths of a position
+ * are spread over the lanes (lane j prices lengths 3+j, 35+j, ...), the cheapest is found with a single
+ * redux.min on the packed (cost, length, candidate) word; the four matches of 32 positions are fetched with one
+ * coalesced 16-byte load per lane and handed round with shuffles.  Same arithmetic as bg_phase_dp(). ---- */
+__device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint32_t lane, uint32_t *ring)
+{
+    uint32_t a, b, e;
+    bg_dp_segment_bounds(c.n, w, 32, &a, &b, &e);
+    if (a >= b) return;
+    const uint8_t *rb = c.regb;
+    const uint4 *cand4 = (const uint4 *)c.cand;
+    if (lane == 0) ring[e & (BG_DP_RING - 1)] = 0;
+    __syncwarp();
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    uint32_t tile_top = 0;
+    for (uint32_t p = e; p-- > a;) {
+        if (((e - 1 - p) & 31u) == 0) {                     /* new tile: positions p, p-1, ..., p-31 */
+            tile_top = p;
+            mine = p >= lane ? __ldcg(cand4 + (p - lane)) : make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t src = tile_top - p;
+        const uint32_t c0 = __shfl_sync(0xffffffffu, mine.x, src), c1 = __shfl_sync(0xffffffffu, mine.y, src);
+        const uint32_t c2 = __shfl_sync(0xffffffffu, mine.z, src), c3 = __shfl_sync(0xffffffffu, mine.w, src);
+        /* lane k < 4 prices the offset of candidate k */
+        const uint32_t mycand = lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
+        uint32_t nbx, exx;
+        const uint32_t myoc = (lane < 4 && (mycand & 0xffffu)) ? rb[BG_B_OFFCOST + bg_off_slot(mycand & 0xffffu, &nbx, &exx)] : 0u;
+        const uint32_t oc0 = __shfl_sync(0xffffffffu, myoc, 0), oc1 = __shfl_sync(0xffffffffu, myoc, 1);
+        const uint32_t oc2 = __shfl_sync(0xffffffffu, myoc, 2), oc3 = __shfl_sync(0xffffffffu, myoc, 3);
+        const uint32_t L0 = c0 >> 16, L1 = c1 >> 16, L2 = c2 >> 16, L3 = c3 >> 16;
+        uint32_t maxl = e - p;
+        if (L0 < maxl) maxl = L0;
+        uint32_t best = 0xffffffffu;
+        if (lane == 0)
+            best = bg_dp_pack(rb[BG_B_LITCOST + bg_ld8(c.dataw, p)] + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
+        for (uint32_t l = 3 + lane; l <= maxl; l += 32) {
+            const uint32_t k = l <= L3 ? 3 : l <= L2 ? 2 : l <= L1 ? 1 : 0;
+            const uint32_t oc = k == 3 ? oc3 : k == 2 ? oc2 : k == 1 ? oc1 : oc0;
+            const uint32_t v = bg_dp_pack(rb[BG_B_LENCOST + l] + oc + ring[(p + l) & (BG_DP_RING - 1)], l, k);
+            best = v < best ? v : best;
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0) {
+            ring[p & (BG_DP_RING - 1)] = best >> 11;
+            if (p < b) bg_dp_commit(c, p, best);
+        }
+        __syncwarp();
+    }
 }
 
 /* ---- 512-key bitonic sort in shared memory (ascending); all threads call it ---- */
@@ -242,6 +297,7 @@ bgzf_compress_kernel(BgzfCompressArgs a)
     c.litflag = smem + SM_LITFLAG;
     c.scal = (uint32_t *)(smem + SM_SCAL);
     c.R = a.scratch + (size_t)blockIdx.x * BGZF_SCRATCH_WORDS;
+    c.cand = a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr;
     c.crcpow = a.crcpow;
     c.prm = a.prm;
 
@@ -308,34 +364,42 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         search_positions(c, t);
         __syncthreads();
         PROF_MARK(4);
-        bg_phase_accept(c, t, T);
-        __syncthreads();
-        PROF_MARK(15);
-        bg_phase_jump(c, t, T);
-        __syncthreads();
-        PROF_MARK(5);
-        bg_phase_walk_clear(c, t, T);
-        bg_phase_clear_freq(c, t, T);
-        __syncthreads();
-        bg_phase_walk_mark(c, t, T);
-        __syncthreads();
-        bg_phase_walk_a(c, t, T);
-        __syncthreads();
-        bg_phase_walk_b(c, t, T);
-        __syncthreads();
-        bg_phase_walk_c(c, t, T);
-        __syncthreads();
-        PROF_MARK(6);
-        bg_phase_tally(c, t, T);
-        __syncthreads();
-        bg_phase_lkeys(c, t, T);
-        __syncthreads();
-        PROF_MARK(7);
-        bitonic_sort_512((uint32_t *)(c.regb + BG_B_KEYS), t);
-        PROF_MARK(11);
-        bg_phase_huff(c, t, T);
-        __syncthreads();
-        PROF_MARK(12);
+        for (int pass = 0; pass <= c.prm.opt_passes; pass++) {
+            if (pass == 0) {
+                bg_phase_accept(c, t, T);
+            } else {
+                bg_phase_costs(c, t, T);
+                __syncthreads();
+                dp_segment_warp(c, t >> 5, t & 31u, (uint32_t *)(smem + SM_REGA + 65536u) + (t >> 5) * BG_DP_RING);
+            }
+            __syncthreads();
+            PROF_MARK(15);
+            bg_phase_jump(c, t, T);
+            __syncthreads();
+            PROF_MARK(5);
+            bg_phase_walk_clear(c, t, T);
+            bg_phase_clear_freq(c, t, T);
+            __syncthreads();
+            bg_phase_walk_mark(c, t, T);
+            __syncthreads();
+            bg_phase_walk_a(c, t, T);
+            __syncthreads();
+            bg_phase_walk_b(c, t, T);
+            __syncthreads();
+            bg_phase_walk_c(c, t, T);
+            __syncthreads();
+            PROF_MARK(6);
+            bg_phase_tally(c, t, T);
+            __syncthreads();
+            bg_phase_lkeys(c, t, T);
+            __syncthreads();
+            PROF_MARK(7);
+            bitonic_sort_512((uint32_t *)(c.regb + BG_B_KEYS), t);
+            PROF_MARK(11);
+            bg_phase_huff(c, t, T);
+            __syncthreads();
+            PROF_MARK(12);
+        }
         bg_phase_hdr1(c, t, T);
         __syncthreads();
         bg_phase_hdr2(c, t, T);

@@ -22,6 +22,7 @@ struct BgzfCompressArgs {
     uint32_t *status;          /* device: 0 ok, 1 member would exceed 65536 bytes */
     uint32_t *err_flag;        /* device: OR of all per-block status words */
     uint32_t *scratch;         /* device: grid * BGZF_SCRATCH_WORDS */
+    uint32_t *cand;            /* device: grid * 4 * 65536 words (near-optimal levels), else NULL */
     const uint32_t *crctab;    /* device u32[256] */
     const uint32_t *crcpow;    /* device u32[1024] */
     unsigned long long *prof;  /* device u64[BGZF_PROF_SLOTS] cycle counters, or NULL */

@@ -16,11 +16,11 @@
 
 namespace {
 struct Emu {
-    std::vector<uint32_t> dataw, regA, regB, R, out, crcpow;
+    std::vector<uint32_t> dataw, regA, regB, R, out, crcpow, cand;
     uint8_t litflag[256];
     uint32_t crctab[256];
     uint32_t scal[BG_S_COUNT];
-    Emu() : dataw(BG_DATA_BYTES / 4), regA(131072 / 4), regB(32768 / 4), R(BG_MAX_BLOCK + 8), out(BG_SLOT_BYTES / 4), crcpow(BG_THREADS)
+    Emu() : dataw(BG_DATA_BYTES / 4), regA(131072 / 4), regB(32768 / 4), R(BG_MAX_BLOCK + 8), out(BG_SLOT_BYTES / 4), crcpow(BG_THREADS), cand(4 * BG_MAX_BLOCK)
     {
         bg_make_crc_table(crctab);
         bg_make_crc_pow(crcpow.data(), BG_THREADS);
@@ -66,6 +66,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     c.crctab = e->crctab;
     c.scal = e->scal;
     c.R = e->R.data();
+    c.cand = e->cand.data();
     c.out = e->out.data();
     c.crcpow = e->crcpow.data();
     c.n = n;
@@ -78,22 +79,31 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     run(bg_phase_hash, c, order, k++);
     bg_build_sequential(c);
     run(bg_phase_search, c, order, k++);
-    run(bg_phase_accept, c, order, k++);
-    run(bg_phase_jump, c, order, k++);
-    run(bg_phase_walk_clear, c, order, k++);
-    run(bg_phase_walk_mark, c, order, k++);
-    run(bg_phase_walk_a, c, order, k++);
-    run(bg_phase_walk_b, c, order, k++);
-    run(bg_phase_walk_c, c, order, k++);
-    if (c.scal[BG_S_WALKEND] != n) { fprintf(stderr, "emul: walk ended at %u, n=%u\n", c.scal[BG_S_WALKEND], n); return -2; }
-    run(bg_phase_clear_freq, c, order, k++);
-    run(bg_phase_tally, c, order, k++);
-    run(bg_phase_lkeys, c, order, k++);
-    {   // twin of the kernel's bitonic sort
-        uint32_t *keys = (uint32_t *)(c.regb + BG_B_KEYS);
-        std::sort(keys, keys + 512);
+    for (int pass = 0; pass <= c.prm.opt_passes; pass++) {
+        if (pass == 0) {
+            run(bg_phase_accept, c, order, k++);
+        } else {
+            run(bg_phase_costs, c, order, k++);
+            // the rings live in the (dead) second half of region A, like in the kernel
+            uint32_t *rings = (uint32_t *)(c.stepcode + 65536);
+            for (uint32_t t = 0; t < BG_THREADS; t++) bg_phase_dp(c, order == 1 ? BG_THREADS - 1 - t : t, BG_THREADS, rings);
+        }
+        run(bg_phase_jump, c, order, k++);
+        run(bg_phase_walk_clear, c, order, k++);
+        run(bg_phase_walk_mark, c, order, k++);
+        run(bg_phase_walk_a, c, order, k++);
+        run(bg_phase_walk_b, c, order, k++);
+        run(bg_phase_walk_c, c, order, k++);
+        if (c.scal[BG_S_WALKEND] != n) { fprintf(stderr, "emul: walk ended at %u, n=%u\n", c.scal[BG_S_WALKEND], n); return -2; }
+        run(bg_phase_clear_freq, c, order, k++);
+        run(bg_phase_tally, c, order, k++);
+        run(bg_phase_lkeys, c, order, k++);
+        {   // twin of the kernel's bitonic sort
+            uint32_t *keys = (uint32_t *)(c.regb + BG_B_KEYS);
+            std::sort(keys, keys + 512);
+        }
+        run(bg_phase_huff, c, order, k++);
     }
-    run(bg_phase_huff, c, order, k++);
     run(bg_phase_hdr1, c, order, k++);
     run(bg_phase_hdr2, c, order, k++);
     run(bg_phase_hdr3, c, order, k++);

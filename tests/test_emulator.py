@@ -57,7 +57,7 @@ def test_schedule_independence_is_bit_exact():
 
 
 @pytest.mark.parametrize("kind", ["fastq", "sam"])
-@pytest.mark.parametrize("level,ref_level", [(1, 1), (6, 6), (9, 9)])
+@pytest.mark.parametrize("level,ref_level", [(1, 1), (6, 6), (12, 12)])
 def test_size_within_tolerance_of_golden_reference(kind, level, ref_level):
     """2 blocks against the committed reference sizes (works without oracle/_ref)"""
     data = H.synth(kind, 2 * H.BLOCK)
@@ -70,9 +70,9 @@ def test_size_within_tolerance_of_golden_reference(kind, level, ref_level):
 
 @needs_ref
 @pytest.mark.parametrize("kind", ["fastq", "sam"])
-@pytest.mark.parametrize("level", [1, 6, 9])
+@pytest.mark.parametrize("level", [1, 6, 9, 12])
 def test_size_and_decode_against_compiled_reference(kind, level):
-    data = H.synth(kind, 4 << 20)
+    data = H.synth(kind, (4 << 20) if level < 10 else (1 << 20))     # the reference's level 12 runs at ~1 MB/s
     mine = H.emul_stream(data, level)
     ref_stream, ref_sizes, _ = H.Ref(level).compress_stream(data)
     assert len(mine) - 28 <= 1.03 * sum(ref_sizes), (len(mine), sum(ref_sizes))

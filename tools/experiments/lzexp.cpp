@@ -9,7 +9,7 @@
 #include <cstring>
 #include <vector>
 
-static int HB = 14, DEPTH = 32, NICE = 65, HBYTES = 4, PARSE = 1, MINLEN_MODE = 1, PASSES = 1;
+static int HB = 14, DEPTH = 32, NICE = 65, HBYTES = 4, PARSE = 1, MINLEN_MODE = 1, PASSES = 1, OPT = 0, NCAND = 1;
 
 static const uint16_t len_base[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
 static const uint8_t len_extra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
@@ -101,6 +101,7 @@ static inline int bsr(uint32_t v) { return 31 - __builtin_clz(v); }
 static size_t compress_block(const uint8_t *in, int n, long *stats) {
     static std::vector<uint16_t> head, prev; static std::vector<uint16_t> mlen, moff;
     head.assign(1 << HB, 0xffff); prev.assign(n + 8, 0xffff); mlen.assign(n + 8, 0); moff.assign(n + 8, 0);
+    static std::vector<uint16_t> mlen2[3], moff2[3]; for (int c = 0; c < 3; c++) { mlen2[c].assign(n + 8, 0); moff2[c].assign(n + 8, 0); }
     std::vector<uint8_t> buf(n + 300, 0); memcpy(buf.data(), in, n); in = buf.data();
     uint64_t hmask = HBYTES >= 8 ? ~0ull : ((1ull << (8 * HBYTES)) - 1);
     auto hash = [&](int p) { uint64_t v; memcpy(&v, in + p, 8); v &= hmask;
@@ -119,7 +120,7 @@ static size_t compress_block(const uint8_t *in, int n, long *stats) {
                 if (rd32(in + q) == rd32(in + p) || (best < 3 && (rd32(in+q) & 0xffffff) == (rd32(in+p) & 0xffffff))) {
                     if (best < 3 || in[q + best] == in[p + best]) {
                         int l = 0; while (l < maxl && in[q + l] == in[p + l]) l++;
-                        if (l > best) { best = l; boff = dist; if (l >= NICE) break; }
+                        if (l > best) { if (best >= 3) { for (int c = 2; c > 0; c--) { mlen2[c][p] = mlen2[c-1][p]; moff2[c][p] = moff2[c-1][p]; } mlen2[0][p] = best; moff2[0][p] = boff; } best = l; boff = dist; if (l >= NICE) break; }
                     }
                 }
                 q = prev[q];
@@ -177,6 +178,34 @@ static size_t compress_block(const uint8_t *in, int n, long *stats) {
         have_costs = true;
         if (pass == PASSES - 1) { for (auto &t : toks) { if (t.len) { stats[1]++; stats[2] += t.len; } else stats[0]++; } }
     }
+    for (int it = 0; it < OPT; it++) {
+        // costs from current ll/dl (0 -> 13 bits guess)
+        std::vector<uint32_t> cost(n + 1, 0); std::vector<uint16_t> choice(n + 1, 1);
+        auto lc = [&](int sym) { return ll[sym] ? ll[sym] : 13; };
+        auto dc = [&](int s2) { return dl[s2] ? dl[s2] : 10; };
+        for (int p = n - 1; p >= 0; p--) {
+            uint32_t best = lc(in[p]) + cost[p + 1]; int bl = 1;
+            for (int c = 0; c < NCAND; c++) {
+                int L = c == 0 ? mlen[p] : mlen2[c-1][p], O = c == 0 ? moff[p] : moff2[c-1][p];
+                if (L < 3) continue;
+                uint32_t oc = dc(off_slot_tab[O]) + off_extra[off_slot_tab[O]];
+                for (int l = 3; l <= L; l++) {
+                    uint32_t v = lc(257 + len_slot[l]) + len_extra[len_slot[l]] + oc + cost[p + l];
+                    if (v < best) { best = v; bl = l | (c << 12); }
+                }
+            }
+            cost[p] = best; choice[p] = bl;
+        }
+        uint32_t lf[288] = {0}, df[32] = {0};
+        for (int p = 0; p < n;) { int bl = choice[p] & 0xfff, c = choice[p] >> 12; if (bl == 1) { lf[in[p]]++; p++; } else { int O = c == 0 ? moff[p] : moff2[c-1][p]; lf[257 + len_slot[bl]]++; df[off_slot_tab[O]]++; p += bl; } }
+        lf[256] = 1;
+        huff_lengths(lf, 288, 15, ll); huff_lengths(df, 32, 15, dl);
+        bits = header_bits(ll, dl);
+        for (int i = 0; i < 288; i++) bits += lf[i] * ll[i];
+        for (int i = 0; i < 30; i++) bits += df[i] * dl[i];
+        for (int i = 0; i < 29; i++) bits += lf[257 + i] * len_extra[i];
+        for (int i = 0; i < 30; i++) bits += df[i] * off_extra[i];
+    }
     size_t bytes = (bits + 7) / 8;
     size_t stored = n + 5;
     return 26 + std::min(bytes, stored);
@@ -192,6 +221,8 @@ int main(int argc, char **argv) {
         if (!strncmp(argv[i], "parse=", 6)) PARSE = atoi(argv[i] + 6);
         if (!strncmp(argv[i], "minlen=", 7)) MINLEN_MODE = atoi(argv[i] + 7);
         if (!strncmp(argv[i], "passes=", 7)) PASSES = atoi(argv[i] + 7);
+        if (!strncmp(argv[i], "opt=", 4)) OPT = atoi(argv[i] + 4);
+        if (!strncmp(argv[i], "ncand=", 6)) NCAND = atoi(argv[i] + 6);
     }
     for (int l = 3; l <= 258; l++) { int s = 0; for (int i = 28; i >= 0; i--) if (l >= len_base[i]) { s = i; break; } len_slot[l] = s; }
     for (int o = 1; o <= 32768; o++) off_slot_tab[o] = off_slot(o);
