@@ -146,6 +146,15 @@ BG_HD uint32_t bg_ld32(const uint32_t *w, uint32_t p)
 
 BG_HD uint32_t bg_ld8(const uint32_t *w, uint32_t p) { return ((const uint8_t *)w)[p]; }
 
+BG_HD uint32_t bg_funnel(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32u - s)) : lo;
+#endif
+}
+
 BG_HD int bg_bsr(uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
@@ -358,6 +367,26 @@ BG_HD void bg_build_sequential(const BgCtx &c)
     }
 }
 
+/* number of equal bytes of p.. and q.. starting at offset l (a multiple of 4), capped at maxl.  The two byte streams
+ * are read as aligned words that slide along (one new word per stream and step) with fixed funnel-shift amounts. */
+BG_HD uint32_t bg_match_len(const uint32_t *dw, uint32_t p, uint32_t q, uint32_t l, uint32_t maxl)
+{
+    if (l >= maxl) return maxl;
+    const uint32_t sp = (p & 3u) * 8u, sq = (q & 3u) * 8u;
+    uint32_t ip = (p + l) >> 2, iq = (q + l) >> 2;
+    uint32_t plo = dw[ip], qlo = dw[iq];
+    for (;;) {
+        const uint32_t phi = dw[++ip], qhi = dw[++iq];
+        const uint32_t x = bg_funnel(plo, phi, sp) ^ bg_funnel(qlo, qhi, sq);
+        if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
+        l += 4;
+        if (l >= maxl) break;
+        plo = phi;
+        qlo = qhi;
+    }
+    return l > maxl ? maxl : l;
+}
+
 /* phase 6: all-position search.
  * For position p: follow the chain of earlier positions with the same hash (nearest first, at most `depth`
  * of them, offsets <= 32768), keep the longest match (first found wins ties, i.e. the nearest), stop at
@@ -462,13 +491,7 @@ BG_HD uint32_t bg_search_one_exact(const BgCtx &c, uint32_t p)
     const uint32_t nice = (uint32_t)c.prm.nice;
     for (;;) {
         if (bg_ld32(dw, q + best - 3) == ptail) {
-            uint32_t l = best > 3 ? 0 : 4;
-            while (l < maxl) {
-                const uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
-                if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
-                l += 4;
-            }
-            if (l > maxl) l = maxl;
+            const uint32_t l = bg_match_len(dw, p, q, best > 3 ? 0 : 4, maxl);
             if (l > best) {
                 best = l;
                 boff = p - q;
@@ -500,13 +523,7 @@ BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
         int depth = c.prm.depth;
         for (;;) {
             if (bg_ld32(dw, q + best - 3) == ptail) {
-                uint32_t l = best > 3 ? 0 : 4;
-                while (l < maxl) {
-                    const uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
-                    if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
-                    l += 4;
-                }
-                if (l > maxl) l = maxl;
+                const uint32_t l = bg_match_len(dw, p, q, best > 3 ? 0 : 4, maxl);
                 if (l > best) {
                     best = l;
                     m3 = m2; m2 = m1; m1 = cur;
@@ -525,33 +542,25 @@ BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
     return cur;
 }
 
-/* What the kernel runs.  Chain members share p's hash, i.e. (collisions aside) its first `skip` bytes, so those
- * bytes are not compared candidate by candidate: lengths are measured from `skip` on and only the winner's
- * prefix is verified, once.  In the (rare) event that it does not match, the exact search above decides, so
- * the result is always the exact one. */
+/* what the kernel runs: the exact search with the next link fetched while the comparisons are in flight.
+ * (Skipping the comparison of the hash-window prefix was tried and dropped: with a 14-bit hash most chain
+ * members are collisions, and the 4-byte check on the first bytes is what rejects them cheaply.) */
 BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
 {
     const uint32_t n = c.n;
     uint32_t maxl = n - p;
     if (maxl > 258) maxl = 258;
-    const uint32_t skip = c.scal[BG_S_HBYTES] & ~3u;         /* 8 or 4: whole words inside the hash window */
-    if (maxl < skip + 1) return bg_search_one_exact(c, p);   /* block tail: nothing to gain */
+    if (maxl < (uint32_t)BG_MIN_LOOKUP) return 0;
     uint32_t q = c.prev[p];
     if (q == BG_NOPOS || p - q > 32768u) return 0;
     const uint32_t *dw = c.dataw;
-    uint32_t best = 0, boff = 0, ptail = 0;
+    uint32_t best = 3, boff = 0, ptail = bg_ld32(dw, p);
     int depth = c.prm.depth;
     const uint32_t nice = (uint32_t)c.prm.nice;
     for (;;) {
-        uint32_t qn = c.prev[q];                             /* next link: in flight during the comparisons */
-        if (best == 0 || bg_ld32(dw, q + best - 3) == ptail) {
-            uint32_t l = skip;
-            while (l < maxl) {
-                const uint32_t x = bg_ld32(dw, p + l) ^ bg_ld32(dw, q + l);
-                if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
-                l += 4;
-            }
-            if (l > maxl) l = maxl;
+        const uint32_t qn = c.prev[q];
+        if (bg_ld32(dw, q + best - 3) == ptail) {
+            const uint32_t l = bg_match_len(dw, p, q, best > 3 ? 0 : 4, maxl);
             if (l > best) {
                 best = l;
                 boff = p - q;
@@ -563,12 +572,7 @@ BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
         q = qn;
         if (q == BG_NOPOS || p - q > 32768u) break;
     }
-    /* verify the winner's unchecked prefix */
-    const uint32_t qb = p - boff;
-    bool ok = bg_ld32(dw, qb) == bg_ld32(dw, p);
-    if (skip == 8) ok = ok && bg_ld32(dw, qb + 4) == bg_ld32(dw, p + 4);
-    if (!ok) return bg_search_one_exact(c, p);
-    return (best << 16) | boff;
+    return best > 3 ? (best << 16) | boff : 0;
 }
 
 /* step-machine twin (kept for the emulator's cross-check of both formulations) */
