@@ -197,6 +197,17 @@ extern "C" const char *b200bgzf_strerror(int code)
     }
 }
 
+extern "C" void *b200bgzf_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void b200bgzf_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" const char *b200bgzf_last_error(const b200bgzf_ctx *ctx) { return ctx ? ctx->err : ""; }
 extern "C" unsigned long long b200bgzf_launch_count(const b200bgzf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

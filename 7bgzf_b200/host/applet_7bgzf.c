@@ -11,9 +11,14 @@
  * terminal on stdin or stdout (:491,498); stderr carries the reference's lines:
  *   "compression level = %d (libdeflate)", "%d done.", "ellapsed time: %.6f sec".
  * Payload blocks are always 0xff00 bytes (the reference's multi-thread rule, 7bgzf.c:141-147).
+ *
+ * Where the reference creates a thread per block, this applet runs a three-stage pipeline over page-locked
+ * slots: a reader thread (stdin -> slot), the calling thread (slot -> GPU codec -> slot), a writer thread
+ * (slot -> stdout), so file I/O, PCIe copies and kernels overlap.
  * Host code is C; CUDA is reached only through the b200bgzf_* C ABI.  No GPU => error, no CPU fallback.
  */
 #include <getopt.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -22,21 +27,18 @@
 
 #include "../../include/b200bgzf.h"
 
-#define CHUNK_BLOCKS 4096u /* 255 MiB of payload per API call */
+#define SLOT_BLOCKS 1024u                     /* 63.75 MiB of payload per slot */
+#define NSLOTS 3
 
 struct method_flag {
     char short_opt;
-    const char *long_opt;
     const char *label;
     int default_level;
-    int max_level;
 };
 
 static const struct method_flag k_flags[] = {
-    { 'z', "zlib", "zlib", 6, 9 },       { 'm', "miniz", "miniz", 1, 9 },      { 's', "slz", "slz", 1, 1 },
-    { 'l', "libdeflate", "libdeflate", 6, 12 }, { 'S', "7zip", "7zip", 2, 9 }, { 'n', "zlibng", "zlibng", 6, 9 },
-    { 'C', "cryptopp", "cryptopp", 6, 9 }, { 'i', "igzip", "igzip", 1, 4 },    { 'K', "kzip", "kzip", 1, 1 },
-    { 'Z', "zopfli", "zopfli", 0, 12 },   { 'T', "store", "store", 1, 1 },
+    { 'z', "zlib", 6 },   { 'm', "miniz", 1 },    { 's', "slz", 1 },     { 'l', "libdeflate", 6 }, { 'S', "7zip", 2 },  { 'n', "zlibng", 6 },
+    { 'C', "cryptopp", 6 }, { 'i', "igzip", 1 },  { 'K', "kzip", 1 },    { 'Z', "zopfli", 0 },     { 'T', "store", 1 },
 };
 #define NFLAGS (sizeof k_flags / sizeof k_flags[0])
 
@@ -62,7 +64,52 @@ static void usage(const char *argv0)
             argv0);
 }
 
-static int read_full(FILE *f, unsigned char *buf, size_t want, size_t *got)
+/* ---- a tiny ordered three-stage pipeline ---- */
+enum { EMPTY = 0, FILLED, DONE };
+struct slot {
+    unsigned char *in, *out;
+    size_t in_len, out_len, members;
+    int state, last;
+};
+struct pipe_state {
+    struct slot s[NSLOTS];
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    FILE *fin, *fout;
+    size_t in_cap, out_cap;
+    int decompress, failed;
+};
+
+static void set_state(struct pipe_state *ps, struct slot *sl, int st)
+{
+    pthread_mutex_lock(&ps->mu);
+    sl->state = st;
+    pthread_cond_broadcast(&ps->cv);
+    pthread_mutex_unlock(&ps->mu);
+}
+static void wait_state(struct pipe_state *ps, struct slot *sl, int st)
+{
+    pthread_mutex_lock(&ps->mu);
+    while (sl->state != st && !ps->failed) pthread_cond_wait(&ps->cv, &ps->mu);
+    pthread_mutex_unlock(&ps->mu);
+}
+static void fail(struct pipe_state *ps)
+{
+    pthread_mutex_lock(&ps->mu);
+    ps->failed = 1;
+    pthread_cond_broadcast(&ps->cv);
+    pthread_mutex_unlock(&ps->mu);
+}
+
+static double now_s(void)
+{
+    struct timeval t;
+    gettimeofday(&t, NULL);
+    return t.tv_sec + t.tv_usec * 1e-6;
+}
+static double g_t_read, g_t_write, g_t_codec, g_t_alloc;
+
+static size_t read_full(FILE *f, unsigned char *buf, size_t want)
 {
     size_t n = 0;
     while (n < want) {
@@ -70,109 +117,160 @@ static int read_full(FILE *f, unsigned char *buf, size_t want, size_t *got)
         if (r == 0) break;
         n += r;
     }
-    *got = n;
-    return ferror(f) ? -1 : 0;
+    return n;
 }
 
-static int do_compress(b200bgzf_ctx *ctx, FILE *in, FILE *out, int level)
+/* whole BGZF members at the front of buf[0..have) whose payloads fit in out_cap: bytes used, members, total ISIZE;
+ * -1: not BGZF (7bgzf.c:81-131) */
+static long whole_members(const unsigned char *buf, size_t have, size_t out_cap, size_t *nm, size_t *isize_total)
 {
-    const size_t chunk = (size_t)CHUNK_BLOCKS * B200BGZF_BLOCK_SIZE;
-    const size_t bound = b200bgzf_compress_bound(chunk, B200BGZF_BLOCK_SIZE);
-    unsigned char *ibuf = (unsigned char *)malloc(chunk), *obuf = (unsigned char *)malloc(bound);
-    if (!ibuf || !obuf) { fprintf(stderr, "out of memory\n"); return 1; }
-    long blocks = 0;
-    int ret = 0;
-    for (;;) {
-        size_t got = 0, produced = 0;
-        if (read_full(in, ibuf, chunk, &got) != 0) { ret = 1; break; }
-        if (got == 0) break;
-        int r = b200bgzf_compress_host(ctx, ibuf, got, B200BGZF_BLOCK_SIZE, level, obuf, bound, &produced, 0);
-        if (r != 0) {
-            if (r == B200BGZF_E_NOFIT) fprintf(stderr, "libdeflate_deflate %d\n", 1);
-            else fprintf(stderr, "b200bgzf: %s (%s)\n", b200bgzf_strerror(r), b200bgzf_last_error(ctx));
-            ret = 1;
-            break;
-        }
-        if (fwrite(obuf, 1, produced, out) != produced) { ret = 1; break; }
-        blocks += (long)((got + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE);
-        fprintf(stderr, "%ld\r", blocks);
-        if (got < chunk) break;
+    size_t used = 0;
+    *nm = 0;
+    *isize_total = 0;
+    while (used + 18 <= have) {
+        const unsigned char *p = buf + used;
+        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4) || p[10] != 6 || p[12] != 'B' || p[13] != 'C') return -1;
+        size_t sz = (size_t)(p[16] | (p[17] << 8)) + 1;
+        if (sz < 28) return -1;
+        if (used + sz > have) break;
+        const unsigned char *t = p + sz - 4;
+        const size_t isz = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+        if (isz > B200BGZF_MAX_BLOCK_SIZE) return -1;
+        if (*isize_total + isz > out_cap) break;
+        *isize_total += isz;
+        used += sz;
+        (*nm)++;
     }
-    if (!ret) {
-        /* EOF marker (7bgzf.c:283-289) */
-        static const unsigned char eof[28] = { 0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43,
-                                               0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-        fwrite(eof, 1, 28, out);
-        fprintf(stderr, "%ld done.\n", blocks);
-    }
-    free(ibuf);
-    free(obuf);
-    return ret;
+    return (long)used;
 }
 
-static int do_decompress(b200bgzf_ctx *ctx, FILE *in, FILE *out)
+static void *reader_main(void *arg)
 {
-    /* read members until ~256 MiB of compressed data is buffered, inflate, repeat */
-    const size_t cap = 256u << 20;
-    unsigned char *ibuf = (unsigned char *)malloc(cap + B200BGZF_MAX_BLOCK_SIZE);
-    size_t ocap = 0;
-    unsigned char *obuf = NULL;
-    if (!ibuf) { fprintf(stderr, "out of memory\n"); return 1; }
-    size_t have = 0;
-    long members = 0;
-    int ret = 0, eof_seen = 0;
-    while (!ret) {
+    struct pipe_state *ps = (struct pipe_state *)arg;
+    size_t carry = 0;
+    unsigned char *carry_src = NULL;
+    int eof_seen = 0;
+    for (unsigned i = 0;; i++) {
+        struct slot *sl = &ps->s[i % NSLOTS];
+        wait_state(ps, sl, EMPTY);
+        if (ps->failed) return NULL;
+        if (carry) memmove(sl->in, carry_src, carry);      /* members left over from the previous slot */
+        size_t have = carry;
         if (!eof_seen) {
-            size_t got = 0;
-            if (read_full(in, ibuf + have, cap - have, &got) != 0) { ret = 1; break; }
+            const double t0 = now_s();
+            const size_t got = read_full(ps->fin, sl->in + carry, ps->in_cap - carry);
+            g_t_read += now_s() - t0;
             have += got;
-            if (have < cap) eof_seen = 1;
+            eof_seen = got < ps->in_cap - carry;
         }
-        if (have == 0) break;
-        /* whole members only */
-        size_t used = 0, total = 0, nm = 0;
-        while (used + 18 <= have) {
-            const unsigned char *p = ibuf + used;
-            if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4) || p[10] != 6 || p[12] != 'B' || p[13] != 'C') {
+        carry = 0;
+        sl->in_len = have;
+        sl->members = 0;
+        if (ps->decompress && have) {
+            size_t nm, isz;
+            const long used = whole_members(sl->in, have, ps->out_cap, &nm, &isz);
+            if (used <= 0) {                               /* not a member, or one cut short by the end of the input */
                 fprintf(stderr, "not BGZF or corrupted\n");
-                ret = -1;
-                break;
+                fail(ps);
+                return NULL;
             }
-            size_t sz = (size_t)(p[16] | (p[17] << 8)) + 1;
-            if (used + sz > have) break;
-            const unsigned char *t = p + sz - 4;
-            total += (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
-            used += sz;
-            nm++;
+            sl->in_len = (size_t)used;
+            sl->members = nm;
+            carry = have - (size_t)used;
+            carry_src = sl->in + used;
         }
-        if (ret) break;
-        if (used == 0) {
-            if (eof_seen) { fprintf(stderr, "not BGZF or corrupted\n"); ret = -1; }
-            break;
-        }
-        if (total > ocap) {
-            free(obuf);
-            ocap = total + (total >> 2) + 65536;
-            obuf = (unsigned char *)malloc(ocap);
-            if (!obuf) { fprintf(stderr, "out of memory\n"); ret = 1; break; }
-        }
-        size_t produced = 0;
-        int r = b200bgzf_inflate_host(ctx, ibuf, used, obuf, ocap, &produced, 0);
-        if (r != 0) {
-            fprintf(stderr, "inflate %d\n", r);
-            ret = 1;
-            break;
-        }
-        if (fwrite(obuf, 1, produced, out) != produced) { ret = 1; break; }
-        members += (long)nm;
-        fprintf(stderr, "%ld\r", members);
-        memmove(ibuf, ibuf + used, have - used);
-        have -= used;
-        if (eof_seen && have == 0) break;
+        sl->last = eof_seen && carry == 0;
+        set_state(ps, sl, FILLED);
+        if (sl->last) return NULL;
     }
-    if (!ret) fprintf(stderr, "%ld done.\n", members);
-    free(ibuf);
-    free(obuf);
+}
+
+static void *writer_main(void *arg)
+{
+    struct pipe_state *ps = (struct pipe_state *)arg;
+    for (unsigned i = 0;; i++) {
+        struct slot *sl = &ps->s[i % NSLOTS];
+        wait_state(ps, sl, DONE);
+        if (ps->failed) return NULL;
+        const double t0 = now_s();
+        if (sl->out_len && fwrite(sl->out, 1, sl->out_len, ps->fout) != sl->out_len) { fail(ps); return NULL; }
+        g_t_write += now_s() - t0;
+        int last = sl->last;
+        set_state(ps, sl, EMPTY);
+        if (last) return NULL;
+    }
+}
+
+static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level)
+{
+    struct pipe_state ps;
+    memset(&ps, 0, sizeof ps);
+    pthread_mutex_init(&ps.mu, NULL);
+    pthread_cond_init(&ps.cv, NULL);
+    ps.fin = stdin;
+    ps.fout = stdout;
+    ps.decompress = decompress;
+    if (decompress) {
+        ps.in_cap = (size_t)32 << 20;        /* members are taken from here until their payloads fill ... */
+        ps.out_cap = (size_t)192 << 20;      /* ... this much output */
+    } else {
+        ps.in_cap = (size_t)SLOT_BLOCKS * B200BGZF_BLOCK_SIZE;
+        ps.out_cap = b200bgzf_compress_bound(ps.in_cap, B200BGZF_BLOCK_SIZE);
+    }
+    const double ta = now_s();
+    for (int i = 0; i < NSLOTS; i++) {
+        ps.s[i].in = (unsigned char *)b200bgzf_host_alloc(ps.in_cap);
+        ps.s[i].out = (unsigned char *)b200bgzf_host_alloc(ps.out_cap);
+        if (!ps.s[i].in || !ps.s[i].out) { fprintf(stderr, "out of memory\n"); return 1; }
+    }
+    g_t_alloc = now_s() - ta;
+    pthread_t rd, wr;
+    pthread_create(&rd, NULL, reader_main, &ps);
+    pthread_create(&wr, NULL, writer_main, &ps);
+    long units = 0;
+    int ret = 0;
+    for (unsigned i = 0; !ret; i++) {
+        struct slot *sl = &ps.s[i % NSLOTS];
+        wait_state(&ps, sl, FILLED);
+        if (ps.failed) { ret = decompress ? -1 : 1; break; }
+        sl->out_len = 0;
+        const double tc = now_s();
+        if (sl->in_len) {
+            int r;
+            if (decompress) {
+                r = b200bgzf_inflate_host(ctx, sl->in, sl->in_len, sl->out, ps.out_cap, &sl->out_len, 0);
+                if (r != 0) { fprintf(stderr, "inflate %d\n", r); ret = 1; }
+                units += (long)sl->members;
+            } else {
+                r = b200bgzf_compress_host(ctx, sl->in, sl->in_len, B200BGZF_BLOCK_SIZE, level, sl->out, ps.out_cap, &sl->out_len,
+                                           sl->last ? B200BGZF_APPEND_EOF : 0);
+                if (r == B200BGZF_E_NOFIT) { fprintf(stderr, "libdeflate_deflate %d\n", 1); ret = 1; }
+                else if (r != 0) { fprintf(stderr, "b200bgzf: %s (%s)\n", b200bgzf_strerror(r), b200bgzf_last_error(ctx)); ret = 1; }
+                units += (long)((sl->in_len + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE);
+            }
+        } else if (!decompress && sl->last) {
+            /* empty tail slot: still owe the EOF marker (7bgzf.c:283-289) */
+            size_t n = 0;
+            b200bgzf_compress_host(ctx, NULL, 0, B200BGZF_BLOCK_SIZE, level, sl->out, ps.out_cap, &n, B200BGZF_APPEND_EOF);
+            sl->out_len = n;
+        }
+        g_t_codec += now_s() - tc;
+        if (ret) { fail(&ps); break; }
+        fprintf(stderr, "%ld\r", units);
+        int last = sl->last;
+        set_state(&ps, sl, DONE);
+        if (last) break;
+    }
+    pthread_join(rd, NULL);
+    pthread_join(wr, NULL);
+    if (ps.failed && !ret) ret = decompress ? -1 : 1;
+    if (!ret) fprintf(stderr, "%ld done.\n", units);
+    if (getenv("B200BGZF_DEBUG"))
+        fprintf(stderr, "stage seconds: pinned alloc %.3f, read %.3f, codec %.3f, write %.3f\n", g_t_alloc, g_t_read, g_t_codec, g_t_write);
+    for (int i = 0; i < NSLOTS; i++) {
+        b200bgzf_host_free(ps.s[i].in);
+        b200bgzf_host_free(ps.s[i].out);
+    }
     return ret;
 }
 
@@ -225,19 +323,24 @@ int main(int argc, char **argv)
         fprintf(stderr, "b200bgzf: cannot initialise the GPU codec: %s\n", b200bgzf_strerror(r));
         return 1;
     }
+    const double t_created = now_s();
     int ret;
     if (decompress) {
-        ret = do_decompress(ctx, stdin, stdout);
+        ret = run_pipeline(ctx, 1, 0);
     } else {
         int level = level_sum;
         fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
         if (level < 1) level = 1;
         if (level > 12) level = 12;
-        ret = do_compress(ctx, stdin, stdout, level);
+        ret = run_pipeline(ctx, 0, level);
     }
     fflush(stdout);
+    const double t_piped = now_s();
     b200bgzf_destroy(ctx);
     gettimeofday(&t1, NULL);
+    if (getenv("B200BGZF_DEBUG"))
+        fprintf(stderr, "seconds: create %.3f, pipeline %.3f, destroy %.3f\n", t_created - (t0.tv_sec + t0.tv_usec * 1e-6), t_piped - t_created,
+                now_s() - t_piped);
     fprintf(stderr, "ellapsed time: %.6f sec\n", (t1.tv_sec + t1.tv_usec * 0.000001) - (t0.tv_sec + t0.tv_usec * 0.000001));
     return ret;
 }

@@ -34,7 +34,7 @@ $(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/hook.o
 
 # the applet
 $(PKG)/7bgzf: $(OBJ)/applet_7bgzf.o $(PKG)/lib7bgzf_b200.so
-	$(CC) -o $@ $(OBJ)/applet_7bgzf.o -L$(PKG) -l7bgzf_b200 -Wl,-rpath,'$$ORIGIN'
+	$(CC) -o $@ $(OBJ)/applet_7bgzf.o -L$(PKG) -l7bgzf_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
 
 # ---- test / bench infrastructure (never linked into the product) ----
 testlibs: build/libdatagen.so build/libemul.so build/datagen oracle/liboracle.so

@@ -81,6 +81,11 @@ int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes
 int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
                           unsigned flags);
 
+/* Page-locked host memory for the *_host entry points (pageable buffers work too, but are copied at a fraction of
+ * the PCIe rate).  The applet reads stdin straight into such buffers. */
+void *b200bgzf_host_alloc(size_t bytes);
+void b200bgzf_host_free(void *p);
+
 /* Per-phase cycle counters of the compress kernel (development aid; n <= 16). Resets them when reset != 0. */
 int b200bgzf_profile(b200bgzf_ctx *ctx, int enable, unsigned long long *cycles, int n, int reset);
 /* number of kernel launches issued by this context so far */
