@@ -155,8 +155,8 @@ class Codec:
         return n.value
 
     def profile(self, enable=True, reset=True):
-        arr = (ctypes.c_ulonglong * 16)()
-        self._check(self.lib.b200bgzf_profile(self.h, 1 if enable else 0, arr, 16, 1 if reset else 0))
+        arr = (ctypes.c_ulonglong * 32)()
+        self._check(self.lib.b200bgzf_profile(self.h, 1 if enable else 0, arr, 32, 1 if reset else 0))
         return list(arr)
 
     def launches(self):

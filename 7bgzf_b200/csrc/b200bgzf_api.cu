@@ -25,7 +25,7 @@ namespace {
 
 constexpr uint32_t kHostBatchBlocks = 1024;     /* 64 MiB of payload per pipelined batch */
 constexpr uint32_t kDeviceBatchBlocks = 16384;  /* 1 GiB of payload per device-resident batch */
-constexpr int kLanes = 3;
+constexpr int kLanes = 4;
 constexpr int kHookLanes = 32;
 constexpr uint32_t kHookLaneBlocks = 4;
 
@@ -602,7 +602,9 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
     out_off.push_back(total);
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t batch = 4096;
+    /* batches small enough that the first kernel starts early and the D2H copies run back to back behind it,
+     * large enough that kLanes of them in flight fill the GPU (one warp per member, ~3100 resident) */
+    const size_t batch = 1024;
     int r;
     bool bad = false;
     size_t i = 0;

@@ -79,7 +79,7 @@
 enum {
     BG_S_NUSED = 0, BG_S_MINLEN, BG_S_HBYTES, BG_S_CRC, BG_S_NITEMS, BG_S_NL, BG_S_ND, BG_S_NP,
     BG_S_BTYPE, BG_S_HDRBITS, BG_S_TOKBITS, BG_S_PAYLOAD, BG_S_STATUS, BG_S_DYNSYMS, BG_S_STASYMS, BG_S_WALKEND,
-    BG_S_EXTRA, BG_S_DYNHDR,
+    BG_S_EXTRA, BG_S_DYNHDR, BG_S_WLIST,
     BG_S_COUNT = 32
 };
 
@@ -191,6 +191,17 @@ BG_HD void bg_add32(uint32_t *a, uint32_t v)
     atomicAdd(a, v);
 #else
     *a += v;
+#endif
+}
+
+BG_HD uint32_t bg_fetch_add32(uint32_t *a, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(a, v);
+#else
+    uint32_t old = *a;
+    *a += v;
+    return old;
 #endif
 }
 
@@ -687,41 +698,49 @@ BG_HD bool bg_match_ok(uint32_t r, uint32_t minlen)
     return len >= minlen && len >= 3 && !(len == 3 && off > 8192);
 }
 
+BG_HD uint32_t bg_accept_code(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t minlen, int lazy, uint32_t nice)
+{
+    if (!bg_match_ok(r0, minlen)) return 0;
+    const uint32_t cl = r0 >> 16, co = r0 & 0xffffu;
+    if (lazy >= 1 && cl < nice) {
+        if (bg_match_ok(r1, minlen)) {
+            const int nl = (int)(r1 >> 16);
+            if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r1 & 0xffffu)) > 2) return 0;
+        }
+        if (lazy >= 2 && bg_match_ok(r2, minlen)) {
+            const int nl = (int)(r2 >> 16);
+            if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r2 & 0xffffu)) > 6) return 0;
+        }
+    }
+    return cl <= 256 ? cl - 2 : 255;
+}
+
+/* Four consecutive positions per thread and step: their six match words come with two vector loads from the
+ * L2-resident scratch, the four step codes leave as one shared-memory word. */
 BG_HD void bg_phase_accept(const BgCtx &c, uint32_t t, uint32_t T)
 {
     const uint32_t n = c.n, minlen = c.scal[BG_S_MINLEN];
     const int lazy = c.prm.lazy;
     const uint32_t nice = (uint32_t)c.prm.nice;
-    /* R lives in the L2-resident scratch: keep the next round's three loads in flight while deciding this one */
-    uint32_t a0 = t < n ? c.R[t] : 0, a1 = t + 1 < n ? c.R[t + 1] : 0, a2 = (lazy >= 2 && t + 2 < n) ? c.R[t + 2] : 0;
-    for (uint32_t p = t; p < n; p += T) {
-        const uint32_t r0 = a0, r1 = a1, r2 = a2;
-        const uint32_t pn = p + T;
-        a0 = pn < n ? c.R[pn] : 0;
-        a1 = pn + 1 < n ? c.R[pn + 1] : 0;
-        a2 = (lazy >= 2 && pn + 2 < n) ? c.R[pn + 2] : 0;
-        uint32_t code = 0;
-        if (bg_match_ok(r0, minlen)) {
-            uint32_t cl = r0 >> 16, co = r0 & 0xffffu;
-            bool take = true;
-            if (lazy >= 1 && cl < nice && p + 1 < n) {
-                if (bg_match_ok(r1, minlen)) {
-                    int nl = (int)(r1 >> 16);
-                    if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r1 & 0xffffu)) > 2)
-                        take = false;
-                }
-                if (take && lazy >= 2 && p + 2 < n) {
-                    if (bg_match_ok(r2, minlen)) {
-                        int nl = (int)(r2 >> 16);
-                        if (nl >= (int)cl && 4 * (nl - (int)cl) + (bg_bsr(co) - bg_bsr(r2 & 0xffffu)) > 6)
-                            take = false;
-                    }
-                }
-            }
-            if (take)
-                code = cl <= 256 ? cl - 2 : 255;
+    for (uint32_t p = 4 * t; p < n; p += 4 * T) {
+        uint32_t r[6];
+#if defined(__CUDA_ARCH__)
+        const uint4 a = __ldcg((const uint4 *)(c.R + p));
+        const uint2 b = __ldcg((const uint2 *)(c.R + p + 4));
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y;
+#else
+        for (uint32_t j = 0; j < 6; j++) r[j] = p + j < n ? c.R[p + j] : 0;
+#endif
+        uint32_t codes = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t j = 0; j < 4; j++) {
+            /* (what lies past the end of the block is no match) */
+            const uint32_t r0 = p + j < n ? r[j] : 0, r1 = p + j + 1 < n ? r[j + 1] : 0, r2 = p + j + 2 < n ? r[j + 2] : 0;
+            codes |= bg_accept_code(r0, r1, r2, minlen, lazy, nice) << (8 * j);
         }
-        c.stepcode[p] = (uint8_t)code;
+        *(uint32_t *)(c.stepcode + p) = codes;
     }
 }
 
@@ -803,22 +822,45 @@ BG_HD void bg_phase_walk_clear(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t nsuper = (c.n + BG_SUPER_POS - 1) / BG_SUPER_POS;
     uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
     for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) xtab[w] = 0;
+    if (t == 0) c.scal[BG_S_WLIST] = 0;
+}
+
+/* possible entry w = (super-chunk, offset): where does a parse entering there leave the super-chunk */
+BG_HD void bg_walk_entry(const BgCtx &c, uint32_t w)
+{
+    const uint32_t n = c.n;
+    uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
+    const uint32_t sc = w / BG_MAX_TOKEN, k = w - sc * BG_MAX_TOKEN;
+    uint32_t send = (sc + 1) * BG_SUPER_POS;
+    if (send > n) send = n;
+    uint32_t e = sc * BG_SUPER_POS + k;
+    if (e < send) e = bg_walk_chunks(c, e, sc * BG_SUPER, (sc + 1) * BG_SUPER, (uint16_t *)0);
+    xtab[w] = (uint16_t)(e >= send ? e - send : 0);
+}
+
+/* 9a-: the possible entries (typically a thousand of the 8 000 table slots, in clusters) are gathered into a list so
+ * that the walks of 9a spread evenly over the threads; what does not fit the list is walked on the spot */
+#define BG_B_WLIST 1408u          /* u16[BG_WLIST_CAP], in histogram/Huffman space that is written only after the walk */
+#define BG_WLIST_CAP 3400u
+BG_HD void bg_phase_walk_list(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t nsuper = (c.n + BG_SUPER_POS - 1) / BG_SUPER_POS;
+    const uint16_t *xtab = (const uint16_t *)(c.regb + BG_B_XTAB);
+    uint16_t *list = (uint16_t *)(c.regb + BG_B_WLIST);
+    for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) {
+        if (xtab[w] != 0xFFFFu) continue;          /* not a possible entry */
+        const uint32_t slot = bg_fetch_add32(&c.scal[BG_S_WLIST], 1);
+        if (slot < BG_WLIST_CAP) list[slot] = (uint16_t)w;
+        else bg_walk_entry(c, w);
+    }
 }
 
 BG_HD void bg_phase_walk_a(const BgCtx &c, uint32_t t, uint32_t T)
 {
-    const uint32_t n = c.n;
-    const uint32_t nsuper = (n + BG_SUPER_POS - 1) / BG_SUPER_POS;
-    uint16_t *xtab = (uint16_t *)(c.regb + BG_B_XTAB);
-    for (uint32_t w = t; w < nsuper * BG_MAX_TOKEN; w += T) {
-        if (xtab[w] != 0xFFFFu) continue;          /* not a possible entry */
-        const uint32_t sc = w / BG_MAX_TOKEN, k = w - sc * BG_MAX_TOKEN;
-        uint32_t send = (sc + 1) * BG_SUPER_POS;
-        if (send > n) send = n;
-        uint32_t e = sc * BG_SUPER_POS + k;
-        if (e < send) e = bg_walk_chunks(c, e, sc * BG_SUPER, (sc + 1) * BG_SUPER, (uint16_t *)0);
-        xtab[w] = (uint16_t)(e >= send ? e - send : 0);
-    }
+    const uint16_t *list = (const uint16_t *)(c.regb + BG_B_WLIST);
+    uint32_t m = c.scal[BG_S_WLIST];
+    if (m > BG_WLIST_CAP) m = BG_WLIST_CAP;
+    for (uint32_t i = t; i < m; i += T) bg_walk_entry(c, list[i]);
 }
 
 BG_HD void bg_phase_walk_b(const BgCtx &c, uint32_t t, uint32_t T)
@@ -1347,6 +1389,25 @@ BG_HD void bg_phase_codes_c(const BgCtx &c, uint32_t t, uint32_t T)
     codes[sym] = (uint16_t)code;
 }
 
+/* phase 14f: bits of every run-length item of the dynamic header (the driver turns them into bit offsets), so that
+ * the header is written by one thread per item instead of one thread for all */
+#define BG_B_IOFF BG_B_XTAB       /* u32[1024]; the walk tables are dead by now */
+BG_HD void bg_phase_hdr_bits(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint8_t *plen = c.regb + BG_B_PLEN;
+    const uint16_t *items = (const uint16_t *)(c.regb + BG_B_ITEMS);
+    uint32_t *ioff = (uint32_t *)(c.regb + BG_B_IOFF);
+    const uint32_t ni = c.scal[BG_S_BTYPE] == 2 ? c.scal[BG_S_NITEMS] : 0;
+    for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
+        uint32_t bits = 0;
+        if (i < ni) {
+            const uint32_t sym = items[i] & 31u;
+            bits = plen[sym] + (sym < 16 ? 0u : sym == 16 ? 2u : sym == 17 ? 3u : 7u);
+        }
+        ioff[i] = bits;
+    }
+}
+
 /* phase 15: bits per chunk with the final code */
 BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
 {
@@ -1507,18 +1568,25 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
             bg_w_put(w, (nl - 257) | ((nd - 1) << 5) | ((np - 4) << 10), 14);
             for (uint32_t i = 0; i < np; i++)
                 bg_w_put(w, plen[bg_precode_order(i)], 3);
-            const uint32_t ni = c.scal[BG_S_NITEMS];
-            for (uint32_t i = 0; i < ni; i++) {
-                uint32_t sym = items[i] & 31u, ex = items[i] >> 5;
-                bg_w_put(w, pcode[sym], plen[sym]);
-                if (sym >= 16) bg_w_put(w, ex, sym == 16 ? 2 : sym == 17 ? 3 : 7);
-            }
         }
         bg_w_flush(w);
         /* end-of-block symbol closes the token stream */
         bg_w_init(w, c.out, base + hdrbits + c.scal[BG_S_TOKBITS] - llen[256]);
         bg_w_put(w, lcode[256], llen[256]);
         bg_w_flush(w);
+    }
+    if (btype == 2) {
+        /* the run-length items of the dynamic header, one thread each, at the bit offsets of phase 14f */
+        const uint32_t *ioff = (const uint32_t *)(rb + BG_B_IOFF);
+        const uint32_t ni = c.scal[BG_S_NITEMS], ibase = base + 17 + 3 * c.scal[BG_S_NP];
+        for (uint32_t i = t; i < ni; i += T) {
+            const uint32_t sym = items[i] & 31u, ex = items[i] >> 5;
+            BgWriter w;
+            bg_w_init(w, c.out, ibase + ioff[i]);
+            bg_w_put(w, pcode[sym], plen[sym]);
+            if (sym >= 16) bg_w_put(w, ex, sym == 16 ? 2 : sym == 17 ? 3 : 7);
+            bg_w_flush(w);
+        }
     }
     for (uint32_t ch = t; ch * BG_CHUNK < n; ch += T) {
         uint32_t p = entry[ch];

@@ -119,43 +119,46 @@ __device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, 
     }
 }
 
-/* Phase B, one warp.  Shared-memory instructions of a warp execute in program order, so the head-table updates of
- * consecutive groups need no barrier between them (the accesses are volatile so the compiler keeps their order);
- * the loop is then bound by issue rate, not by the load->store round trip of every group. */
-__device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *notes, uint32_t lane)
+/* Phase B, a relay of BG_LINKERS warps: warp k takes tiles k, k+BG_LINKERS, ...  Only the head-table part of a tile
+ * must run in tile order (and inside it, group order: shared-memory instructions of one warp execute in program order,
+ * the accesses are volatile so the compiler keeps that order); it is entered when the `turn` word in shared memory
+ * reaches the tile and hands the turn on as soon as its last head update is out.  Fetching the notes and the
+ * leaders' hashes before, and storing the links after, overlap with the other warps' turns.  head[] reads and
+ * writes go out back to back; the links they return are parked in registers until the turn has been passed on. */
+#define BG_LINKERS 4u
+__device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *notes, uint32_t warp, uint32_t lane, volatile uint32_t *turn)
 {
     const uint32_t n = c.n;
     const uint32_t ntiles = (n + 511u) >> 9;
     volatile uint16_t *vhead = c.head;
-    volatile uint16_t *vprev = c.prev;
-    const uint4 none = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    uint4 n1 = ntiles > 0 ? __ldcg(notes + lane) : none;
-    uint4 n2 = ntiles > 1 ? __ldcg(notes + 32u + lane) : none;
-    for (uint32_t tile = 0; tile < ntiles; tile++) {
-        const uint4 cur = n1;
-        n1 = n2;
-        if (tile + 2 < ntiles) n2 = __ldcg(notes + (tile + 2) * 32u + lane);     /* two tiles (32 groups) ahead */
+    for (uint32_t tile = warp; tile < ntiles; tile += BG_LINKERS) {
+        const uint4 cur = __ldcg(notes + tile * 32u + lane);
         const uint32_t w[4] = { cur.x, cur.y, cur.z, cur.w };
-        /* the hash slots of this tile's leaders are untouched until their group is processed: fetch them all now */
+        /* the hash slots of this tile's leaders are untouched until their links are stored below: fetch them all now */
         uint32_t hs[16];
 #pragma unroll
         for (uint32_t g = 0; g < 16; g++) {
-            const uint32_t p = tile * 512u + g * 32u + lane;
             const uint32_t note = (w[g >> 2] >> (8 * (g & 3))) & 0xffu;
-            hs[g] = (note != 0xffu && p < n) ? (uint32_t)vprev[p] : 0xffffffffu;
+            hs[g] = note != 0xffu ? (uint32_t)c.prev[tile * 512u + g * 32u + lane] : 0xffffffffu;
         }
+        while (*turn != tile) {}
+        __threadfence_block();
+        uint16_t old[16];
 #pragma unroll
         for (uint32_t g = 0; g < 16; g++) {
-            const uint32_t base = tile * 512u + g * 32u;
             const uint32_t h = hs[g];
             if (h != 0xffffffffu) {
                 const uint32_t note = (w[g >> 2] >> (8 * (g & 3))) & 31u;
-                const uint16_t old = vhead[h];
-                vhead[h] = (uint16_t)(base + note);
-                vprev[base + lane] = old;
+                old[g] = vhead[h];
+                vhead[h] = (uint16_t)(tile * 512u + g * 32u + note);
             }
         }
+        __threadfence_block();
         __syncwarp();
+        if (lane == 0) *turn = tile + 1;
+#pragma unroll
+        for (uint32_t g = 0; g < 16; g++)
+            if (hs[g] != 0xffffffffu) c.prev[tile * 512u + g * 32u + lane] = old[g];
     }
 }
 
@@ -354,11 +357,11 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bg_phase_hash(c, t, T);
         __syncthreads();
         PROF_MARK(2);
-        uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build notes live behind the match scratch */
+        uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build commands live behind the match scratch */
         build_peers_phase(c, hi, t);
         __syncthreads();
         PROF_MARK(3);
-        if (t < 32u) build_link_phase(c, hi, t);     /* the other warps wait at the barrier */
+        if (t < 32u * BG_LINKERS) build_link_phase(c, hi, t >> 5, t & 31u, &c.scal[BG_S_WLIST]);   /* the other warps wait at the barrier */
         __syncthreads();
         PROF_MARK(10);
         search_positions(c, t);
@@ -382,10 +385,15 @@ bgzf_compress_kernel(BgzfCompressArgs a)
             __syncthreads();
             bg_phase_walk_mark(c, t, T);
             __syncthreads();
+            bg_phase_walk_list(c, t, T);
+            __syncthreads();
+            PROF_MARK(16);
             bg_phase_walk_a(c, t, T);
             __syncthreads();
+            PROF_MARK(17);
             bg_phase_walk_b(c, t, T);
             __syncthreads();
+            PROF_MARK(18);
             bg_phase_walk_c(c, t, T);
             __syncthreads();
             PROF_MARK(6);
@@ -421,9 +429,11 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bg_phase_codes_c(c, t, T);
         __syncthreads();
         PROF_MARK(8);
+        bg_phase_hdr_bits(c, t, T);
         bg_phase_sizes(c, t, T);
         __syncthreads();
         block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_CBITS), scan_scratch, t);
+        block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_IOFF), scan_scratch, t);
         bg_phase_zero_out(c, t, T);
         __syncthreads();
         PROF_MARK(14);

@@ -7,7 +7,7 @@
 #include "bgzf_block.h"
 
 #define BGZF_SCRATCH_WORDS (65536u + 32u + 16384u + 32u)   /* per-CTA scratch: u32 match per position + u8 build notes */
-#define BGZF_PROF_SLOTS 16
+#define BGZF_PROF_SLOTS 32
 
 struct BgzfCompressArgs {
     const uint8_t *in;         /* device: payload bytes */

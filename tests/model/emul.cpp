@@ -91,6 +91,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
         run(bg_phase_jump, c, order, k++);
         run(bg_phase_walk_clear, c, order, k++);
         run(bg_phase_walk_mark, c, order, k++);
+        run(bg_phase_walk_list, c, order, k++);
         run(bg_phase_walk_a, c, order, k++);
         run(bg_phase_walk_b, c, order, k++);
         run(bg_phase_walk_c, c, order, k++);
@@ -126,6 +127,11 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     run(bg_phase_codes_a, c, order, k++);
     run(bg_phase_codes_b, c, order, k++);
     run(bg_phase_codes_c, c, order, k++);
+    run(bg_phase_hdr_bits, c, order, k++);
+    {   // twin of the kernel's block-wide exclusive scan
+        uint32_t *io = (uint32_t *)(c.regb + BG_B_IOFF), acc = 0;
+        for (uint32_t i = 0; i < BG_MAX_CHUNKS; i++) { uint32_t v = io[i]; io[i] = acc; acc += v; }
+    }
     run(bg_phase_sizes, c, order, k++);
     {   // twin of the kernel's block-wide exclusive scan
         uint32_t *cb = (uint32_t *)(c.regb + BG_B_CBITS), acc = 0;
