@@ -10,10 +10,13 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200bgzf.h"
@@ -25,8 +28,10 @@ namespace {
 
 constexpr uint32_t kHostBatchBlocks = 1024;     /* 64 MiB of payload per pipelined batch */
 constexpr uint32_t kDeviceBatchBlocks = 16384;  /* 1 GiB of payload per device-resident batch */
-constexpr int kLanes = 4;
-constexpr int kHookLanes = 32;
+constexpr int kLanes = 8;        /* lanes a host-buffer call may rotate through (it uses the first few) */
+constexpr size_t kInflateBatch = 1024;  /* members per pipelined inflate batch (measured: 512 and 4096 are both slower) */
+constexpr int kInflateLanes = 6;        /* 6 x 1024 members in flight keep the GPU (~4700 resident members) and the D2H engine busy */
+constexpr int kHookLanes = 128;
 constexpr uint32_t kHookLaneBlocks = 4;
 
 struct Lane {
@@ -46,6 +51,7 @@ struct Lane {
     size_t pend_out_off = 0;
     bool busy = false;
     int scratch_ctas = 0;
+    cudaEvent_t done = nullptr;   /* blocking-sync event (hook lanes): lets a waiting caller sleep instead of spin */
 };
 
 }  // namespace
@@ -66,7 +72,7 @@ struct b200bgzf_ctx {
     uint32_t *d_idx_tilecount = nullptr, *d_idx_isize = nullptr, *d_idx_status = nullptr, *d_inf_status = nullptr;
     size_t idx_cap = 0, idx_tiles = 0;
     uint64_t *h_idx = nullptr;
-    unsigned long long launches = 0;
+    std::atomic<unsigned long long> launches{0};   /* hook callers bump it concurrently */
     char err[256] = { 0 };
 };
 
@@ -109,6 +115,7 @@ void lane_free(Lane &l)
     if (l.h_in) cudaFreeHost(l.h_in);
     if (l.h_out) cudaFreeHost(l.h_out);
     if (l.h_meta) cudaFreeHost(l.h_meta);
+    if (l.done) cudaEventDestroy(l.done);
     if (l.stream) cudaStreamDestroy(l.stream);
     l = Lane();
 }
@@ -209,7 +216,7 @@ extern "C" void b200bgzf_host_free(void *p)
 }
 
 extern "C" const char *b200bgzf_last_error(const b200bgzf_ctx *ctx) { return ctx ? ctx->err : ""; }
-extern "C" unsigned long long b200bgzf_launch_count(const b200bgzf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" unsigned long long b200bgzf_launch_count(const b200bgzf_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 extern "C" size_t b200bgzf_compress_bound(size_t in_bytes, uint32_t block_size)
 {
@@ -423,6 +430,63 @@ int compress_blocks_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *const *src, 
     return worst;
 }
 
+/* One payload, one member: the shape of every call the LD_PRELOAD hook makes.  Latency is everything here (the caller
+ * blocks), so the round trip is pared down to: copy in, one kernel, ONE copy out (the whole 64 KiB slot with the member
+ * size and status words parked right behind it), one synchronisation.  No scan, no gather, no metadata uploads. */
+int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t slen, void *dst, size_t *dlen, int *status, int level,
+                         bool sleep_wait)
+{
+    int r = lane_reserve(ctx, l, 1, BG_SLOT_BYTES + 64, 0, true, (int)kHookLaneBlocks);
+    if (r) return r;
+    CK(grow(&l.h_in, &l.host_in_cap, (size_t)BG_SLOT_BYTES, true));
+    CK(grow(&l.h_out, &l.host_out_cap, (size_t)BG_SLOT_BYTES + 64, true));
+    memcpy(l.h_in, src, slen);
+    const size_t up = ((size_t)slen + 15u) & ~(size_t)15u;
+    if (up) CK(cudaMemcpyAsync(l.d_in, l.h_in, up, cudaMemcpyHostToDevice, l.stream));
+    uint32_t *tail = (uint32_t *)(l.d_slots + BG_SLOT_BYTES);    /* [0] member size, [1] status, [2] error flag (inside the slot array's pad) */
+    BgzfCompressArgs a;
+    memset(&a, 0, sizeof a);
+    a.in = l.d_in;
+    a.in_bytes = slen;
+    a.block_size = B200BGZF_MAX_BLOCK_SIZE;
+    a.nblocks = 1;
+    a.prm = bg_level_params(level);
+    a.slots = l.d_slots;
+    a.out_len = tail;
+    a.status = tail + 1;
+    a.err_flag = tail + 2;
+    a.scratch = l.d_scratch;
+    if (a.prm.opt_passes > 0) {
+        if (!l.d_cand) CK(cudaMalloc((void **)&l.d_cand, (size_t)l.scratch_ctas * 4u * BG_MAX_BLOCK * sizeof(uint32_t)));
+        a.cand = l.d_cand;
+    }
+    a.crctab = ctx->d_crctab;
+    a.crcpow = ctx->d_crcpow;
+    a.prof = nullptr;
+    CK(bgzf_launch_compress(&a, 1, l.stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(l.h_out, l.d_slots, (size_t)BG_SLOT_BYTES + 8, cudaMemcpyDeviceToHost, l.stream));
+    if (sleep_wait) {
+        /* more callers in flight than host cores (samtools -@64 on a 16-core box): a spinning wait would starve the
+         * others, so poll with short sleeps instead */
+        if (!l.done) CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        CK(cudaEventRecord(l.done, l.stream));
+        /* (a blocking-sync event costs about a millisecond per wake-up here; short sleeps between polls cost ~0.1 ms) */
+        const struct timespec nap = { 0, 30000 };
+        cudaError_t q;
+        while ((q = cudaEventQuery(l.done)) == cudaErrorNotReady) nanosleep(&nap, nullptr);
+        CK(q);
+    } else {
+        CK(cudaStreamSynchronize(l.stream));
+    }
+    const uint32_t n = *(const uint32_t *)(l.h_out + BG_SLOT_BYTES);
+    int st = 0;
+    if (n == 0 || n > *dlen) st = B200BGZF_E_NOFIT;
+    else { memcpy(dst, l.h_out, n); *dlen = n; }
+    if (status) *status = st;
+    return st;
+}
+
 }  // namespace
 
 extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, const uint32_t *slen, void *const *dst,
@@ -436,17 +500,23 @@ extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *cons
     if (nblocks <= kHookLaneBlocks) {
         /* small calls (the hook): grab any free one-block lane so concurrent callers run on different SMs */
         Lane *l = nullptr;
+        int in_flight = 0;
         {
             std::unique_lock<std::mutex> lk(ctx->hook_mu);
             for (;;) {
-                for (auto &h : ctx->hook_lanes)
-                    if (!h.busy) { l = &h; break; }
+                in_flight = 0;
+                for (auto &h : ctx->hook_lanes) {
+                    if (h.busy) in_flight++;
+                    else if (!l) l = &h;
+                }
                 if (l) break;
                 ctx->hook_cv.wait(lk);
             }
             l->busy = true;
         }
-        int r = compress_blocks_on_lane(ctx, *l, src, slen, dst, dlen, status, nblocks, level);
+        static const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+        int r = nblocks == 1 ? compress_one_on_lane(ctx, *l, src[0], slen[0], dst[0], dlen, status, level, in_flight + 1 > cores)
+                             : compress_blocks_on_lane(ctx, *l, src, slen, dst, dlen, status, nblocks, level);
         {
             std::lock_guard<std::mutex> lk(ctx->hook_mu);
             l->busy = false;
@@ -580,55 +650,58 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
 {
     (void)flags;
     if (!ctx || !in || !out_bytes) return B200BGZF_E_ARG;
-    /* host walk of the member headers (applet/7bgzf.c:306-330) */
     const uint8_t *p = (const uint8_t *)in;
-    std::vector<uint64_t> in_off, out_off;
-    size_t off = 0, total = 0;
-    while (off < in_bytes) {
-        const uint32_t sz = member_size(p + off, in_bytes - off);
-        if (!sz) return B200BGZF_E_FORMAT;
-        const uint8_t *t = p + off + sz - 4;
-        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-        if (isize > B200BGZF_MAX_BLOCK_SIZE) return B200BGZF_E_FORMAT;
-        in_off.push_back(off);
-        out_off.push_back(total);
-        total += isize;
-        off += sz;
-    }
-    *out_bytes = total;
-    if (total > out_cap || (!out && total)) return B200BGZF_E_NOSPACE;
-    const size_t nm = in_off.size();
-    in_off.push_back(in_bytes);
-    out_off.push_back(total);
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    /* batches small enough that the first kernel starts early and the D2H copies run back to back behind it,
-     * large enough that kLanes of them in flight fill the GPU (one warp per member, ~3100 resident) */
-    const size_t batch = 1024;
+    /* Batches of members rotate through the lanes (H2D, kernel, D2H on the lane's stream).  The host walk of the
+     * member headers (applet/7bgzf.c:306-330) is done batch by batch, between submissions, so the GPU starts on the
+     * first members while the host is still finding the later ones; the first batches are small so that the D2H
+     * copies — the longest leg — start early, then kInflateBatch members each over kInflateLanes lanes. */
+    const size_t kBatchMax = kInflateBatch;
+    const int nlanes = kInflateLanes;
+    size_t batch = kBatchMax < 128 ? kBatchMax : 128;
     int r;
     bool bad = false;
-    size_t i = 0;
+    size_t off = 0, total = 0, i = 0;
+    *out_bytes = 0;
     auto complete = [&](Lane &l) -> int {
         CK(cudaStreamSynchronize(l.stream));
         if (l.h_total[1]) bad = true;
         l.pending = false;
         return 0;
     };
-    for (size_t first = 0; first < nm; first += batch, i++) {
-        Lane &l = ctx->lanes[i % kLanes];
+    auto drain = [&]() -> int {
+        for (auto &l : ctx->lanes)
+            if (l.pending && (r = complete(l))) return r;
+        return 0;
+    };
+    while (off < in_bytes) {
+        Lane &l = ctx->lanes[i % nlanes];
         if (l.pending && (r = complete(l))) return r;
-        const size_t nb = std::min(batch, nm - first);
-        const size_t cbytes = (size_t)(in_off[first + nb] - in_off[first]);
-        const size_t obytes = (size_t)(out_off[first + nb] - out_off[first]);
-        if ((r = lane_reserve(ctx, l, (uint32_t)batch, cbytes + 256, obytes + 256, false))) return r;
-        CK(grow(&l.h_meta, &l.meta_cap, 2 * batch, true));
-        for (size_t k = 0; k < nb; k++) {
-            l.h_meta[k] = in_off[first + k] - in_off[first];
-            l.h_meta[batch + k] = out_off[first + k] - out_off[first];
+        if ((r = lane_reserve(ctx, l, (uint32_t)kBatchMax, 0, 0, false))) return r;
+        CK(grow(&l.h_meta, &l.meta_cap, 2 * kBatchMax, true));
+        /* walk the next `batch` members */
+        const size_t in0 = off, out0 = total;
+        size_t nb = 0;
+        while (nb < batch && off < in_bytes) {
+            const uint32_t sz = member_size(p + off, in_bytes - off);
+            if (!sz) { drain(); return B200BGZF_E_FORMAT; }
+            const uint8_t *t = p + off + sz - 4;
+            const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            if (isize > B200BGZF_MAX_BLOCK_SIZE) { drain(); return B200BGZF_E_FORMAT; }
+            l.h_meta[nb] = off - in0;
+            l.h_meta[kBatchMax + nb] = total - out0;
+            total += isize;
+            off += sz;
+            nb++;
         }
-        CK(cudaMemcpyAsync(l.d_in, p + in_off[first], cbytes, cudaMemcpyHostToDevice, l.stream));
+        *out_bytes = total;
+        if (total > out_cap || (!out && total)) { drain(); return B200BGZF_E_NOSPACE; }
+        const size_t cbytes = off - in0, obytes = total - out0;
+        if ((r = lane_reserve(ctx, l, (uint32_t)kBatchMax, cbytes + 256, obytes + 256, false))) return r;
+        CK(cudaMemcpyAsync(l.d_in, p + in0, cbytes, cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemcpyAsync(l.d_inoff, l.h_meta, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
-        CK(cudaMemcpyAsync(l.d_outoff, l.h_meta + batch, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemcpyAsync(l.d_outoff, l.h_meta + kBatchMax, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
         BgzfInflateArgs a;
         memset(&a, 0, sizeof a);
@@ -642,11 +715,12 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
         a.crctab = ctx->d_crctab;
         CK(bgzf_launch_inflate(&a, l.stream));
         ctx->launches += 1;
-        if (obytes) CK(cudaMemcpyAsync((uint8_t *)out + out_off[first], l.d_out, obytes, cudaMemcpyDeviceToHost, l.stream));
+        if (obytes) CK(cudaMemcpyAsync((uint8_t *)out + out0, l.d_out, obytes, cudaMemcpyDeviceToHost, l.stream));
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
         l.pending = true;
+        i++;
+        batch = batch * 2 < kBatchMax ? batch * 2 : kBatchMax;
     }
-    for (auto &l : ctx->lanes)
-        if (l.pending && (r = complete(l))) return r;
+    if ((r = drain())) return r;
     return bad ? B200BGZF_E_FORMAT : B200BGZF_OK;
 }

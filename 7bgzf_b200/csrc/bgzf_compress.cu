@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "bgzf_block.h"
 #include "bgzf_kernels.h"
 
@@ -510,8 +512,15 @@ bgzf_gather_kernel(const uint8_t *slots, const uint32_t *len, const uint64_t *of
 
 extern "C" cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(bgzf_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e != cudaSuccess) return e;
+    /* (per device, once: the hook launches this kernel from many threads at a high rate) */
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured.load() >> dev) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(bgzf_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(1ull << dev);
+    }
     bgzf_compress_kernel<<<grid, BG_THREADS, SM_TOTAL, stream>>>(*a);
     return cudaGetLastError();
 }

@@ -24,9 +24,11 @@
 #include "bgzf_block.h"
 #include "bgzf_kernels.h"
 
-#define INF_LROOT 10
+#ifndef INF_LROOT
+#define INF_LROOT 9     /* 9-bit litlen root + 1 KiB window + 64 registers: 6.5 KB and one warp per member => 32 members per SM */
+#endif
 #define INF_DROOT 8
-#define INF_LTAB (1024 + 352)   /* litlen root + sub-tables (valid codes need <= 1334) */
+#define INF_LTAB ((1u << INF_LROOT) + 352u)   /* litlen root + sub-tables (valid codes need <= 1334 with a 10-bit root, 852 with 9) */
 #define INF_DTAB (256 + 160)    /* offset root + sub-tables (valid codes need <= 402) */
 #define INF_PTAB 128
 #define INF_WARPS_PER_CTA 1
@@ -52,7 +54,9 @@
 #define INF_E_STORED 7u     /* LEN != ~NLEN */
 #define INF_E_SHORT 8u      /* output shorter than ISIZE */
 
-#define INF_WIN 2048u            /* bytes of recent output kept in shared memory per member (power of two) */
+#ifndef INF_WIN
+#define INF_WIN 1024u            /* bytes of recent output kept in shared memory per member (power of two) */
+#endif
 
 struct InfSmem {
     uint32_t ltab[INF_LTAB];
@@ -70,6 +74,7 @@ struct OutWin {
     uint8_t *gline;      /* 128-byte aligned global base (gline + apos = address of output byte) */
     uint8_t *win;
     uint32_t first;      /* apos of the member's first byte (0..127) */
+    uint32_t end;        /* apos one past the member's last byte (first + ISIZE): nothing at or beyond it is stored */
     uint32_t apos;       /* apos of the next byte to produce */
     uint32_t flushed;    /* lines below this index are in global memory */
     uint32_t lane;
@@ -81,23 +86,29 @@ __device__ __forceinline__ void ow_flush_lines(OutWin &o, uint32_t upto_line)
     for (uint32_t L = o.flushed; L < upto_line; L++) {
         const uint32_t a = L * 128u + o.lane * 4u;
         const uint32_t v = *(const uint32_t *)(o.win + (a & (INF_WIN - 1u)));
-        if (a >= o.first) {
+        if (a >= o.first && a + 4 <= o.end) {
             *(uint32_t *)(o.gline + a) = v;                /* whole word belongs to this member */
-        } else if (a + 4 > o.first) {
-            for (uint32_t k = o.first - a; k < 4; k++) o.gline[a + k] = (uint8_t)(v >> (8 * k));   /* ragged first word */
+        } else {
+            for (uint32_t k = 0; k < 4; k++)               /* ragged first / last word */
+                if (a + k >= o.first && a + k < o.end) o.gline[a + k] = (uint8_t)(v >> (8 * k));
         }
     }
     o.flushed = upto_line;
 }
 
-__device__ __forceinline__ void ow_advance(OutWin &o, uint32_t nbytes)
+/* Literals are not checked against the end of the output one by one: the window is circular, so a corrupt stream
+ * can do no harm there, and what leaves for global memory is clipped to the member.  The check happens here, when a
+ * line completes (at most 128 + 258 bytes late).  Returns true when the stream has produced more than ISIZE. */
+__device__ __forceinline__ bool ow_advance(OutWin &o, uint32_t nbytes)
 {
     o.apos += nbytes;
     const uint32_t complete = o.apos >> 7;
     if (complete != o.flushed) {
         __syncwarp();
         ow_flush_lines(o, complete);
+        return o.apos > o.end;
     }
+    return false;
 }
 
 /* the tail that never completed a line */
@@ -105,7 +116,8 @@ __device__ __forceinline__ void ow_finish(OutWin &o)
 {
     __syncwarp();
     const uint32_t base = o.flushed * 128u;
-    for (uint32_t a = (base > o.first ? base : o.first) + o.lane; a < o.apos; a += 32)
+    const uint32_t stop = o.apos < o.end ? o.apos : o.end;
+    for (uint32_t a = (base > o.first ? base : o.first) + o.lane; a < stop; a += 32)
         o.gline[a] = o.win[a & (INF_WIN - 1u)];
 }
 
@@ -333,7 +345,10 @@ __device__ __forceinline__ uint32_t lookup(const uint32_t *tab, uint32_t root, u
     return e;
 }
 
-__global__ void __launch_bounds__(32 * INF_WARPS_PER_CTA)
+#ifndef INF_MINCTAS
+#define INF_MINCTAS 32
+#endif
+__global__ void __launch_bounds__(32 * INF_WARPS_PER_CTA, INF_MINCTAS)
 bgzf_inflate_kernel(BgzfInflateArgs a)
 {
     __shared__ InfSmem sm;
@@ -366,9 +381,10 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
     o.gline = out - o.first;
     o.win = (uint8_t *)sm.win;
     o.apos = o.first;
+    o.end = o.first + isize;
     o.flushed = 0;
     o.lane = lane;
-    const uint32_t end_apos = o.first + isize;
+    const uint32_t end_apos = o.end;
     bool last = false;
     while (!last && err == INF_OK) {
         last = br_take(r, 1);
@@ -443,14 +459,10 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
                 nb = INF_LROOT + (e & 15u);
             }
             if (e & F_LIT) {
-                if (o.apos >= end_apos) { err = INF_E_OVERRUN; break; }
-                uint32_t cnt = 1;
-                if (e & F_LIT2) {
-                    if (o.apos + 2 <= end_apos) cnt = 2; else nb = (e >> 4) & 15u;
-                }
+                const uint32_t cnt = 1u + ((e >> 14) & 1u);          /* F_LIT2: two literals in one entry */
                 br_consume(r, nb);
                 if (lane < cnt) o.win[(o.apos + lane) & (INF_WIN - 1u)] = (uint8_t)(e >> (16 + 8 * lane));
-                ow_advance(o, cnt);
+                if (ow_advance(o, cnt)) { err = INF_E_OVERRUN; break; }
                 continue;
             }
             const uint32_t kind = (e >> 8) & 7u;

@@ -3,7 +3,7 @@ NVCC      ?= nvcc
 CC        ?= gcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v $(NVEXTRA)
 CFLAGS    := -O2 -Wall -fPIC -std=gnu99
 PKG       := 7bgzf_b200
 CSRC      := $(PKG)/csrc
@@ -37,13 +37,16 @@ $(PKG)/7bgzf: $(OBJ)/applet_7bgzf.o $(PKG)/lib7bgzf_b200.so
 	$(CC) -o $@ $(OBJ)/applet_7bgzf.o -L$(PKG) -l7bgzf_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
 
 # ---- test / bench infrastructure (never linked into the product) ----
-testlibs: build/libdatagen.so build/libemul.so build/datagen oracle/liboracle.so
+testlibs: build/libdatagen.so build/libemul.so build/datagen build/hook_mt oracle/liboracle.so
 
 build/libdatagen.so: tools/datagen.c
 	@mkdir -p build
 	$(CC) -O2 -fPIC -shared -o $@ $<
 build/datagen: tools/datagen.c
 	$(CC) -O2 -DDATAGEN_MAIN -o $@ $<
+build/hook_mt: tools/hook_mt.c
+	@mkdir -p build
+	$(CC) -O2 -o $@ $< -ldl -lpthread
 build/libemul.so: tests/model/emul.cpp $(CSRC)/bgzf_block.h $(CSRC)/bgzf_tables.h
 	@mkdir -p build
 	$(CXX) -O2 -fPIC -shared -o $@ tests/model/emul.cpp
