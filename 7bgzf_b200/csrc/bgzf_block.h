@@ -79,7 +79,7 @@
 enum {
     BG_S_NUSED = 0, BG_S_MINLEN, BG_S_HBYTES, BG_S_CRC, BG_S_NITEMS, BG_S_NL, BG_S_ND, BG_S_NP,
     BG_S_BTYPE, BG_S_HDRBITS, BG_S_TOKBITS, BG_S_PAYLOAD, BG_S_STATUS, BG_S_DYNSYMS, BG_S_STASYMS, BG_S_WALKEND,
-    BG_S_EXTRA, BG_S_DYNHDR, BG_S_WLIST,
+    BG_S_EXTRA, BG_S_DYNHDR, BG_S_WLIST, BG_S_HM, BG_S_HOVF, BG_S_DM, BG_S_PM,
     BG_S_COUNT = 32
 };
 
@@ -899,6 +899,7 @@ BG_HD void bg_phase_clear_freq(const BgCtx &c, uint32_t t, uint32_t T)
     uint32_t *f = (uint32_t *)(c.regb + BG_B_LFREQ);
     for (uint32_t i = t; i < (BG_B_LLEN - BG_B_LFREQ) / 4; i += T)
         f[i] = 0;
+    if (t == 0) { c.scal[BG_S_HM] = 0; c.scal[BG_S_DM] = 0; }
 }
 
 /* phase 11: tally symbols along the parse; remember match offsets in smem */
@@ -915,7 +916,15 @@ BG_HD void bg_phase_tally(const BgCtx &c, uint32_t t, uint32_t T)
         uint32_t end = ch * BG_CHUNK + BG_CHUNK;
         if (end > n) end = n;
         while (p < end) {
-            if (c.stepcode[p] == 0) {
+            if ((p & 3u) == 0 && p + 4 <= end && *(const uint32_t *)(c.stepcode + p) == 0) {
+                /* four literals in a row (sequence and quality text is full of them): one look at the step codes */
+                const uint32_t d = c.dataw[p >> 2];
+                bg_add32(&lfreq[d & 0xffu], 1);
+                bg_add32(&lfreq[(d >> 8) & 0xffu], 1);
+                bg_add32(&lfreq[(d >> 16) & 0xffu], 1);
+                bg_add32(&lfreq[d >> 24], 1);
+                p += 4;
+            } else if (c.stepcode[p] == 0) {
                 bg_add32(&lfreq[bg_ld8(c.dataw, p)], 1);
                 p++;
             } else {
@@ -936,8 +945,11 @@ BG_HD void bg_phase_lkeys(const BgCtx &c, uint32_t t, uint32_t T)
 {
     const uint32_t *lfreq = (const uint32_t *)(c.regb + BG_B_LFREQ);
     uint32_t *keys = (uint32_t *)(c.regb + BG_B_KEYS);
-    for (uint32_t i = t; i < 512; i += T)
-        keys[i] = (i < 288 && lfreq[i]) ? (lfreq[i] << 9) | i : 0xFFFFFFFFu;
+    for (uint32_t i = t; i < 512; i += T) {
+        const bool used = i < 288 && lfreq[i];
+        keys[i] = used ? (lfreq[i] << 9) | i : 0xFFFFFFFFu;
+        if (used) bg_add32(&c.scal[BG_S_HM], 1);       /* number of used litlen symbols (zeroed with the histograms) */
+    }
 }
 
 /* ---- sequential Huffman pieces (one thread; arrays in shared memory) ---------------------------- */
@@ -953,6 +965,22 @@ BG_HD uint32_t bg_small_keys(const uint32_t *freq, uint32_t nsym, uint32_t *keys
         keys[i] = k;
     }
     return m;
+}
+
+/* The same sort, one thread per symbol: a used symbol's place is the number of used symbols with a smaller key
+ * (keys are distinct: the symbol is part of the key).  Returns true for a used symbol (the caller counts them). */
+BG_HD bool bg_rank_key(const uint32_t *freq, uint32_t nsym, uint32_t sym, uint32_t *keys)
+{
+    const uint32_t f = freq[sym];
+    if (!f) return false;
+    const uint32_t k = (f << 9) | sym;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nsym; j++) {
+        const uint32_t fj = freq[j];
+        rank += (fj != 0 && ((fj << 9) | j) < k) ? 1u : 0u;
+    }
+    keys[rank] = k;
+    return true;
 }
 
 /* keys: ascending (freq<<9|sym) for the m used symbols.  lens[] must be zeroed by the caller.
@@ -1070,27 +1098,123 @@ BG_HD uint32_t bg_precode_order(uint32_t i)
     return (uint32_t)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31u);
 }
 
-/* phase 13: thread 0 builds the litlen lengths, thread 32 the distance lengths */
+/* The two-queue merge of bg_huff_lengths() with the heads of both queues held in registers, so that picking the two
+ * lightest nodes does not wait for shared memory (a node just made is often the very next one needed).  Same picks,
+ * same ties (a leaf before an internal node of equal weight).  w[0..m) = leaf weights ascending; fills w[m..2m-1), par. */
+BG_HD void bg_huff_merge(uint32_t m, uint32_t *w, uint16_t *par)
+{
+    const uint32_t none = 0xFFFFFFFFu;
+    uint32_t a = 0, b = m, e = m;
+    uint32_t wa = w[0], wb = none;
+    while (e < 2 * m - 1) {
+        uint32_t x0, x1, v0, v1;
+        if (wa <= wb) { x0 = a; v0 = wa; a++; wa = a < m ? w[a] : none; }
+        else { x0 = b; v0 = wb; b++; wb = b < e ? w[b] : none; }
+        if (wa <= wb && wa != none) { x1 = a; v1 = wa; a++; wa = a < m ? w[a] : none; }
+        else { x1 = b; v1 = wb; b++; wb = b < e ? w[b] : none; }
+        const uint32_t v = v0 + v1;
+        w[e] = v;
+        par[x0] = (uint16_t)e;
+        par[x1] = (uint16_t)e;
+        if (b == e) wb = v;                     /* the internal queue had run empty: the new node is its head */
+        e++;
+    }
+}
+
+#define BG_B_BLC BG_B_SCRATCH           /* u32[16] litlen codewords per length */
+
+/* phase 13a (parallel): leaf weights in sorted order, cleared lengths and counters */
+BG_HD void bg_phase_huff_prep(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint8_t *rb = c.regb;
+    const uint32_t *keys = (const uint32_t *)(rb + BG_B_KEYS);
+    uint32_t *w = (uint32_t *)(rb + BG_B_TREEW);
+    const uint32_t m = c.scal[BG_S_HM];
+    for (uint32_t i = t; i < 288; i += T) {
+        if (i < m) w[i] = keys[i] >> 9;
+        rb[BG_B_LLEN + i] = 0;
+    }
+    if (t < 16) ((uint32_t *)(rb + BG_B_BLC))[t] = 0;
+    if (t == 16 % T) c.scal[BG_S_HOVF] = 0;
+    /* the distance alphabet's sort keys, one thread per symbol (BG_S_DM was zeroed with the histograms) */
+    for (uint32_t sym = t; sym < 30; sym += T)
+        if (bg_rank_key((const uint32_t *)(rb + BG_B_DFREQ), 30, sym, (uint32_t *)(rb + BG_B_DKEYS))) bg_add32(&c.scal[BG_S_DM], 1);
+}
+
+/* phase 13b: thread 0 merges the litlen tree, thread 32 builds the (small) distance code start to finish */
 BG_HD void bg_phase_huff(const BgCtx &c, uint32_t t, uint32_t T)
 {
-    (void)T;
     uint8_t *rb = c.regb;
     if (t == 0) {
         const uint32_t *keys = (const uint32_t *)(rb + BG_B_KEYS);
         uint8_t *llen = rb + BG_B_LLEN;
-        for (uint32_t i = 0; i < 288; i++) llen[i] = 0;
-        uint32_t m = 0;
-        while (m < 288 && keys[m] != 0xFFFFFFFFu) m++;
-        bg_huff_lengths(keys, m, 15, (uint32_t *)(rb + BG_B_TREEW), (uint16_t *)(rb + BG_B_TREEP),
-                        (uint32_t *)(rb + BG_B_SCRATCH), llen);
+        const uint32_t m = c.scal[BG_S_HM];
+        if (m == 0) { llen[0] = 1; llen[1] = 1; }
+        else if (m == 1) {
+            const uint32_t s1 = keys[0] & 511u;
+            llen[s1] = 1;
+            llen[s1 ? 0 : 1] = 1;
+        } else {
+            bg_huff_merge(m, (uint32_t *)(rb + BG_B_TREEW), (uint16_t *)(rb + BG_B_TREEP));
+        }
     }
     if (t == 32 % T) {
         uint32_t *dkeys = (uint32_t *)(rb + BG_B_DKEYS);
         uint8_t *dlen = rb + BG_B_DLEN;
         for (uint32_t i = 0; i < 32; i++) dlen[i] = 0;
-        uint32_t m = bg_small_keys((const uint32_t *)(rb + BG_B_DFREQ), 30, dkeys);
+        const uint32_t m = c.scal[BG_S_DM];
         bg_huff_lengths(dkeys, m, 15, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP),
                         (uint32_t *)(rb + BG_B_SCRATCH) + 32, dlen);
+    }
+}
+
+/* phase 13c (parallel): depth of every node by walking up to the root; leaves count into the per-length table, and
+ * every node deeper than 15 counts as overflow — the sums the sequential pass of bg_huff_lengths() produces */
+BG_HD void bg_phase_huff_depth(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint8_t *rb = c.regb;
+    const uint32_t m = c.scal[BG_S_HM];
+    if (m < 2) return;
+    const uint16_t *par = (const uint16_t *)(rb + BG_B_TREEP);
+    uint32_t *blc = (uint32_t *)(rb + BG_B_BLC);
+    const uint32_t root = 2 * m - 2;
+    for (uint32_t i = t; i < root; i += T) {
+        uint32_t d = 0;
+        for (uint32_t x = i; x != root; x = par[x]) d++;
+        if (d > 15) { d = 15; bg_add32(&c.scal[BG_S_HOVF], 1); }
+        if (i < m) bg_add32(&blc[d], 1);
+    }
+}
+
+/* phase 13d (thread 0): the overflow repair on the per-length counts (zlib's gen_bitlen) */
+BG_HD void bg_phase_huff_fix(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    (void)T;
+    if (t != 0 || c.scal[BG_S_HM] < 2) return;
+    uint32_t *blc = (uint32_t *)(c.regb + BG_B_BLC);
+    int overflow = (int)c.scal[BG_S_HOVF];
+    while (overflow > 0) {
+        uint32_t bits = 14;
+        while (blc[bits] == 0) bits--;
+        blc[bits]--;
+        blc[bits + 1] += 2;
+        blc[15]--;
+        overflow -= 2;
+    }
+}
+
+/* phase 13e (parallel): the i-th rarest symbol gets the i-th longest length */
+BG_HD void bg_phase_huff_assign(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint8_t *rb = c.regb;
+    const uint32_t m = c.scal[BG_S_HM];
+    if (m < 2) return;
+    const uint32_t *keys = (const uint32_t *)(rb + BG_B_KEYS);
+    const uint32_t *blc = (const uint32_t *)(rb + BG_B_BLC);
+    for (uint32_t i = t; i < m; i += T) {
+        uint32_t bits = 15, cum = blc[15];
+        while (cum <= i) cum += blc[--bits];
+        rb[BG_B_LLEN + (keys[i] & 511u)] = (uint8_t)bits;
     }
 }
 
@@ -1156,6 +1280,7 @@ BG_HD void bg_phase_hdr1(const BgCtx &c, uint32_t t, uint32_t T)
     c.scal[BG_S_EXTRA] += extra;
 #endif
     if (t < 20) ((uint32_t *)(rb + BG_B_PFREQ))[t] = 0;
+    if (t == 20 % T) c.scal[BG_S_PM] = 0;
     if (t < 12) ((uint32_t *)(rb + BG_B_RUNMASK))[t] = 0;
 }
 
@@ -1261,6 +1386,13 @@ BG_HD void bg_phase_hdr4(const BgCtx &c, uint32_t t, uint32_t T)
     }
 }
 
+/* the precode alphabet's sort keys, one thread per symbol */
+BG_HD void bg_phase_hdr4b(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    for (uint32_t sym = t; sym < 19; sym += T)
+        if (bg_rank_key((const uint32_t *)(c.regb + BG_B_PFREQ), 19, sym, (uint32_t *)(c.regb + BG_B_PKEYS))) bg_add32(&c.scal[BG_S_PM], 1);
+}
+
 BG_HD void bg_phase_hdr5(const BgCtx &c, uint32_t t, uint32_t T, uint32_t nitems)
 {
     (void)T;
@@ -1272,7 +1404,7 @@ BG_HD void bg_phase_hdr5(const BgCtx &c, uint32_t t, uint32_t T, uint32_t nitems
     uint8_t *plen = rb + BG_B_PLEN;
     uint32_t *pkeys = (uint32_t *)(rb + BG_B_PKEYS);
     for (uint32_t i = 0; i < 19; i++) plen[i] = 0;
-    const uint32_t pm = bg_small_keys(pfreq, 19, pkeys);
+    const uint32_t pm = c.scal[BG_S_PM];
     bg_huff_lengths(pkeys, pm, 7, (uint32_t *)(rb + BG_B_DTREEW), (uint16_t *)(rb + BG_B_DTREEP), (uint32_t *)(rb + BG_B_SCRATCH) + 16, plen);
     uint32_t np = 19;
     while (np > 4 && plen[bg_precode_order(np - 1)] == 0) np--;
@@ -1425,6 +1557,12 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
             uint32_t end = ch * BG_CHUNK + BG_CHUNK;
             if (end > n) end = n;
             while (p < end) {
+                if ((p & 3u) == 0 && p + 4 <= end && *(const uint32_t *)(c.stepcode + p) == 0) {
+                    const uint32_t d = c.dataw[p >> 2];                 /* four literals in a row */
+                    bits += llen[d & 0xffu] + llen[(d >> 8) & 0xffu] + llen[(d >> 16) & 0xffu] + llen[d >> 24];
+                    p += 4;
+                    continue;
+                }
                 uint32_t sc = c.stepcode[p];
                 if (sc == 0) {
                     bits += llen[bg_ld8(c.dataw, p)];
@@ -1597,6 +1735,16 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
         BgWriter w;
         bg_w_init(w, c.out, base + hdrbits + cbits[ch]);
         while (p < end) {
+            if ((p & 3u) == 0 && p + 4 <= end && *(const uint32_t *)(c.stepcode + p) == 0) {
+                /* four literals in a row: two puts of two code words each (<= 30 bits) */
+                const uint32_t d = c.dataw[p >> 2];
+                const uint32_t b0 = d & 0xffu, b1 = (d >> 8) & 0xffu, b2 = (d >> 16) & 0xffu, b3 = d >> 24;
+                const uint32_t l0 = llen[b0], l1 = llen[b1], l2 = llen[b2], l3 = llen[b3];
+                bg_w_put(w, (uint32_t)lcode[b0] | ((uint32_t)lcode[b1] << l0), l0 + l1);
+                bg_w_put(w, (uint32_t)lcode[b2] | ((uint32_t)lcode[b3] << l2), l2 + l3);
+                p += 4;
+                continue;
+            }
             uint32_t sc = c.stepcode[p];
             if (sc == 0) {
                 uint32_t b = bg_ld8(c.dataw, p);

@@ -406,7 +406,15 @@ bgzf_compress_kernel(BgzfCompressArgs a)
             PROF_MARK(7);
             bitonic_sort_512((uint32_t *)(c.regb + BG_B_KEYS), t);
             PROF_MARK(11);
+            bg_phase_huff_prep(c, t, T);
+            __syncthreads();
             bg_phase_huff(c, t, T);
+            __syncthreads();
+            bg_phase_huff_depth(c, t, T);
+            __syncthreads();
+            bg_phase_huff_fix(c, t, T);
+            __syncthreads();
+            bg_phase_huff_assign(c, t, T);
             __syncthreads();
             PROF_MARK(12);
         }
@@ -418,6 +426,8 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         __syncthreads();
         const uint32_t nitems = block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_CBITS), scan_scratch, t);
         bg_phase_hdr4(c, t, T);
+        __syncthreads();
+        bg_phase_hdr4b(c, t, T);
         __syncthreads();
         bg_phase_hdr5(c, t, T, nitems);
         __syncthreads();
@@ -434,8 +444,10 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         bg_phase_hdr_bits(c, t, T);
         bg_phase_sizes(c, t, T);
         __syncthreads();
+        PROF_MARK(19);
         block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_CBITS), scan_scratch, t);
         block_exclusive_scan_1024((uint32_t *)(c.regb + BG_B_IOFF), scan_scratch, t);
+        PROF_MARK(20);
         bg_phase_zero_out(c, t, T);
         __syncthreads();
         PROF_MARK(14);

@@ -103,7 +103,11 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
             uint32_t *keys = (uint32_t *)(c.regb + BG_B_KEYS);
             std::sort(keys, keys + 512);
         }
+        run(bg_phase_huff_prep, c, order, k++);
         run(bg_phase_huff, c, order, k++);
+        run(bg_phase_huff_depth, c, order, k++);
+        run(bg_phase_huff_fix, c, order, k++);
+        run(bg_phase_huff_assign, c, order, k++);
     }
     run(bg_phase_hdr1, c, order, k++);
     run(bg_phase_hdr2, c, order, k++);
@@ -114,6 +118,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
         for (uint32_t i = 0; i < BG_MAX_CHUNKS; i++) { uint32_t v = cb[i]; cb[i] = nitems; nitems += v; }
     }
     run(bg_phase_hdr4, c, order, k++);
+    run(bg_phase_hdr4b, c, order, k++);
     for (uint32_t t = 0; t < BG_THREADS; t++) bg_phase_hdr5(c, t, BG_THREADS, nitems);
     {   // cross-check against the sequential rule
         static uint16_t ref_items[400]; uint32_t ref_pf[19];

@@ -58,4 +58,5 @@ print("cycles/block %.0f  build-link %.0f" % (sum(prof) / nblk, prof[10] / nblk)
 print("  ".join(f"{n}={p / nblk:.0f}" for n, p in zip(names, prof[:10])))
 print("  detail: sort=%.0f trees=%.0f header=%.0f codes=%.0f | accept=%.0f jump=%.0f | sizes+scan+zero=%.0f emit=%.0f" % tuple(x / nblk for x in (prof[11], prof[12], prof[13], prof[8], prof[15], prof[5], prof[14], prof[9])))
 print("  walk: clear+mark=%.0f a=%.0f b=%.0f c=%.0f" % tuple(x / nblk for x in (prof[16], prof[17], prof[18], prof[6])))
+print("  sizes=%.0f scans=%.0f zero=%.0f" % tuple(x / nblk for x in (prof[19], prof[20], prof[14])))
 print("launches", c.launches())
