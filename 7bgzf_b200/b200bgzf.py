@@ -15,6 +15,7 @@ BLOCK_SIZE = 0xFF00
 MAX_BLOCK_SIZE = 0x10000
 APPEND_EOF = 1
 VERIFY = 2
+E_NOFIT, E_ARG, E_CUDA, E_FORMAT, E_NOSPACE, E_CRC = 1, -1, -2, -3, -4, -5
 EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 EXPORTS = [

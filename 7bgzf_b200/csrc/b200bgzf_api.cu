@@ -579,7 +579,6 @@ extern "C" int b200bgzf_inflate_size_host(const void *in, size_t in_bytes, size_
 extern "C" int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes, void *d_out, size_t out_cap,
                                        size_t *out_bytes, unsigned flags, void *stream_)
 {
-    (void)flags;
     if (!ctx || !d_in || !out_bytes || in_bytes < 28) return B200BGZF_E_ARG;
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -638,17 +637,19 @@ extern "C" int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size
     a.status = ctx->d_inf_status;
     a.err_flag = ctx->d_idx_status + 1;
     a.crctab = ctx->d_crctab;
+    a.crcpow = ctx->d_crcpow;
+    a.verify_crc = (flags & B200BGZF_VERIFY) ? 1 : 0;
     CK(bgzf_launch_inflate(&a, stream));
-    ctx->launches += 1;
+    ctx->launches += 1 + a.verify_crc;
     CK(cudaMemcpyAsync(ctx->h_idx + 3, ctx->d_idx_status + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    return (uint32_t)ctx->h_idx[3] ? B200BGZF_E_FORMAT : B200BGZF_OK;
+    const uint32_t ef = (uint32_t)ctx->h_idx[3];
+    return (ef & 1u) ? B200BGZF_E_FORMAT : (ef & 2u) ? B200BGZF_E_CRC : B200BGZF_OK;
 }
 
 extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
                                      unsigned flags)
 {
-    (void)flags;
     if (!ctx || !in || !out_bytes) return B200BGZF_E_ARG;
     const uint8_t *p = (const uint8_t *)in;
     DeviceGuard g(ctx->device);
@@ -661,12 +662,13 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
     const int nlanes = kInflateLanes;
     size_t batch = kBatchMax < 128 ? kBatchMax : 128;
     int r;
-    bool bad = false;
+    bool bad = false, badcrc = false;
     size_t off = 0, total = 0, i = 0;
     *out_bytes = 0;
     auto complete = [&](Lane &l) -> int {
         CK(cudaStreamSynchronize(l.stream));
-        if (l.h_total[1]) bad = true;
+        if (l.h_total[1] & 1u) bad = true;
+        if (l.h_total[1] & 2u) badcrc = true;
         l.pending = false;
         return 0;
     };
@@ -713,8 +715,10 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
         a.status = l.d_status;
         a.err_flag = (uint32_t *)(l.d_total + 1);
         a.crctab = ctx->d_crctab;
+        a.crcpow = ctx->d_crcpow;
+        a.verify_crc = (flags & B200BGZF_VERIFY) ? 1 : 0;
         CK(bgzf_launch_inflate(&a, l.stream));
-        ctx->launches += 1;
+        ctx->launches += 1 + a.verify_crc;
         if (obytes) CK(cudaMemcpyAsync((uint8_t *)out + out0, l.d_out, obytes, cudaMemcpyDeviceToHost, l.stream));
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
         l.pending = true;
@@ -722,5 +726,5 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
         batch = batch * 2 < kBatchMax ? batch * 2 : kBatchMax;
     }
     if ((r = drain())) return r;
-    return bad ? B200BGZF_E_FORMAT : B200BGZF_OK;
+    return bad ? B200BGZF_E_FORMAT : badcrc ? B200BGZF_E_CRC : B200BGZF_OK;
 }

@@ -20,6 +20,9 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <atomic>
 
 #include "bgzf_block.h"
 #include "bgzf_kernels.h"
@@ -513,6 +516,61 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* B200BGZF_VERIFY: CRC-32 of every member's output against the trailer (the reference's decompress loop checks
+ * neither CRC32 nor ISIZE, applet/7bgzf.c:350-354; htslib does).  One CTA per member: the payload is staged in
+ * shared memory and summed with the compressor's own slice-and-combine phase (bg_phase_scan: 1024 right-aligned
+ * 68-byte slices, each multiplied by x^(8*68*k) mod P — zlib's crc32_combine algebra, lib/zlib/crc32.c:1021-1026). */
+#define INF_E_CRC 9u
+#define VER_SMEM (BG_DATA_BYTES + 1024u + 256u + 4u * BG_S_COUNT)
+
+__global__ void __launch_bounds__(BG_THREADS, 2)
+bgzf_verify_kernel(BgzfInflateArgs a)
+{
+    extern __shared__ __align__(16) uint8_t vs[];
+    const uint32_t t = threadIdx.x, m = blockIdx.x;
+    if (m >= a.nblocks || a.status[m] != INF_OK) return;          /* (uniform for the CTA) */
+    const uint8_t *mem = a.in + a.in_off[m];
+    const uint32_t msize = ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
+    const uint8_t *tr = mem + msize - 8;
+    const uint32_t want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+    const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    const uint8_t *out = a.out + a.out_off[m];
+    BgCtx c;
+    memset(&c, 0, sizeof c);
+    c.dataw = (uint32_t *)vs;
+    c.crctab = (uint32_t *)(vs + BG_DATA_BYTES);
+    c.litflag = vs + BG_DATA_BYTES + 1024u;
+    c.scal = (uint32_t *)(vs + BG_DATA_BYTES + 1024u + 256u);
+    c.crcpow = a.crcpow;
+    c.n = isize;
+    /* stage: bytes up to the first 16-byte boundary of the source, 16-byte loads for the body, bytes for the rest */
+    const uint32_t head = isize < 16 ? isize : (uint32_t)((16u - ((uintptr_t)out & 15u)) & 15u);
+    const uint32_t body = (isize - head) & ~15u;
+    if (t < head) vs[t] = out[t];
+    for (uint32_t i = t * 16u; i < body; i += BG_THREADS * 16u) {
+        const uint4 v = __ldcs((const uint4 *)(out + head + i));
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        for (uint32_t k = 0; k < 16; k++) vs[head + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));   /* (destination is not aligned when head != 0) */
+    }
+    for (uint32_t i = head + body + t; i < isize; i += BG_THREADS) vs[i] = out[i];
+    if (t < 28) vs[isize + t] = 0;
+    if (t < 256) c.crctab[t] = a.crctab[t];
+    if (t < BG_S_COUNT) c.scal[t] = 0;
+    __syncthreads();
+    bg_phase_scan(c, t, BG_THREADS);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t r = c.scal[BG_S_CRC];
+        if ((isize >> 2) == 0) r = 0xFFFFFFFFu;
+        for (uint32_t p = isize & ~3u; p < isize; p++) r = bg_crc_byte(c.crctab, r, vs[p]);
+        if (~r != want) {
+            a.status[m] = INF_E_CRC;
+            atomicOr(a.err_flag, 2u);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* member index of a device-resident stream                                                         */
 
 #define IDX_TILE 32768u
@@ -632,6 +690,17 @@ extern "C" cudaError_t bgzf_launch_inflate(const BgzfInflateArgs *a, cudaStream_
         configured = true;
     }
     bgzf_inflate_kernel<<<a->nblocks, 32 * INF_WARPS_PER_CTA, 0, stream>>>(*a);
+    if (a->verify_crc) {
+        static std::atomic<unsigned long long> vconf{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((vconf.load() >> dev) & 1ull)) {
+            cudaError_t e = cudaFuncSetAttribute(bgzf_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VER_SMEM);
+            if (e != cudaSuccess) return e;
+            vconf.fetch_or(1ull << dev);
+        }
+        bgzf_verify_kernel<<<a->nblocks, BG_THREADS, VER_SMEM, stream>>>(*a);
+    }
     return cudaGetLastError();
 }
 

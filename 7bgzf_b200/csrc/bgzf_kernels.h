@@ -36,8 +36,9 @@ struct BgzfInflateArgs {
     uint8_t *out;              /* device */
     uint32_t *status;          /* device: 0 ok, else error code per member */
     uint32_t *err_flag;        /* device: set to non-zero when any member fails */
-    int verify_crc;
+    int verify_crc;            /* also run bgzf_verify_kernel: CRC-32 of every member's output against its trailer */
     const uint32_t *crctab;
+    const uint32_t *crcpow;    /* device u32[1024] (verify) */
 };
 
 #ifdef __cplusplus

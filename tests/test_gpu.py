@@ -199,6 +199,38 @@ def test_device_resident_api_roundtrip(codec):
         codec.inflate_device(bad.data_ptr(), n, back.data_ptr(), back.numel(), stream=s)
 
 
+def test_verify_flag_checks_crc32_of_every_member(codec):
+    """B200BGZF_VERIFY: CRC32 of the inflated payload against the trailer (the reference's decompress loop does not
+    check it, applet/7bgzf.c:350-354): a flipped trailer byte is caught with the flag and ignored without."""
+    import torch
+    data = H.synth("fastq", 7 * H.BLOCK + 4321) + b"tail"
+    for stream in (codec.compress(data, 6), H.Ref(6).compress_stream(data)[0] + H.EOF_BLOCK if H.have_ref() else None):
+        if stream is None:
+            continue
+        assert codec.inflate(stream, flags=b200bgzf.VERIFY) == data          # intact: passes, host path
+        mem = H.members(stream)
+        off, size = mem[3][0], mem[3][1]
+        for victim in (off + size - 8, off + size - 5):                      # first and last byte of the CRC32 field
+            bad = bytearray(stream)
+            bad[victim] ^= 0x40
+            bad = bytes(bad)
+            assert codec.inflate(bad) == data                                # like the reference: not checked
+            with pytest.raises(b200bgzf.B200BgzfError) as e:
+                codec.inflate(bad, flags=b200bgzf.VERIFY)
+            assert e.value.code == b200bgzf.E_CRC
+            d = torch.frombuffer(bytearray(bad), dtype=torch.uint8).cuda()
+            back = torch.empty(len(data) + 64, dtype=torch.uint8, device="cuda")
+            s = torch.cuda.current_stream().cuda_stream
+            assert codec.inflate_device(d.data_ptr(), len(bad), back.data_ptr(), back.numel(), stream=s) == len(data)
+            with pytest.raises(b200bgzf.B200BgzfError) as e:
+                codec.inflate_device(d.data_ptr(), len(bad), back.data_ptr(), back.numel(), flags=b200bgzf.VERIFY, stream=s)
+            assert e.value.code == b200bgzf.E_CRC
+        # a payload byte changed by a literal flip (stream still decodes, same length): only the CRC can tell
+    # odd sizes and unaligned output offsets: every member of a ragged stream verifies
+    ragged = b"".join(codec.compress(H.synth("sam", n), 6, eof=False) for n in (1, 3, 17, 4097, 65280, 33333)) + H.EOF_BLOCK
+    assert codec.inflate(ragged, flags=b200bgzf.VERIFY) == b"".join(H.synth("sam", n) for n in (1, 3, 17, 4097, 65280, 33333))
+
+
 HOOK_DRIVER = r"""
 import ctypes, sys, threading
 sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
