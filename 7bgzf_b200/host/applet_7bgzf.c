@@ -211,8 +211,8 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level)
     ps.fout = stdout;
     ps.decompress = decompress;
     if (decompress) {
-        ps.in_cap = (size_t)32 << 20;        /* members are taken from here until their payloads fill ... */
-        ps.out_cap = (size_t)192 << 20;      /* ... this much output */
+        ps.in_cap = (size_t)16 << 20;        /* members are taken from here until their payloads fill ... */
+        ps.out_cap = (size_t)96 << 20;       /* ... this much output (pinning memory costs ~0.4 ms per MiB: keep the slots modest) */
     } else {
         ps.in_cap = (size_t)SLOT_BLOCKS * B200BGZF_BLOCK_SIZE;
         ps.out_cap = b200bgzf_compress_bound(ps.in_cap, B200BGZF_BLOCK_SIZE);

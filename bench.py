@@ -238,12 +238,12 @@ def main():
         def comp_e2e():
             clen[0] = codec.compress_into(h_in.data_ptr(), nbytes, h_out.data_ptr(), bound, args.level)
 
-        _, w_e2e, _ = run_timed(comp_e2e, args.steps, 1)
+        _, w_e2e, _ = run_timed(comp_e2e, args.steps, args.warmup)
 
         def inf_e2e():
             codec.inflate_into(h_out.data_ptr(), clen[0], h_back.data_ptr(), nbytes)
 
-        _, w_ie2e, _ = run_timed(inf_e2e, args.steps, 1)
+        _, w_ie2e, _ = run_timed(inf_e2e, args.steps, args.warmup)
     ok = bool(torch.equal(d_back, d_in)) and bool(torch.equal(h_back, h_in))
 
     steps = args.steps

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box call that produces every measured artefact of a round under gpurun_out/ (then: tools/summarise_round.sh here).
+#   gpurun --timeout 1500 -- 'bash tools/capture_round.sh r01'
+R=${1:-r01}; O=gpurun_out; mkdir -p $O
+python bench.py --steps 5 --warmup 3 > $O/bench_$R.json 2> $O/bench_$R.err
+python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_${R}_reference.json 2>> $O/bench_$R.err
+python tools/level_sweep.py 256 > $O/levels_$R.jsonl 2>> $O/bench_$R.err
+python tools/pcie_probe.py > $O/pcie_$R.txt 2>&1
+python tools/e2e_probe.py 1024 >> $O/pcie_$R.txt 2>&1
+./build/datagen sam 268435456 2 > /tmp/sam256.bin
+( export BGZF_METHOD=libdeflate6; for t in 1 16 64; do ./build/hook_mt 7bgzf_b200/7bgzf.so $t /tmp/sam256.bin 4; done; echo reference; for t in 1 16; do ./build/hook_mt oracle/_ref/7bgzf_ref.so $t /tmp/sam256.bin; done ) > $O/hook_$R.txt 2>&1
+bash tools/applet_compare.sh 1024 > $O/applet_$R.txt 2>&1
+# launch list of the bench command (shares per kernel; times under ncu are cold-cache and serialised)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$R.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_bench_$R.log 2>&1
+# one full capture of each dominant kernel
+ncu --set full --clock-control none --import-source on -k regex:bgzf_compress_kernel --launch-skip 1 --launch-count 1 -f -o $O/prof_compress_$R python tools/prof_run.py compress 148 6 fastq 2 > $O/ncu_compress_$R.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bgzf_inflate_kernel --launch-skip 1 --launch-count 1 -f -o $O/prof_inflate_$R python tools/prof_run.py inflate 1024 6 fastq 2 > $O/ncu_inflate_$R.log 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv > $O/gpu_$R.txt
+ls -la $O | tail -20
