@@ -722,11 +722,18 @@ BG_HD void bg_phase_accept(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t n = c.n, minlen = c.scal[BG_S_MINLEN];
     const int lazy = c.prm.lazy;
     const uint32_t nice = (uint32_t)c.prm.nice;
+#if defined(__CUDA_ARCH__)
+    /* the next step's loads are in flight while this step decides (the scratch is an L2 round trip away) */
+    uint4 na = make_uint4(0, 0, 0, 0);
+    uint2 nb = make_uint2(0, 0);
+    if (4 * t < n) { na = __ldcg((const uint4 *)(c.R + 4 * t)); nb = __ldcg((const uint2 *)(c.R + 4 * t + 4)); }
+#endif
     for (uint32_t p = 4 * t; p < n; p += 4 * T) {
         uint32_t r[6];
 #if defined(__CUDA_ARCH__)
-        const uint4 a = __ldcg((const uint4 *)(c.R + p));
-        const uint2 b = __ldcg((const uint2 *)(c.R + p + 4));
+        const uint4 a = na;
+        const uint2 b = nb;
+        if (p + 4 * T < n) { na = __ldcg((const uint4 *)(c.R + p + 4 * T)); nb = __ldcg((const uint2 *)(c.R + p + 4 * T + 4)); }
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y;
 #else
         for (uint32_t j = 0; j < 6; j++) r[j] = p + j < n ? c.R[p + j] : 0;
@@ -1180,7 +1187,7 @@ BG_HD void bg_phase_huff_depth(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t root = 2 * m - 2;
     for (uint32_t i = t; i < root; i += T) {
         uint32_t d = 0;
-        for (uint32_t x = i; x != root; x = par[x]) d++;
+        for (uint32_t x = i; x != root && d < 2 * 288; x = par[x]) d++;     /* (the cap only matters if memory were corrupt) */
         if (d > 15) { d = 15; bg_add32(&c.scal[BG_S_HOVF], 1); }
         if (i < m) bg_add32(&blc[d], 1);
     }
@@ -1195,7 +1202,7 @@ BG_HD void bg_phase_huff_fix(const BgCtx &c, uint32_t t, uint32_t T)
     int overflow = (int)c.scal[BG_S_HOVF];
     while (overflow > 0) {
         uint32_t bits = 14;
-        while (blc[bits] == 0) bits--;
+        while (bits > 1 && blc[bits] == 0) bits--;
         blc[bits]--;
         blc[bits + 1] += 2;
         blc[15]--;
@@ -1213,7 +1220,7 @@ BG_HD void bg_phase_huff_assign(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t *blc = (const uint32_t *)(rb + BG_B_BLC);
     for (uint32_t i = t; i < m; i += T) {
         uint32_t bits = 15, cum = blc[15];
-        while (cum <= i) cum += blc[--bits];
+        while (cum <= i && bits > 1) cum += blc[--bits];
         rb[BG_B_LLEN + (keys[i] & 511u)] = (uint8_t)bits;
     }
 }

@@ -121,6 +121,25 @@ def cpu_reference(args, data_addr, nbytes, kind_name, steps=1, warmup=0):
     return res
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU boxes have two sockets: run this rank (and first-touch its pinned buffers) on the cores next to its
+    GPU, or every host<->device copy of the end-to-end legs crosses the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +188,9 @@ def main():
     import b200bgzf
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    if numa:
+        config["host_binding"] = f"each rank pinned to the {numa} cores of its GPU's NUMA node"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
