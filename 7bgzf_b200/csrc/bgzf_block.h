@@ -1528,6 +1528,37 @@ BG_HD void bg_phase_codes_c(const BgCtx &c, uint32_t t, uint32_t T)
     codes[sym] = (uint16_t)code;
 }
 
+/* phase 14e': ready-made token tables for the two passes over the parse that follow (sizes, emit), in tree space that
+ * is dead by now:  literal b -> code | bits << 24;  match length l -> (code | extra << codelen) | bits << 24;
+ * offset slot s -> code | codelen << 24 */
+#define BG_B_LITTAB BG_B_TREEW                 /* u32[256] */
+#define BG_B_LENTAB (BG_B_TREEW + 1024u)       /* u32[260] (index = match length) */
+#define BG_B_OFFTAB (BG_B_TREEW + 2064u)       /* u32[32]  */
+BG_HD void bg_phase_tabs(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    uint8_t *rb = c.regb;
+    if (c.scal[BG_S_BTYPE] == 0) return;
+    const uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN;
+    const uint16_t *lcode = (const uint16_t *)(rb + BG_B_LCODE), *dcode = (const uint16_t *)(rb + BG_B_DCODE);
+    for (uint32_t i = t; i < 256 + 260 + 32; i += T) {
+        if (i < 256) {
+            ((uint32_t *)(rb + BG_B_LITTAB))[i] = (uint32_t)lcode[i] | ((uint32_t)llen[i] << 24);
+        } else if (i < 516) {
+            const uint32_t len = i - 256;
+            uint32_t v = 0;
+            if (len >= 3 && len <= 258) {
+                uint32_t nb, ex;
+                const uint32_t ls = 257 + bg_len_slot(len, &nb, &ex);
+                v = ((uint32_t)lcode[ls] | (ex << llen[ls])) | ((llen[ls] + nb) << 24);
+            }
+            ((uint32_t *)(rb + BG_B_LENTAB))[len] = v;
+        } else {
+            const uint32_t sl = i - 516;
+            ((uint32_t *)(rb + BG_B_OFFTAB))[sl] = sl < 30 ? (uint32_t)dcode[sl] | ((uint32_t)dlen[sl] << 24) : 0;
+        }
+    }
+}
+
 /* phase 14f: bits of every run-length item of the dynamic header (the driver turns them into bit offsets), so that
  * the header is written by one thread per item instead of one thread for all */
 #define BG_B_IOFF BG_B_XTAB       /* u32[1024]; the walk tables are dead by now */
@@ -1552,7 +1583,8 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
 {
     const uint32_t n = c.n;
     uint8_t *rb = c.regb;
-    const uint8_t *llen = rb + BG_B_LLEN, *dlen = rb + BG_B_DLEN;
+    const uint32_t *littab = (const uint32_t *)(rb + BG_B_LITTAB), *lentab = (const uint32_t *)(rb + BG_B_LENTAB);
+    const uint32_t *offtab = (const uint32_t *)(rb + BG_B_OFFTAB);
     const uint16_t *entry = (const uint16_t *)(rb + BG_B_ENTRY);
     uint32_t *cbits = (uint32_t *)(rb + BG_B_CBITS);
     const bool coded = c.scal[BG_S_BTYPE] != 0;
@@ -1566,18 +1598,18 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
             while (p < end) {
                 if ((p & 3u) == 0 && p + 4 <= end && *(const uint32_t *)(c.stepcode + p) == 0) {
                     const uint32_t d = c.dataw[p >> 2];                 /* four literals in a row */
-                    bits += llen[d & 0xffu] + llen[(d >> 8) & 0xffu] + llen[(d >> 16) & 0xffu] + llen[d >> 24];
+                    bits += (littab[d & 0xffu] >> 24) + (littab[(d >> 8) & 0xffu] >> 24) + (littab[(d >> 16) & 0xffu] >> 24) + (littab[d >> 24] >> 24);
                     p += 4;
                     continue;
                 }
                 uint32_t sc = c.stepcode[p];
                 if (sc == 0) {
-                    bits += llen[bg_ld8(c.dataw, p)];
+                    bits += littab[bg_ld8(c.dataw, p)] >> 24;
                     p++;
                 } else {
                     uint32_t len = sc == 255 ? (c.R[p] >> 16) : sc + 2, nb, ex;
-                    bits += llen[257 + bg_len_slot(len, &nb, &ex)] + nb;
-                    bits += dlen[bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex)] + nb;
+                    bits += lentab[len] >> 24;
+                    bits += (offtab[bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex)] >> 24) + nb;
                     p += len;
                 }
             }
@@ -1702,6 +1734,8 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
     const uint16_t *pcode = (const uint16_t *)(rb + BG_B_PCODE), *items = (const uint16_t *)(rb + BG_B_ITEMS);
     const uint16_t *entry = (const uint16_t *)(rb + BG_B_ENTRY);
     const uint32_t *cbits = (const uint32_t *)(rb + BG_B_CBITS);
+    const uint32_t *littab = (const uint32_t *)(rb + BG_B_LITTAB), *lentab = (const uint32_t *)(rb + BG_B_LENTAB);
+    const uint32_t *offtab = (const uint32_t *)(rb + BG_B_OFFTAB);
     const uint32_t hdrbits = c.scal[BG_S_HDRBITS];
     if (t == 0) {
         bg_emit_frame(c);
@@ -1745,24 +1779,24 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
             if ((p & 3u) == 0 && p + 4 <= end && *(const uint32_t *)(c.stepcode + p) == 0) {
                 /* four literals in a row: two puts of two code words each (<= 30 bits) */
                 const uint32_t d = c.dataw[p >> 2];
-                const uint32_t b0 = d & 0xffu, b1 = (d >> 8) & 0xffu, b2 = (d >> 16) & 0xffu, b3 = d >> 24;
-                const uint32_t l0 = llen[b0], l1 = llen[b1], l2 = llen[b2], l3 = llen[b3];
-                bg_w_put(w, (uint32_t)lcode[b0] | ((uint32_t)lcode[b1] << l0), l0 + l1);
-                bg_w_put(w, (uint32_t)lcode[b2] | ((uint32_t)lcode[b3] << l2), l2 + l3);
+                const uint32_t e0 = littab[d & 0xffu], e1 = littab[(d >> 8) & 0xffu], e2 = littab[(d >> 16) & 0xffu], e3 = littab[d >> 24];
+                const uint32_t l0 = e0 >> 24, l2 = e2 >> 24;
+                bg_w_put(w, (e0 & 0xffffffu) | ((e1 & 0xffffffu) << l0), l0 + (e1 >> 24));
+                bg_w_put(w, (e2 & 0xffffffu) | ((e3 & 0xffffffu) << l2), l2 + (e3 >> 24));
                 p += 4;
                 continue;
             }
             uint32_t sc = c.stepcode[p];
             if (sc == 0) {
-                uint32_t b = bg_ld8(c.dataw, p);
-                bg_w_put(w, lcode[b], llen[b]);
+                const uint32_t e = littab[bg_ld8(c.dataw, p)];
+                bg_w_put(w, e & 0xffffffu, e >> 24);
                 p++;
             } else {
                 uint32_t len = sc == 255 ? (c.R[p] >> 16) : sc + 2, nb, ex;
-                uint32_t ls = 257 + bg_len_slot(len, &nb, &ex);
-                bg_w_put(w, (uint32_t)lcode[ls] | (ex << llen[ls]), llen[ls] + nb);
-                uint32_t ds = bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex);
-                bg_w_put(w, (uint32_t)dcode[ds] | (ex << dlen[ds]), dlen[ds] + nb);
+                const uint32_t el = lentab[len];
+                bg_w_put(w, el & 0xffffffu, el >> 24);
+                const uint32_t eo = offtab[bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex)];
+                bg_w_put(w, (eo & 0xffffffu) | (ex << (eo >> 24)), (eo >> 24) + nb);
                 p += len;
             }
         }

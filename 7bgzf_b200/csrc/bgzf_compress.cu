@@ -440,6 +440,8 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         __syncthreads();
         bg_phase_codes_c(c, t, T);
         __syncthreads();
+        bg_phase_tabs(c, t, T);
+        __syncthreads();
         PROF_MARK(8);
         bg_phase_hdr_bits(c, t, T);
         bg_phase_sizes(c, t, T);

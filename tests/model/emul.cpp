@@ -132,6 +132,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     run(bg_phase_codes_a, c, order, k++);
     run(bg_phase_codes_b, c, order, k++);
     run(bg_phase_codes_c, c, order, k++);
+    run(bg_phase_tabs, c, order, k++);
     run(bg_phase_hdr_bits, c, order, k++);
     {   // twin of the kernel's block-wide exclusive scan
         uint32_t *io = (uint32_t *)(c.regb + BG_B_IOFF), acc = 0;
