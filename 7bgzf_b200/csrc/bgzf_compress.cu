@@ -176,10 +176,13 @@ __device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
         c.R[p] = bg_search_one(c, p);
 }
 
-/* ---- near-optimal class: one backward min-cost pass, warp w owning segment w.  The candidate lengths of a position
- * are spread over the lanes (lane j prices lengths 3+j, 35+j, ...), the cheapest is found with a single
- * redux.min on the packed (cost, length, candidate) word; the four matches of 32 positions are fetched with one
- * coalesced 16-byte load per lane and handed round with shuffles.  Same arithmetic as bg_phase_dp(). ---- */
+/* ---- near-optimal class: one backward min-cost pass, warp w owning segment w.  Same arithmetic as bg_phase_dp().
+ * Positions are taken in tiles of 32: each lane fetches the four matches of ITS position of the tile (one coalesced
+ * 16-byte load per lane, issued a tile ahead), prices their offsets and its literal, and parks the packed result in a
+ * 512-byte staging row of shared memory.  The sequential part then costs, per position: one broadcast 16-byte load
+ * of the staged row, the candidate lengths spread over the lanes (lane j prices lengths 3+j, 35+j, ...), one
+ * redux.min on the packed (cost, length, candidate) word, and the owning lane (which still holds the offsets in
+ * registers) recording cost and decision — nothing on that path goes further than shared memory. ---- */
 __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint32_t lane, uint32_t *ring)
 {
     uint32_t a, b, e;
@@ -187,42 +190,64 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
     if (a >= b) return;
     const uint8_t *rb = c.regb;
     const uint4 *cand4 = (const uint4 *)c.cand;
+    uint4 *stage = (uint4 *)(c.regb + BG_B_XTAB) + w * 32u;        /* the walk tables are dead during the passes */
     if (lane == 0) ring[e & (BG_DP_RING - 1)] = 0;
-    __syncwarp();
-    uint4 mine = make_uint4(0, 0, 0, 0);
-    uint32_t tile_top = 0;
-    for (uint32_t p = e; p-- > a;) {
-        if (((e - 1 - p) & 31u) == 0) {                     /* new tile: positions p, p-1, ..., p-31 */
-            tile_top = p;
-            mine = p >= lane ? __ldcg(cand4 + (p - lane)) : make_uint4(0, 0, 0, 0);
-        }
-        const uint32_t src = tile_top - p;
-        const uint32_t c0 = __shfl_sync(0xffffffffu, mine.x, src), c1 = __shfl_sync(0xffffffffu, mine.y, src);
-        const uint32_t c2 = __shfl_sync(0xffffffffu, mine.z, src), c3 = __shfl_sync(0xffffffffu, mine.w, src);
-        /* lane k < 4 prices the offset of candidate k */
-        const uint32_t mycand = lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
-        uint32_t nbx, exx;
-        const uint32_t myoc = (lane < 4 && (mycand & 0xffffu)) ? rb[BG_B_OFFCOST + bg_off_slot(mycand & 0xffffu, &nbx, &exx)] : 0u;
-        const uint32_t oc0 = __shfl_sync(0xffffffffu, myoc, 0), oc1 = __shfl_sync(0xffffffffu, myoc, 1);
-        const uint32_t oc2 = __shfl_sync(0xffffffffu, myoc, 2), oc3 = __shfl_sync(0xffffffffu, myoc, 3);
-        const uint32_t L0 = c0 >> 16, L1 = c1 >> 16, L2 = c2 >> 16, L3 = c3 >> 16;
-        uint32_t maxl = e - p;
-        if (L0 < maxl) maxl = L0;
-        uint32_t best = 0xffffffffu;
-        if (lane == 0)
-            best = bg_dp_pack(rb[BG_B_LITCOST + bg_ld8(c.dataw, p)] + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
-        for (uint32_t l = 3 + lane; l <= maxl; l += 32) {
-            const uint32_t k = l <= L3 ? 3 : l <= L2 ? 2 : l <= L1 ? 1 : 0;
-            const uint32_t oc = k == 3 ? oc3 : k == 2 ? oc2 : k == 1 ? oc1 : oc0;
-            const uint32_t v = bg_dp_pack(rb[BG_B_LENCOST + l] + oc + ring[(p + l) & (BG_DP_RING - 1)], l, k);
-            best = v < best ? v : best;
-        }
-        best = __reduce_min_sync(0xffffffffu, best);
-        if (lane == 0) {
-            ring[p & (BG_DP_RING - 1)] = best >> 11;
-            if (p < b) bg_dp_commit(c, p, best);
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    uint32_t top = e - 1;                                            /* first position of the current tile */
+    uint4 next = top >= lane && top - lane >= a ? __ldcg(cand4 + (top - lane)) : zero4;
+    for (;;) {
+        const uint4 mine = next;
+        const uint32_t q = top - lane;                               /* my position of this tile (may be below a: unused) */
+        const bool more = top >= a + 32u;
+        if (more) next = top - 32u >= lane && top - 32u - lane >= a ? __ldcg(cand4 + (top - 32u - lane)) : zero4;
+        {
+            uint32_t oc = 0, litc = 0;
+            if (top >= lane && q >= a) {
+                const uint32_t cd[4] = { mine.x, mine.y, mine.z, mine.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t off = cd[k] & 0xffffu;
+                    uint32_t nbx, exx;
+                    if (off) oc |= (uint32_t)rb[BG_B_OFFCOST + bg_off_slot(off, &nbx, &exx)] << (8 * k);
+                }
+                litc = rb[BG_B_LITCOST + bg_ld8(c.dataw, q)];
+            }
+            stage[lane] = make_uint4((mine.x >> 16) | (mine.y & 0xffff0000u), (mine.z >> 16) | (mine.w & 0xffff0000u), oc, litc);
         }
         __syncwarp();
+        const uint32_t steps = top - a + 1 < 32u ? top - a + 1 : 32u;
+        for (uint32_t j = 0; j < steps; j++) {
+            const uint32_t p = top - j;
+            const uint4 st = stage[j];
+            const uint32_t L0 = st.x & 0xffffu, L1 = st.x >> 16, L2 = st.y & 0xffffu, L3 = st.y >> 16;
+            uint32_t maxl = e - p;
+            if (L0 < maxl) maxl = L0;
+            uint32_t best = 0xffffffffu;
+            if (lane == 0) best = bg_dp_pack(st.w + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
+            for (uint32_t l = 3 + lane; l <= maxl; l += 32) {
+                const uint32_t k = l <= L3 ? 3 : l <= L2 ? 2 : l <= L1 ? 1 : 0;
+                const uint32_t oc = (st.z >> (8 * k)) & 0xffu;
+                const uint32_t v = bg_dp_pack(rb[BG_B_LENCOST + l] + oc + ring[(p + l) & (BG_DP_RING - 1)], l, k);
+                best = v < best ? v : best;
+            }
+            best = __reduce_min_sync(0xffffffffu, best);
+            if (lane == j) {
+                ring[p & (BG_DP_RING - 1)] = best >> 11;
+                if (p < b) {
+                    const uint32_t l = (best >> 2) & 511u, k = best & 3u;
+                    if (l == 1) {
+                        c.stepcode[p] = 0;
+                    } else {
+                        const uint32_t off = (k == 0 ? mine.x : k == 1 ? mine.y : k == 2 ? mine.z : mine.w) & 0xffffu;
+                        c.stepcode[p] = (uint8_t)(l <= 256 ? l - 2 : 255);
+                        c.R[p] = (l << 16) | off;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (!more) break;
+        top -= 32u;
     }
 }
 
