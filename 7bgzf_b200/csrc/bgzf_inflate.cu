@@ -28,7 +28,7 @@
 #include "bgzf_kernels.h"
 
 #ifndef INF_LROOT
-#define INF_LROOT 9     /* 9-bit litlen root + 1 KiB window + 64 registers: 6.5 KB and one warp per member => 32 members per SM */
+#define INF_LROOT 9     /* 9-bit litlen root + 512-byte window + 64 registers: 6.0 KB and one warp per member => 32 members per SM (the CTA limit) */
 #endif
 #define INF_DROOT 8
 #define INF_LTAB ((1u << INF_LROOT) + 352u)   /* litlen root + sub-tables (valid codes need <= 1334 with a 10-bit root, 852 with 9) */
@@ -58,7 +58,7 @@
 #define INF_E_SHORT 8u      /* output shorter than ISIZE */
 
 #ifndef INF_WIN
-#define INF_WIN 1024u            /* bytes of recent output kept in shared memory per member (power of two) */
+#define INF_WIN 512u             /* bytes of recent output kept in shared memory per member (power of two) */
 #endif
 
 struct InfSmem {

@@ -1,6 +1,7 @@
 """CPU: the C-ABI boundary — the shared objects load, export exactly what include/b200bgzf.h declares (and
 nothing unprefixed besides bgzf_compress), and fail loudly without a GPU (no CPU fallback)."""
 import ctypes
+import json
 import os
 import re
 import subprocess
@@ -98,3 +99,24 @@ def test_applet_cli_contract():
     assert r.returncode == 1                                             # two methods
     r = subprocess.run([b200bgzf.APPLET_PATH, "-d", "-l6"], input=b"", capture_output=True)
     assert r.returncode == 1                                             # method together with -d
+
+
+def test_thread_pool_harness_against_the_reference_hook(tmp_path):
+    """build/hook_mt (the stand-in for htslib's pool used for the hook numbers) drives any .so that exports
+    bgzf_compress: here the reference's, on CPU; and it fails cleanly on the GPU hook when there is no GPU."""
+    exe = os.path.join(H.ROOT, "build", "hook_mt")
+    if not os.path.exists(exe) or not H.have_ref():
+        pytest.skip("build/hook_mt or oracle/_ref missing")
+    f = tmp_path / "in.sam"
+    f.write_bytes(H.synth("sam", 6 * H.BLOCK + 123))
+    env = dict(os.environ, BGZF_METHOD="libdeflate6")
+    r = subprocess.run([exe, H.REF_SO, "3", str(f)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["threads"] == 3 and out["bytes"] == 6 * H.BLOCK + 123 and 0.05 < out["ratio"] < 0.3
+    r = subprocess.run([exe, b200bgzf.HOOK_PATH, "2", str(f)], capture_output=True, text=True, env=env)
+    try:
+        b200bgzf.Codec().close()
+        assert r.returncode == 0, r.stderr                           # (a GPU is present: the hook works)
+    except b200bgzf.B200BgzfError:
+        assert r.returncode != 0 and "failed" in r.stderr        # no GPU here: every call returns -1, nothing is faked
