@@ -51,7 +51,8 @@ struct Lane {
     size_t pend_out_off = 0;
     bool busy = false;
     int scratch_ctas = 0;
-    cudaEvent_t done = nullptr;   /* blocking-sync event (hook lanes): lets a waiting caller sleep instead of spin */
+    cudaEvent_t done = nullptr;   /* hook lanes: polled with short sleeps when callers outnumber the host's cores */
+    uint8_t *one_dev = nullptr, *one_host = nullptr;   /* one-block fast path: everything it needs in one device and one pinned slab */
 };
 
 }  // namespace
@@ -116,6 +117,8 @@ void lane_free(Lane &l)
     if (l.h_out) cudaFreeHost(l.h_out);
     if (l.h_meta) cudaFreeHost(l.h_meta);
     if (l.done) cudaEventDestroy(l.done);
+    cudaFree(l.one_dev);
+    if (l.one_host) cudaFreeHost(l.one_host);
     if (l.stream) cudaStreamDestroy(l.stream);
     l = Lane();
 }
@@ -440,28 +443,34 @@ int compress_blocks_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *const *src, 
 int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t slen, void *dst, size_t *dlen, int *status, int level,
                          bool sleep_wait)
 {
-    int r = lane_reserve(ctx, l, 1, BG_SLOT_BYTES + 64, 0, true, (int)kHookLaneBlocks);
-    if (r) return r;
-    CK(grow(&l.h_in, &l.host_in_cap, (size_t)BG_SLOT_BYTES, true));
-    CK(grow(&l.h_out, &l.host_out_cap, (size_t)BG_SLOT_BYTES + 64, true));
-    memcpy(l.h_in, src, slen);
+    /* first use of the lane: a stream and two slabs (each allocation is a device-wide synchronisation, and a pool of
+     * callers hits this at the same moment) */
+    constexpr size_t kIn = BG_SLOT_BYTES + 64, kSlot = BG_SLOT_BYTES + 64, kScratch = (size_t)BGZF_SCRATCH_WORDS * sizeof(uint32_t);
+    if (!l.stream) CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    if (!l.one_dev) {
+        CK(cudaMalloc((void **)&l.one_dev, kIn + kSlot + kScratch));
+        CK(cudaMallocHost((void **)&l.one_host, kIn + kSlot));
+    }
+    uint8_t *d_in = l.one_dev, *d_slot = l.one_dev + kIn, *h_in = l.one_host, *h_out = l.one_host + kIn;
+    uint32_t *d_scratch = (uint32_t *)(l.one_dev + kIn + kSlot);
+    memcpy(h_in, src, slen);
     const size_t up = ((size_t)slen + 15u) & ~(size_t)15u;
-    if (up) CK(cudaMemcpyAsync(l.d_in, l.h_in, up, cudaMemcpyHostToDevice, l.stream));
-    uint32_t *tail = (uint32_t *)(l.d_slots + BG_SLOT_BYTES);    /* [0] member size, [1] status, [2] error flag (inside the slot array's pad) */
+    if (up) CK(cudaMemcpyAsync(d_in, h_in, up, cudaMemcpyHostToDevice, l.stream));
+    uint32_t *tail = (uint32_t *)(d_slot + BG_SLOT_BYTES);    /* [0] member size, [1] status, [2] error flag (the slot's pad) */
     BgzfCompressArgs a;
     memset(&a, 0, sizeof a);
-    a.in = l.d_in;
+    a.in = d_in;
     a.in_bytes = slen;
     a.block_size = B200BGZF_MAX_BLOCK_SIZE;
     a.nblocks = 1;
     a.prm = bg_level_params(level);
-    a.slots = l.d_slots;
+    a.slots = d_slot;
     a.out_len = tail;
     a.status = tail + 1;
     a.err_flag = tail + 2;
-    a.scratch = l.d_scratch;
+    a.scratch = d_scratch;
     if (a.prm.opt_passes > 0) {
-        if (!l.d_cand) CK(cudaMalloc((void **)&l.d_cand, (size_t)l.scratch_ctas * 4u * BG_MAX_BLOCK * sizeof(uint32_t)));
+        if (!l.d_cand) CK(cudaMalloc((void **)&l.d_cand, (size_t)std::max(l.scratch_ctas, 1) * 4u * BG_MAX_BLOCK * sizeof(uint32_t)));
         a.cand = l.d_cand;
     }
     a.crctab = ctx->d_crctab;
@@ -469,7 +478,7 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     a.prof = nullptr;
     CK(bgzf_launch_compress(&a, 1, l.stream));
     ctx->launches += 1;
-    CK(cudaMemcpyAsync(l.h_out, l.d_slots, (size_t)BG_SLOT_BYTES + 8, cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaMemcpyAsync(h_out, d_slot, (size_t)BG_SLOT_BYTES + 8, cudaMemcpyDeviceToHost, l.stream));
     if (sleep_wait) {
         /* more callers in flight than host cores (samtools -@64 on a 16-core box): a spinning wait would starve the
          * others, so poll with short sleeps instead */
@@ -483,10 +492,10 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     } else {
         CK(cudaStreamSynchronize(l.stream));
     }
-    const uint32_t n = *(const uint32_t *)(l.h_out + BG_SLOT_BYTES);
+    const uint32_t n = *(const uint32_t *)(h_out + BG_SLOT_BYTES);
     int st = 0;
     if (n == 0 || n > *dlen) st = B200BGZF_E_NOFIT;
-    else { memcpy(dst, l.h_out, n); *dlen = n; }
+    else { memcpy(dst, h_out, n); *dlen = n; }
     if (status) *status = st;
     return st;
 }
