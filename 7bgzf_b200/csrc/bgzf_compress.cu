@@ -4,11 +4,13 @@
  *   bgzf_compress_kernel : persistent, one CTA (1024 threads) per SM; each CTA takes BGZF blocks b, b+grid, ...
  *       1. the <=64 KiB payload is staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier)
  *       2. CRC-32 slices + literal census, hash of every position             (bgzf_block.h phases)
- *       3. hash chains linked by warp 0 with __match_any_sync (in position order => deterministic)
+ *       3. hash chains: equal-hash lanes found with one ballot per hash bit (all warps), then linked through the
+ *          head table by a relay of 4 warps taking turns tile by tile (position order => deterministic)
  *       4. all-position chain search, 1024 positions at a time, results to an L2-resident scratch
+ *          (levels 10-12: up to four matches per position, then min-cost-path passes, one warp per 1/32 of the block)
  *       5. local lazy rule -> step codes, per-chunk jump table, chunk-to-chunk walk
- *       6. histograms, length-limited Huffman (bitonic sort + two-queue tree), block type choice
- *       7. per-chunk bit sizes, block-wide prefix sum, parallel bit packing, BGZF header/BSIZE/CRC/ISIZE
+ *       6. histograms, length-limited Huffman (bitonic sort, two-queue merge, parallel depths), block type choice
+ *       7. per-chunk bit sizes, block-wide prefix sums, parallel bit packing, BGZF header/BSIZE/CRC/ISIZE
  *   bgzf_scan_kernel / bgzf_gather_kernel : exclusive scan of member sizes and compaction of the
  *       fixed-stride slots into one contiguous BGZF stream (+ the 28-byte EOF marker).
  *
