@@ -79,7 +79,7 @@
 enum {
     BG_S_NUSED = 0, BG_S_MINLEN, BG_S_HBYTES, BG_S_CRC, BG_S_NITEMS, BG_S_NL, BG_S_ND, BG_S_NP,
     BG_S_BTYPE, BG_S_HDRBITS, BG_S_TOKBITS, BG_S_PAYLOAD, BG_S_STATUS, BG_S_DYNSYMS, BG_S_STASYMS, BG_S_WALKEND,
-    BG_S_EXTRA, BG_S_DYNHDR, BG_S_WLIST, BG_S_HM, BG_S_HOVF, BG_S_DM, BG_S_PM,
+    BG_S_EXTRA, BG_S_DYNHDR, BG_S_WLIST, BG_S_HM, BG_S_HOVF, BG_S_DM, BG_S_PM, BG_S_DEPTH,
     BG_S_COUNT = 32
 };
 
@@ -344,6 +344,10 @@ BG_HD void bg_phase_settle(const BgCtx &c, uint32_t t, uint32_t T)
         r = bg_crc_byte(c.crctab, r, bg_ld8(c.dataw, p));
     c.scal[BG_S_CRC] = ~r;
     c.scal[BG_S_MINLEN] = bg_min_match_len(c.scal[BG_S_NUSED], c.prm.depth, n);
+    /* binary-looking blocks (BAM records, executables: 80+ distinct byte values) get half as much chain depth again:
+     * their matches are spread over more candidates than those of text, and the fixed depth that reaches the
+     * reference's size on FASTQ/SAM text is 1 % short of it there (ratio probe) */
+    c.scal[BG_S_DEPTH] = c.scal[BG_S_NUSED] >= 80 && c.prm.opt_passes == 0 ? (uint32_t)c.prm.depth + ((uint32_t)c.prm.depth + 1) / 2 : (uint32_t)c.prm.depth;
     /* hash width follows the literal census alone (not the depth cap): cheap literals => only long matches pay */
     c.scal[BG_S_HBYTES] = bg_min_match_len(c.scal[BG_S_NUSED], 1000, n) >= 5 ? (uint32_t)c.prm.hlong : 4u;
 }
@@ -427,7 +431,7 @@ BG_HD bool bg_search_begin(const BgCtx &c, BgSearch &s, uint32_t p)
     s.best = 3;
     s.boff = 0;
     s.l = 0;
-    s.depth = c.prm.depth;
+    s.depth = (int)c.scal[BG_S_DEPTH];
     s.ext = false;
     s.ptail = bg_ld32(c.dataw, p);
     return true;
@@ -498,7 +502,7 @@ BG_HD uint32_t bg_search_one_exact(const BgCtx &c, uint32_t p)
     if (q == BG_NOPOS || p - q > 32768u) return 0;
     const uint32_t *dw = c.dataw;
     uint32_t best = 3, boff = 0, ptail = bg_ld32(dw, p);
-    int depth = c.prm.depth;
+    int depth = (int)c.scal[BG_S_DEPTH];
     const uint32_t nice = (uint32_t)c.prm.nice;
     for (;;) {
         if (bg_ld32(dw, q + best - 3) == ptail) {
@@ -531,7 +535,7 @@ BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
     if (q != BG_NOPOS && p - q <= 32768u) {
         const uint32_t *dw = c.dataw;
         uint32_t best = 3, ptail = bg_ld32(dw, p);
-        int depth = c.prm.depth;
+        int depth = (int)c.scal[BG_S_DEPTH];
         for (;;) {
             if (bg_ld32(dw, q + best - 3) == ptail) {
                 const uint32_t l = bg_match_len(dw, p, q, best > 3 ? 0 : 4, maxl);
@@ -566,7 +570,7 @@ BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
     if (q == BG_NOPOS || p - q > 32768u) return 0;
     const uint32_t *dw = c.dataw;
     uint32_t best = 3, boff = 0, ptail = bg_ld32(dw, p);
-    int depth = c.prm.depth;
+    int depth = (int)c.scal[BG_S_DEPTH];
     const uint32_t nice = (uint32_t)c.prm.nice;
     for (;;) {
         const uint32_t qn = c.prev[q];

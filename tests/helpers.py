@@ -188,3 +188,27 @@ def zlib_member(payload, level=6, strategy=zlib.Z_DEFAULT_STRATEGY):
 
 def gunzip(stream):
     return gzip.decompress(stream)
+
+
+def bamlike(n, seed=5):
+    """A BAM-shaped binary record stream made from the SAM-like text (what htslib hands to bgzf_compress when samtools
+    writes BAM, BASELINE config 5): 32-byte little-endian core, NUL-terminated name, one CIGAR word, 4-bit packed bases,
+    raw Phred bytes, a few binary tags.  Not a valid BAM file; it has BAM's byte statistics."""
+    import random, struct
+    rnd = random.Random(seed)
+    out = bytearray()
+    code = {65: 1, 67: 2, 71: 4, 84: 8, 78: 15}
+    for l in synth("sam", 2 * n).split(b"\n"):
+        f = l.split(b"\t")
+        if l.startswith(b"@") or len(f) < 11:
+            continue
+        seq, qual, name = f[9], f[10], f[0] + b"\0"
+        packed = bytes(((code.get(seq[i], 15) << 4) | (code.get(seq[i + 1], 15) if i + 1 < len(seq) else 0)) for i in range(0, len(seq), 2))
+        core = struct.pack("<iiBBHHHIiii", 0, int(f[3]) & 0x7fffffff, len(name) & 255, int(f[4]) & 255, 4681, 1, int(f[1]) & 0xffff, len(seq), 0,
+                           int(f[7]) & 0x7fffffff, max(-2**31, min(2**31 - 1, int(f[8]))))
+        tags = b"NMC" + bytes([rnd.randrange(4)]) + b"ASC" + bytes([150 - rnd.randrange(10)]) + b"RGZgrp1\0"
+        rec = core + name + struct.pack("<I", len(seq) << 4) + packed + bytes(max(0, c - 33) for c in qual) + tags
+        out += struct.pack("<I", len(rec)) + rec
+        if len(out) >= n:
+            break
+    return bytes(out[:n])

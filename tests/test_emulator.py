@@ -90,3 +90,15 @@ def test_reference_applet_decodes_our_stream(tmp_path):
     stream = H.emul_stream(data, 6)
     r = subprocess.run([H.REF_7BGZF, "-d"], input=stream, capture_output=True)
     assert r.returncode == 0 and r.stdout == data
+
+
+@needs_ref
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_size_on_bam_like_binary_records(level):
+    """what reaches bgzf_compress when samtools writes BAM (BASELINE config 5) is binary, not SAM text"""
+    data = H.bamlike(1 << 20)
+    mine = H.emul_stream(data, level)
+    _, ref_sizes, _ = H.Ref(level).compress_stream(data, keep=False)
+    assert len(mine) - 28 <= 1.03 * sum(ref_sizes), (len(mine), sum(ref_sizes))
+    rc, out, _ = H.Ref(level).inflate_stream(mine)
+    assert rc == 0 and out == data

@@ -90,6 +90,15 @@ def test_whole_stream_bit_exact_vs_emulator(codec, kind):
         assert codec.compress(data, level) == H.emul_stream(data, level)
 
 
+@pytest.mark.parametrize("level", [1, 6])
+def test_bam_like_binary_records_bit_exact_vs_emulator(codec, level):
+    """binary-looking blocks take the deeper chains (bg_phase_settle): same bytes as the CPU run, decodes, inflates"""
+    data = H.bamlike(6 * H.BLOCK + 1234)
+    got = codec.compress(data, level)
+    assert got == H.emul_stream(data, level)
+    assert H.gunzip(got) == data and codec.inflate(got, flags=b200bgzf.VERIFY) == data
+
+
 def test_odd_block_sizes_and_unaligned_sources(codec):
     """payload blocks that are not multiples of 16 bytes (no TMA alignment) and tiny blocks"""
     data = H.synth("sam", 300000) + H.lcg_noise(777)
