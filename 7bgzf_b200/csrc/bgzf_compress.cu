@@ -218,6 +218,7 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
         }
         __syncwarp();
         const uint32_t steps = top - a + 1 < 32u ? top - a + 1 : 32u;
+        uint32_t mybest = 0;
         for (uint32_t j = 0; j < steps; j++) {
             const uint32_t p = top - j;
             const uint4 st = stage[j];
@@ -226,27 +227,35 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
             if (L0 < maxl) maxl = L0;
             uint32_t best = 0xffffffffu;
             if (lane == 0) best = bg_dp_pack(st.w + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
-            for (uint32_t l = 3 + lane; l <= maxl; l += 32) {
-                const uint32_t k = l <= L3 ? 3 : l <= L2 ? 2 : l <= L1 ? 1 : 0;
-                const uint32_t oc = (st.z >> (8 * k)) & 0xffu;
-                const uint32_t v = bg_dp_pack(rb[BG_B_LENCOST + l] + oc + ring[(p + l) & (BG_DP_RING - 1)], l, k);
-                best = v < best ? v : best;
+            /* (most matches are shorter than 35: one length per lane; the loop proper is kept rolled so that the common
+             * step does not run through an unrolled loop's prologue and remainder code) */
+            uint32_t l = 3 + lane;
+            if (l <= maxl) {
+#pragma unroll 1
+                do {
+                    const uint32_t k = (l <= L3 ? 1u : 0u) + (l <= L2 ? 1u : 0u) + (l <= L1 ? 1u : 0u);
+                    const uint32_t oc = (st.z >> (8 * k)) & 0xffu;
+                    const uint32_t v = bg_dp_pack(rb[BG_B_LENCOST + l] + oc + ring[(p + l) & (BG_DP_RING - 1)], l, k);
+                    best = v < best ? v : best;
+                    l += 32;
+                } while (l <= maxl);
             }
             best = __reduce_min_sync(0xffffffffu, best);
             if (lane == j) {
                 ring[p & (BG_DP_RING - 1)] = best >> 11;
-                if (p < b) {
-                    const uint32_t l = (best >> 2) & 511u, k = best & 3u;
-                    if (l == 1) {
-                        c.stepcode[p] = 0;
-                    } else {
-                        const uint32_t off = (k == 0 ? mine.x : k == 1 ? mine.y : k == 2 ? mine.z : mine.w) & 0xffffu;
-                        c.stepcode[p] = (uint8_t)(l <= 256 ? l - 2 : 255);
-                        c.R[p] = (l << 16) | off;
-                    }
-                }
+                mybest = best;                          /* my position's decision: recorded after the tile, all lanes at once */
             }
             __syncwarp();
+        }
+        if (lane < steps && q < b) {
+            const uint32_t l = (mybest >> 2) & 511u, k = mybest & 3u;
+            if (l == 1) {
+                c.stepcode[q] = 0;
+            } else {
+                const uint32_t off = (k == 0 ? mine.x : k == 1 ? mine.y : k == 2 ? mine.z : mine.w) & 0xffffu;
+                c.stepcode[q] = (uint8_t)(l <= 256 ? l - 2 : 255);
+                c.R[q] = (l << 16) | off;
+            }
         }
         if (!more) break;
         top -= 32u;
