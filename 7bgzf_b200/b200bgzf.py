@@ -22,7 +22,7 @@ EXPORTS = [
     "b200bgzf_create", "b200bgzf_destroy", "b200bgzf_strerror", "b200bgzf_last_error", "b200bgzf_compress_bound",
     "b200bgzf_compress_device", "b200bgzf_compress_host", "b200bgzf_compress_blocks_host", "b200bgzf_inflate_size_host",
     "b200bgzf_inflate_device", "b200bgzf_inflate_host", "b200bgzf_profile", "b200bgzf_launch_count", "b200bgzf_parse_method",
-    "b200bgzf_host_alloc", "b200bgzf_host_free",
+    "b200bgzf_host_alloc", "b200bgzf_host_free", "b200bgzf_member_header",
 ]
 
 
@@ -58,6 +58,8 @@ def load(path=LIB_PATH):
     lib.b200bgzf_launch_count.argtypes = [vp]
     lib.b200bgzf_launch_count.restype = ctypes.c_ulonglong
     lib.b200bgzf_parse_method.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32), ctypes.c_char_p, sz]
+    lib.b200bgzf_member_header.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64)]
+    lib.b200bgzf_member_header.restype = u32
     return lib
 
 
@@ -162,3 +164,11 @@ class Codec:
 
     def launches(self):
         return self.lib.b200bgzf_launch_count(self.h)
+
+
+def member_header(data, lib=None):
+    """(header length, member size) of the gzip member at the front of `data` (any flavour of applet/7bgzf.c:81-131), or (0, 0)"""
+    lib = lib or load()
+    n = ctypes.c_uint64()
+    h = lib.b200bgzf_member_header(_addr(data), len(data), ctypes.byref(n))
+    return h, n.value

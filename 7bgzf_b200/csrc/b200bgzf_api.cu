@@ -554,20 +554,57 @@ extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *cons
 
 namespace {
 
-/* applet/7bgzf.c:81-131 for the BGZF flavour: returns the member size, 0 if this is not a BGZF member */
-uint32_t member_size(const uint8_t *p, size_t avail)
+uint32_t rd16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+uint32_t rd32(const uint8_t *p) { return rd16(p) | (rd16(p + 2) << 16); }
+
+/* The member header parser of the applet's decompress loop (applet/7bgzf.c:81-131), all its flavours: BGZF
+ * ("BC", BSIZE), MiGz ("MZ", compressed size), mgzip v1/v2 ("IG"), jerodsanto's mgzip; optional name / comment /
+ * header-CRC fields are skipped.  Returns the header length (offset of the DEFLATE data) and the whole member size,
+ * or 0 if `p` does not start such a member or the member is cut short by `avail`. */
+uint32_t member_parse(const uint8_t *p, size_t avail, uint64_t *member_bytes)
 {
-    if (avail < 28) return 0;
-    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || p[3] != 4) return 0;
-    if (p[10] != 6 || p[11] != 0 || p[12] != 'B' || p[13] != 'C' || p[14] != 2 || p[15] != 0) return 0;
-    const uint32_t sz = ((uint32_t)p[16] | ((uint32_t)p[17] << 8)) + 1u;
-    if (sz < 28 || sz > avail) return 0;
-    return sz;
+    if (avail < 4 || p[0] != 0x1f || p[1] != 0x8b) return 0;
+    const uint32_t flags = p[3];
+    if (p[2] != 8 || (flags & 0xE0u)) return 0;
+    size_t n = 10, xoff = 12, xlen = 0;
+    if (flags & 0x04u) {
+        if (avail < n + 2) return 0;
+        xlen = rd16(p + n);
+        n += 2;
+        xoff = n;
+        if (avail < n + xlen) return 0;
+        n += xlen;
+    }
+    if (flags & 0x08u) while (n < avail && p[n++]) {}
+    if (flags & 0x10u) while (n < avail && p[n++]) {}
+    if (flags & 0x02u) {
+        if (n + 2 > avail) return 0;
+        n += 2;
+    }
+    const uint8_t *x = p + xoff;
+    uint64_t sz;
+    if (xlen == 6 && !memcmp(x, "BC\x02\x00", 4)) sz = (uint64_t)rd16(x + 4) + 1;
+    else if (xlen == 8 && !memcmp(x, "MZ\x04\x00", 4)) sz = (uint64_t)rd32(x + 4) + n + 8;
+    else if (xlen == 20 && !memcmp(x, "IG\x10\x00", 4)) sz = rd32(x + 4);   /* (64-bit field; the reference keeps its low half: `int`) */
+    else if (xlen == 8 && !memcmp(x, "IG\x04\x00", 4)) sz = rd32(x + 4);
+    else if (xlen == 4 && x[3] == 0x7d) sz = rd32(x) & 0xffffffu;
+    else return 0;
+    if (sz < n + 8 || sz > avail || sz > 0xffffffffull || n > 0xffff) return 0;
+    *member_bytes = sz;
+    return (uint32_t)n;
 }
 
 int inflate_status_to_code(uint32_t st) { return st == 0 ? B200BGZF_OK : B200BGZF_E_FORMAT; }
 
 }  // namespace
+
+extern "C" uint32_t b200bgzf_member_header(const void *p, size_t avail, uint64_t *member_bytes)
+{
+    uint64_t sz = 0;
+    const uint32_t n = p ? member_parse((const uint8_t *)p, avail, &sz) : 0;
+    if (member_bytes) *member_bytes = n ? sz : 0;
+    return n;
+}
 
 extern "C" int b200bgzf_inflate_size_host(const void *in, size_t in_bytes, size_t *out_bytes, size_t *nmembers)
 {
@@ -575,13 +612,10 @@ extern "C" int b200bgzf_inflate_size_host(const void *in, size_t in_bytes, size_
     const uint8_t *p = (const uint8_t *)in;
     size_t off = 0, total = 0, n = 0;
     while (off < in_bytes) {
-        const uint32_t sz = member_size(p + off, in_bytes - off);
-        if (!sz) return B200BGZF_E_FORMAT;
-        const uint8_t *t = p + off + sz - 4;
-        const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-        if (isize > B200BGZF_MAX_BLOCK_SIZE) return B200BGZF_E_FORMAT;
-        total += isize;
-        off += sz;
+        uint64_t sz = 0;
+        if (!member_parse(p + off, in_bytes - off, &sz)) return B200BGZF_E_FORMAT;
+        total += rd32(p + off + sz - 4);
+        off += (size_t)sz;
         n++;
     }
     if (out_bytes) *out_bytes = total;
@@ -694,20 +728,21 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
         Lane &l = ctx->lanes[i % nlanes];
         if (l.pending && (r = complete(l))) return r;
         if ((r = lane_reserve(ctx, l, (uint32_t)kBatchMax, 0, 0, false))) return r;
-        CK(grow(&l.h_meta, &l.meta_cap, 2 * kBatchMax, true));
+        CK(grow(&l.h_meta, &l.meta_cap, 3 * kBatchMax, true));
+        uint32_t *h_hdr = (uint32_t *)(l.h_meta + 2 * kBatchMax), *h_msz = h_hdr + kBatchMax;
         /* walk the next `batch` members */
         const size_t in0 = off, out0 = total;
         size_t nb = 0;
         while (nb < batch && off < in_bytes) {
-            const uint32_t sz = member_size(p + off, in_bytes - off);
-            if (!sz) { drain(); return B200BGZF_E_FORMAT; }
-            const uint8_t *t = p + off + sz - 4;
-            const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-            if (isize > B200BGZF_MAX_BLOCK_SIZE) { drain(); return B200BGZF_E_FORMAT; }
+            uint64_t sz = 0;
+            const uint32_t hlen = member_parse(p + off, in_bytes - off, &sz);
+            if (!hlen) { drain(); return B200BGZF_E_FORMAT; }
             l.h_meta[nb] = off - in0;
             l.h_meta[kBatchMax + nb] = total - out0;
-            total += isize;
-            off += sz;
+            h_hdr[nb] = hlen;
+            h_msz[nb] = (uint32_t)sz;
+            total += rd32(p + off + sz - 4);           /* ISIZE: the member's share of the output */
+            off += (size_t)sz;
             nb++;
         }
         *out_bytes = total;
@@ -717,12 +752,16 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
         CK(cudaMemcpyAsync(l.d_in, p + in0, cbytes, cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemcpyAsync(l.d_inoff, l.h_meta, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemcpyAsync(l.d_outoff, l.h_meta + kBatchMax, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemcpyAsync(l.d_inlen, h_hdr, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
+        CK(cudaMemcpyAsync(l.d_len, h_msz, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
         BgzfInflateArgs a;
         memset(&a, 0, sizeof a);
         a.in = l.d_in;
         a.in_off = l.d_inoff;
         a.out_off = l.d_outoff;
+        a.hdr_len = l.d_inlen;                          /* headers were parsed here: any flavour the applet's loop accepts */
+        a.msize = l.d_len;
         a.nblocks = (uint32_t)nb;
         a.out = l.d_out;
         a.status = l.d_status;

@@ -361,24 +361,36 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
 
     const uint8_t *mem = a.in + a.in_off[m];
     uint32_t err = INF_OK;
-    /* header: 1f 8b 08 04 .... XLEN=6 'B' 'C' 02 00 BSIZE */
-    const bool hdr_ok = mem[0] == 0x1f && mem[1] == 0x8b && mem[2] == 8 && (mem[3] & 4) && mem[10] == 6 && mem[11] == 0 &&
-                        mem[12] == 'B' && mem[13] == 'C' && mem[14] == 2 && mem[15] == 0;
-    if (!hdr_ok) {
+    uint32_t msize, hlen;
+    if (a.hdr_len) {
+        /* the host has parsed the header (BGZF, MiGz, mgzip: applet/7bgzf.c:81-131) */
+        hlen = a.hdr_len[m];
+        msize = a.msize[m];
+    } else {
+        /* header: 1f 8b 08 04 .... XLEN=6 'B' 'C' 02 00 BSIZE */
+        const bool hdr_ok = mem[0] == 0x1f && mem[1] == 0x8b && mem[2] == 8 && (mem[3] & 4) && mem[10] == 6 && mem[11] == 0 &&
+                            mem[12] == 'B' && mem[13] == 'C' && mem[14] == 2 && mem[15] == 0;
+        if (!hdr_ok) {
+            if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
+            return;
+        }
+        hlen = 18;
+        msize = ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
+    }
+    if (msize < hlen + 8u) {
         if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
         return;
     }
-    const uint32_t msize = ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
     const uint8_t *trailer = mem + msize - 8;
     const uint32_t isize = (uint32_t)trailer[4] | ((uint32_t)trailer[5] << 8) | ((uint32_t)trailer[6] << 16) | ((uint32_t)trailer[7] << 24);
     uint8_t *out = a.out + a.out_off[m];
-    if (msize < 28 || isize > 65536u) {
+    if (!a.hdr_len && isize > 65536u) {                 /* (a BGZF payload is at most 64 KiB; other containers' members may be larger) */
         if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
         return;
     }
 
     BitReader r;
-    br_init(r, mem + 18, trailer, lane);
+    br_init(r, mem + hlen, trailer, lane);
     OutWin o;
     o.first = (uint32_t)((uintptr_t)out & 127u);
     o.gline = out - o.first;
@@ -530,11 +542,12 @@ bgzf_verify_kernel(BgzfInflateArgs a)
     const uint32_t t = threadIdx.x, m = blockIdx.x;
     if (m >= a.nblocks || a.status[m] != INF_OK) return;          /* (uniform for the CTA) */
     const uint8_t *mem = a.in + a.in_off[m];
-    const uint32_t msize = ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
+    const uint32_t msize = a.hdr_len ? a.msize[m] : ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
     const uint8_t *tr = mem + msize - 8;
     const uint32_t want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
     const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
     const uint8_t *out = a.out + a.out_off[m];
+    if (isize > BG_MAX_BLOCK) return;                 /* (members of other containers may be larger than a BGZF block: not checked) */
     BgCtx c;
     memset(&c, 0, sizeof c);
     c.dataw = (uint32_t *)vs;

@@ -32,6 +32,9 @@ struct BgzfInflateArgs {
     const uint8_t *in;         /* device: BGZF stream */
     const uint64_t *in_off;    /* device: byte offset of each member */
     const uint64_t *out_off;   /* device: byte offset of each member's payload in `out` */
+    const uint32_t *hdr_len;   /* device, optional: offset of the DEFLATE data inside each member, as found by the host's header
+                                  parser (any flavour of applet/7bgzf.c:81-131); NULL: strict BGZF headers, parsed by the kernel */
+    const uint32_t *msize;     /* device, with hdr_len: whole member size */
     uint32_t nblocks;
     uint8_t *out;              /* device */
     uint32_t *status;          /* device: 0 ok, else error code per member */

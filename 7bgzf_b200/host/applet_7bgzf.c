@@ -120,25 +120,33 @@ static size_t read_full(FILE *f, unsigned char *buf, size_t want)
     return n;
 }
 
-/* whole BGZF members at the front of buf[0..have) whose payloads fit in out_cap: bytes used, members, total ISIZE;
- * -1: not BGZF (7bgzf.c:81-131) */
-static long whole_members(const unsigned char *buf, size_t have, size_t out_cap, size_t *nm, size_t *isize_total)
+/* whole members at the front of buf[0..have) whose payloads fit in out_cap: bytes used, members, total ISIZE;
+ * -1: not a member the reference's loop would accept (7bgzf.c:81-131: BGZF, MiGz, mgzip), -2: one member alone is
+ * larger than a slot */
+static long whole_members(const unsigned char *buf, size_t have, size_t in_cap, size_t out_cap, int at_eof, size_t *nm, size_t *isize_total)
 {
     size_t used = 0;
     *nm = 0;
     *isize_total = 0;
-    while (used + 18 <= have) {
+    while (used < have) {
         const unsigned char *p = buf + used;
-        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4) || p[10] != 6 || p[12] != 'B' || p[13] != 'C') return -1;
-        size_t sz = (size_t)(p[16] | (p[17] << 8)) + 1;
-        if (sz < 28) return -1;
-        if (used + sz > have) break;
+        uint64_t sz = 0;
+        if (!b200bgzf_member_header(p, have - used, &sz)) {
+            /* either garbage, or a member that continues beyond what has been read so far */
+            if (have - used >= 2 && (p[0] != 0x1f || p[1] != 0x8b)) return -1;
+            if (!at_eof && have - used < in_cap && *nm > 0) break;
+            if (!at_eof && *nm == 0 && have - used >= in_cap) return -2;
+            if (at_eof || *nm == 0) return -1;
+            break;
+        }
         const unsigned char *t = p + sz - 4;
         const size_t isz = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
-        if (isz > B200BGZF_MAX_BLOCK_SIZE) return -1;
-        if (*isize_total + isz > out_cap) break;
+        if (*isize_total + isz > out_cap) {
+            if (*nm == 0) return -2;
+            break;
+        }
         *isize_total += isz;
-        used += sz;
+        used += (size_t)sz;
         (*nm)++;
     }
     return (long)used;
@@ -168,9 +176,10 @@ static void *reader_main(void *arg)
         sl->members = 0;
         if (ps->decompress && have) {
             size_t nm, isz;
-            const long used = whole_members(sl->in, have, ps->out_cap, &nm, &isz);
+            const long used = whole_members(sl->in, have, ps->in_cap, ps->out_cap, eof_seen, &nm, &isz);
             if (used <= 0) {                               /* not a member, or one cut short by the end of the input */
-                fprintf(stderr, "not BGZF or corrupted\n");
+                fprintf(stderr, used == -2 ? "a member larger than %zu MiB (compressed) / %zu MiB (payload) is not supported\n" : "not BGZF or corrupted\n",
+                        ps->in_cap >> 20, ps->out_cap >> 20);
                 fail(ps);
                 return NULL;
             }

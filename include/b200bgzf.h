@@ -76,6 +76,12 @@ int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, con
  * total ISIZE so the caller can size the output.
  */
 int b200bgzf_inflate_size_host(const void *in, size_t in_bytes, size_t *out_bytes, size_t *nmembers);
+/* The member header parser of that loop (_read_gz_header, applet/7bgzf.c:81-131), every flavour it accepts: BGZF ("BC"),
+ * MiGz ("MZ"), mgzip v1/v2 ("IG"), jerodsanto's mgzip; optional name / comment / header-CRC fields are skipped.  Returns
+ * the header length (offset of the DEFLATE data) and stores the whole member size, or returns 0 if `p` does not start
+ * such a member (or it is cut short by `avail`).  The *_host inflate entry points accept all of these; the
+ * device-resident one, which finds members by their signature on the device, takes BGZF only. */
+uint32_t b200bgzf_member_header(const void *p, size_t avail, uint64_t *member_bytes);
 int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes, void *d_out, size_t out_cap,
                             size_t *out_bytes, unsigned flags, void *stream);
 int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,

@@ -120,3 +120,64 @@ def test_thread_pool_harness_against_the_reference_hook(tmp_path):
         assert r.returncode == 0, r.stderr                           # (a GPU is present: the hook works)
     except b200bgzf.B200BgzfError:
         assert r.returncode != 0 and "failed" in r.stderr        # no GPU here: every call returns -1, nothing is faked
+
+
+def _gz_member(payload, flavour, level=6, name=None):
+    """one gzip member in a block-gzip flavour the reference's decompress loop accepts (applet/7bgzf.c:81-131)"""
+    import struct, zlib
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    raw = co.compress(payload) + co.flush()
+    tail = struct.pack("<II", zlib.crc32(payload), len(payload) & 0xffffffff)
+    flags = 4 | (8 if name else 0)
+    fixed = bytes([0x1f, 0x8b, 8, flags, 0, 0, 0, 0, 0, 0xff])
+    nm = (name + b"\0") if name else b""
+    def build(extra):
+        return fixed + struct.pack("<H", len(extra)) + extra + nm + raw + tail
+    if flavour == "bgzf":
+        total = len(build(b"BC\x02\x00\0\0"))
+        return build(b"BC\x02\x00" + struct.pack("<H", total - 1))
+    if flavour == "migz":
+        return build(b"MZ\x04\x00" + struct.pack("<I", len(raw)))
+    if flavour == "mgzip2":
+        total = len(build(b"IG\x04\x00\0\0\0\0"))
+        return build(b"IG\x04\x00" + struct.pack("<I", total))
+    if flavour == "mgzip1":
+        total = len(build(b"IG\x10\x00" + bytes(16)))
+        return build(b"IG\x10\x00" + struct.pack("<QQ", total, len(payload)))
+    raise ValueError(flavour)
+
+
+def test_member_header_parser_matches_the_oracle_and_the_reference_decoder(tmp_path):
+    """b200bgzf_member_header (product) against oracle_read_gz_header (restatement of applet/7bgzf.c:81-131) on every
+    flavour, with and without a name field, on truncations and on mutated bytes; and the reference applet itself
+    decodes the fixtures this test builds, so the fixtures are what the reference means by these formats."""
+    import random
+    lib = b200bgzf.load()
+    o = H.oracle()
+    payload = H.synth("sam", 70000)
+    eo, el, bl = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rnd = random.Random(7)
+    for flavour in ("bgzf", "migz", "mgzip1", "mgzip2"):
+        for name in (None, b"file.txt"):
+            m = _gz_member(payload[:40000] if flavour == "bgzf" else payload, flavour, name=name)
+            want = o.oracle_read_gz_header(m, len(m), eo, el, bl)
+            assert want > 0 and bl.value == len(m), (flavour, name)
+            assert b200bgzf.member_header(m, lib) == (want, len(m))
+            assert b200bgzf.member_header(m + b"trailing", lib) == (want, len(m))
+            assert b200bgzf.member_header(m[:-1], lib) == (0, 0)                    # cut short: not a whole member
+            for _ in range(200):                                                     # mutated headers: same verdict as the oracle
+                bad = bytearray(m)
+                k = rnd.randrange(0, want)
+                bad[k] ^= 1 << rnd.randrange(8)
+                bad = bytes(bad)
+                w = o.oracle_read_gz_header(bad, len(bad), eo, el, bl)
+                got = b200bgzf.member_header(bad, lib)
+                if w > 0 and want + 8 <= bl.value <= len(bad):
+                    assert got == (w, bl.value), (flavour, k)
+                else:
+                    assert got == (0, 0), (flavour, k)
+    assert b200bgzf.member_header(b"\x1f\x8b\x08\x00" + bytes(40), lib) == (0, 0)       # plain gzip: no block length
+    if H.have_ref():
+        stream = b"".join(_gz_member(payload, f) for f in ("migz", "mgzip2", "mgzip1")) + _gz_member(payload[:30000], "bgzf")
+        r = subprocess.run([os.path.join(H.ROOT, "oracle", "_ref", "7bgzf"), "-d"], input=stream, capture_output=True)
+        assert r.returncode == 0 and r.stdout == payload * 3 + payload[:30000]

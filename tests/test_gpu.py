@@ -240,6 +240,39 @@ def test_verify_flag_checks_crc32_of_every_member(codec):
     assert codec.inflate(ragged, flags=b200bgzf.VERIFY) == b"".join(H.synth("sam", n) for n in (1, 3, 17, 4097, 65280, 33333))
 
 
+def test_inflate_other_block_gzip_flavours_like_the_reference_loop(codec):
+    """the applet's decompress loop takes MiGz / mgzip members and optional header fields besides BGZF
+    (applet/7bgzf.c:81-131); so do the host-buffer inflate and our applet; the fixtures are pinned by the reference
+    applet in tests/test_abi.py"""
+    from test_abi import _gz_member
+    big, small = H.synth("sam", 200000), H.synth("fastq", 30000)
+    parts = [(big, "migz", None), (small, "bgzf", b"reads.fq"), (big[:70001], "mgzip2", None), (small, "mgzip1", b"x"),
+             (b"", "migz", None), (big, "migz", b"named")]
+    stream = b"".join(_gz_member(d, f, name=n) for d, f, n in parts)
+    want = b"".join(d for d, _, _ in parts)
+    assert codec.inflate(stream) == want
+    assert codec.inflate(stream, flags=b200bgzf.VERIFY) == want            # members <= 64 KiB are CRC-checked, larger ones pass
+    bad = bytearray(stream)
+    off = len(_gz_member(big, "migz"))                                      # the BGZF member's trailer CRC
+    off += len(_gz_member(small, "bgzf", name=b"reads.fq")) - 8
+    bad[off] ^= 1
+    with pytest.raises(b200bgzf.B200BgzfError) as e:
+        codec.inflate(bytes(bad), flags=b200bgzf.VERIFY)
+    assert e.value.code == b200bgzf.E_CRC
+    r = subprocess.run([b200bgzf.APPLET_PATH, "-d"], input=stream, capture_output=True)
+    assert r.returncode == 0 and r.stdout == want
+    if H.have_ref():
+        # (without the empty member: the reference reads 64 header bytes at a time and gives up on members shorter than that)
+        s2 = b"".join(_gz_member(d, f, name=n) for d, f, n in parts if d)
+        rr = subprocess.run([os.path.join(H.ROOT, "oracle", "_ref", "7bgzf"), "-d"], input=s2, capture_output=True)
+        assert rr.returncode == 0 and rr.stdout == want and codec.inflate(s2) == want
+    # truncated last member / garbage: an error, not a hang or a partial success
+    with pytest.raises(b200bgzf.B200BgzfError):
+        codec.inflate(stream[:-3])
+    with pytest.raises(b200bgzf.B200BgzfError):
+        codec.inflate(stream + b"garbage after the last member")
+
+
 HOOK_DRIVER = r"""
 import ctypes, sys, threading
 sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
