@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr uint32_t kHostBatchBlocks = 512;      /* 32 MiB of payload per pipelined batch: measured best of 296/512/592/1024/2048/4096 (all within 7 %) */
+constexpr uint32_t kHostBatchBlocks = 512;      /* 32 MiB of payload per pipelined batch: best of 296 ... 4096 (all within 7 %) */
 constexpr uint32_t kDeviceBatchBlocks = 16384;  /* 1 GiB of payload per device-resident batch */
 constexpr int kLanes = 8;        /* lanes a host-buffer call may rotate through (it uses the first few) */
 constexpr size_t kInflateBatch = 1024;  /* members per pipelined inflate batch (measured: 512 and 4096 are both slower) */
@@ -337,11 +337,12 @@ extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t 
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const uint64_t nb_total = (in_bytes + block_size - 1) / block_size;
-    /* batches rotate through kCompressLanes lanes (H2D, kernels, D2H on the lane's stream); the first ones are small so
-     * that the first kernel starts early, the later ones large so that the per-batch hand-over happens less often */
+    /* batches rotate through the lanes (H2D, kernels, D2H on the lane's stream).  Measured: 400-512 blocks per batch is
+     * best; multiples of the SM count are 5 % WORSE — when every CTA of a launch finishes at the same moment nothing of the
+     * next launch overlaps with the hand-over, while uneven block counts let its CTAs trickle in */
     const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), kHostBatchBlocks);
     const size_t batch_in = (size_t)batch * block_size, batch_out = b200bgzf_compress_bound(batch_in, block_size);
-    uint32_t cur = std::min<uint32_t>(batch, 256);
+    uint32_t cur = batch;
     size_t host_off = 0;
     bool nofit = false;
     int r;
