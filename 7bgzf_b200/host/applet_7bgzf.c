@@ -210,7 +210,7 @@ static void *writer_main(void *arg)
     }
 }
 
-static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level)
+static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t block)
 {
     struct pipe_state ps;
     memset(&ps, 0, sizeof ps);
@@ -223,8 +223,8 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level)
         ps.in_cap = (size_t)16 << 20;        /* members are taken from here until their payloads fill ... */
         ps.out_cap = (size_t)96 << 20;       /* ... this much output (pinning memory costs ~0.4 ms per MiB: keep the slots modest) */
     } else {
-        ps.in_cap = (size_t)SLOT_BLOCKS * B200BGZF_BLOCK_SIZE;
-        ps.out_cap = b200bgzf_compress_bound(ps.in_cap, B200BGZF_BLOCK_SIZE);
+        ps.in_cap = (size_t)SLOT_BLOCKS * block;
+        ps.out_cap = b200bgzf_compress_bound(ps.in_cap, B200BGZF_BLOCK_SIZE);   /* (the bound of the smaller block size is the larger one) */
     }
     const double ta = now_s();
     for (int i = 0; i < NSLOTS; i++) {
@@ -251,16 +251,24 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level)
                 if (r != 0) { fprintf(stderr, "inflate %d\n", r); ret = 1; }
                 units += (long)sl->members;
             } else {
-                r = b200bgzf_compress_host(ctx, sl->in, sl->in_len, B200BGZF_BLOCK_SIZE, level, sl->out, ps.out_cap, &sl->out_len,
+                r = b200bgzf_compress_host(ctx, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len,
                                            sl->last ? B200BGZF_APPEND_EOF : 0);
+                if (r == B200BGZF_E_NOFIT && block > B200BGZF_BLOCK_SIZE) {
+                    /* a 65536-byte payload that does not compress cannot fit a member: the reference's single-thread path
+                     * shrinks the block and redoes it (7bgzf.c:135-147,256-262); here the slot is redone in 0xff00-byte
+                     * blocks, which always fit */
+                    r = b200bgzf_compress_host(ctx, sl->in, sl->in_len, B200BGZF_BLOCK_SIZE, level, sl->out, ps.out_cap, &sl->out_len,
+                                               sl->last ? B200BGZF_APPEND_EOF : 0);
+                    units += (long)((sl->in_len + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE) - (long)((sl->in_len + block - 1) / block);
+                }
                 if (r == B200BGZF_E_NOFIT) { fprintf(stderr, "libdeflate_deflate %d\n", 1); ret = 1; }
                 else if (r != 0) { fprintf(stderr, "b200bgzf: %s (%s)\n", b200bgzf_strerror(r), b200bgzf_last_error(ctx)); ret = 1; }
-                units += (long)((sl->in_len + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE);
+                units += (long)((sl->in_len + block - 1) / block);
             }
         } else if (!decompress && sl->last) {
             /* empty tail slot: still owe the EOF marker (7bgzf.c:283-289) */
             size_t n = 0;
-            b200bgzf_compress_host(ctx, NULL, 0, B200BGZF_BLOCK_SIZE, level, sl->out, ps.out_cap, &n, B200BGZF_APPEND_EOF);
+            b200bgzf_compress_host(ctx, NULL, 0, block, level, sl->out, ps.out_cap, &n, B200BGZF_APPEND_EOF);
             sl->out_len = n;
         }
         g_t_codec += now_s() - tc;
@@ -311,7 +319,6 @@ int main(int argc, char **argv)
             if (k_flags[k].short_opt == opt)
                 levels[k] = optarg ? (int)strtol(optarg, NULL, 10) : k_flags[k].default_level;
     }
-    (void)nthreads;
     int chosen = -1, nchosen = 0, level_sum = 0;
     for (size_t k = 0; k < NFLAGS; k++)
         if (levels[k]) { chosen = (int)k; nchosen++; level_sum += levels[k]; }
@@ -335,13 +342,15 @@ int main(int argc, char **argv)
     const double t_created = now_s();
     int ret;
     if (decompress) {
-        ret = run_pipeline(ctx, 1, 0);
+        ret = run_pipeline(ctx, 1, 0, 0);
     } else {
         int level = level_sum;
         fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
         if (level < 1) level = 1;
         if (level > 12) level = 12;
-        ret = run_pipeline(ctx, 0, level);
+        /* block size rule of the reference (7bgzf.c:141-147): 0x10000 with one thread, 0xff00 with -@N; the thread count has
+         * no other meaning here (the GPU works on all blocks of a slot at once) */
+        ret = run_pipeline(ctx, 0, level, nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE);
     }
     fflush(stdout);
     const double t_piped = now_s();

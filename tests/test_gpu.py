@@ -336,6 +336,18 @@ def test_applet_roundtrip_and_stderr_contract():
         assert len(r.stdout) <= 1.03 * len(ref.stdout)
     bad = subprocess.run([b200bgzf.APPLET_PATH, "-d"], input=b"this is not bgzf at all, not even close........", capture_output=True)
     assert bad.returncode != 0 and b"not BGZF or corrupted" in bad.stderr
+    # block size rule of the reference (7bgzf.c:141-147): one thread (the default) cuts 0x10000-byte blocks, -@N 0xff00-byte ones
+    r1 = subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6"], input=data, capture_output=True)
+    assert r1.returncode == 0 and r1.stdout == H.emul_stream(data, 6, 0x10000)
+    assert [m[2] for m in H.members(r1.stdout)[:2]] == [0x10000, 0x10000]
+    if os.path.exists(H.REF_7BGZF):
+        ref1 = subprocess.run([H.REF_7BGZF, "-c", "-l6"], input=data, capture_output=True)
+        assert [m[2] for m in H.members(ref1.stdout)[:-1]] == [m[2] for m in H.members(r1.stdout)[:-1]]   # same block boundaries
+        assert len(r1.stdout) <= 1.03 * len(ref1.stdout)
+    # ... and a 0x10000-byte block that does not compress cannot fit a member: the slot is redone in 0xff00-byte blocks
+    noisy = H.lcg_noise(3 * 0x10000 + 777) + data[:100000]
+    rn = subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6"], input=noisy, capture_output=True)
+    assert rn.returncode == 0 and H.gunzip(rn.stdout) == noisy and rn.stdout == H.emul_stream(noisy, 6)
 
 
 def test_full_size_properties_1gib(codec):
