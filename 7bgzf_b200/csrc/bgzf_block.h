@@ -407,119 +407,9 @@ BG_HD uint32_t bg_match_len(const uint32_t *dw, uint32_t p, uint32_t q, uint32_t
  * of them, offsets <= 32768), keep the longest match (first found wins ties, i.e. the nearest), stop at
  * `nice` or at the end of the block.  A candidate is examined only if the 4 bytes ending just past the best
  * length so far agree (they must, for it to be longer).
- *
- * It is written as a per-lane state machine: one call of bg_search_step() does exactly one 4-byte comparison
- * (a tail check or an extension word), so the 32 lanes of a warp stay converged while each works through its
- * own candidates and positions at its own pace. */
-struct BgSearch {
-    uint32_t p, q, maxl, best, boff, l, ptail;
-    int depth;
-    bool ext;
-};
-
-/* false: nothing to search at p (result 0) */
-BG_HD bool bg_search_begin(const BgCtx &c, BgSearch &s, uint32_t p)
-{
-    uint32_t maxl = c.n - p;
-    if (maxl > 258) maxl = 258;
-    if (maxl < (uint32_t)BG_MIN_LOOKUP) return false;
-    const uint32_t q = c.prev[p];
-    if (q == BG_NOPOS || p - q > 32768u) return false;
-    s.p = p;
-    s.q = q;
-    s.maxl = maxl;
-    s.best = 3;
-    s.boff = 0;
-    s.l = 0;
-    s.depth = (int)c.scal[BG_S_DEPTH];
-    s.ext = false;
-    s.ptail = bg_ld32(c.dataw, p);
-    return true;
-}
-
-/* true: position finished, result in s.best / s.boff */
-#ifdef BG_STATS
-static unsigned long long bg_stat_steps, bg_stat_tail, bg_stat_pos;
-#endif
-BG_HD bool bg_search_step(const BgCtx &c, BgSearch &s)
-{
-#ifdef BG_STATS
-    bg_stat_steps++;
-    if (!s.ext) bg_stat_tail++;
-#endif
-    const uint32_t *dw = c.dataw;
-    const uint32_t o = s.ext ? s.l : s.best - 3;
-    const uint32_t wq = bg_ld32(dw, s.q + o);
-    const uint32_t wp = s.ext ? bg_ld32(dw, s.p + o) : s.ptail;
-    const uint32_t x = wq ^ wp;
-    bool advance;
-    if (!s.ext) {
-        advance = x != 0;
-        if (!advance) {
-            s.ext = true;                      /* tail agrees: measure the whole match */
-            s.l = s.best > 3 ? 0 : 4;          /* (with no match yet the tail is bytes 0..3: already compared) */
-        }
-    } else {
-        uint32_t len = 0;
-        bool end = true;
-        if (x == 0) {
-            s.l += 4;
-            if (s.l >= s.maxl) len = s.maxl; else end = false;
-        } else {
-            len = s.l + ((uint32_t)bg_ctz(x) >> 3);
-            if (len > s.maxl) len = s.maxl;
-        }
-        advance = end;
-        if (end) {
-            s.ext = false;
-            if (len > s.best) {
-                s.best = len;
-                s.boff = s.p - s.q;
-                if (len >= (uint32_t)c.prm.nice || len == s.maxl) return true;
-                s.ptail = bg_ld32(dw, s.p + len - 3);
-            }
-        }
-    }
-    if (advance) {
-        if (--s.depth <= 0) return true;
-        const uint32_t q = c.prev[s.q];
-        if (q == BG_NOPOS || s.p - q > 32768u) return true;
-        s.q = q;
-    }
-    return false;
-}
-
-BG_HD uint32_t bg_search_result(const BgSearch &s) { return s.best > 3 ? (s.best << 16) | s.boff : 0; }
-
-/* the same search as a plain loop, exact (every candidate fully verified) */
-BG_HD uint32_t bg_search_one_exact(const BgCtx &c, uint32_t p)
-{
-    const uint32_t n = c.n;
-    uint32_t maxl = n - p;
-    if (maxl > 258) maxl = 258;
-    if (maxl < (uint32_t)BG_MIN_LOOKUP) return 0;
-    uint32_t q = c.prev[p];
-    if (q == BG_NOPOS || p - q > 32768u) return 0;
-    const uint32_t *dw = c.dataw;
-    uint32_t best = 3, boff = 0, ptail = bg_ld32(dw, p);
-    int depth = (int)c.scal[BG_S_DEPTH];
-    const uint32_t nice = (uint32_t)c.prm.nice;
-    for (;;) {
-        if (bg_ld32(dw, q + best - 3) == ptail) {
-            const uint32_t l = bg_match_len(dw, p, q, best > 3 ? 0 : 4, maxl);
-            if (l > best) {
-                best = l;
-                boff = p - q;
-                if (l >= nice || l == maxl) break;
-                ptail = bg_ld32(dw, p + best - 3);
-            }
-        }
-        if (--depth <= 0) break;
-        q = c.prev[q];
-        if (q == BG_NOPOS || p - q > 32768u) break;
-    }
-    return best > 3 ? (best << 16) | boff : 0;
-}
+ * (A per-lane step machine — one 4-byte comparison per call, lanes refilling themselves — and a per-lane parse of
+ * ranges with match remainders were both built and measured this round; in lock-step they cost more than these
+ * nested loops save: DESIGN.md section 3, branch exp/range-parse.) */
 
 /* near-optimal class: like the exact search, but remembers the last four improvements.  Because the chain runs
  * from the nearest candidate outwards, lengths and offsets both grow along that list: for any length the
@@ -588,15 +478,6 @@ BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
         if (q == BG_NOPOS || p - q > 32768u) break;
     }
     return best > 3 ? (best << 16) | boff : 0;
-}
-
-/* step-machine twin (kept for the emulator's cross-check of both formulations) */
-BG_HD uint32_t bg_search_one_steps(const BgCtx &c, uint32_t p)
-{
-    BgSearch s;
-    if (!bg_search_begin(c, s, p)) return 0;
-    while (!bg_search_step(c, s)) {}
-    return bg_search_result(s);
 }
 
 BG_HD void bg_phase_search(const BgCtx &c, uint32_t t, uint32_t T)
@@ -965,20 +846,7 @@ BG_HD void bg_phase_lkeys(const BgCtx &c, uint32_t t, uint32_t T)
 
 /* ---- sequential Huffman pieces (one thread; arrays in shared memory) ---------------------------- */
 
-/* insertion sort of up to 32 keys, used for the distance and precode alphabets */
-BG_HD uint32_t bg_small_keys(const uint32_t *freq, uint32_t nsym, uint32_t *keys)
-{
-    uint32_t m = 0;
-    for (uint32_t s = 0; s < nsym; s++) {
-        if (!freq[s]) continue;
-        uint32_t k = (freq[s] << 9) | s, i = m++;
-        while (i > 0 && keys[i - 1] > k) { keys[i] = keys[i - 1]; i--; }
-        keys[i] = k;
-    }
-    return m;
-}
-
-/* The same sort, one thread per symbol: a used symbol's place is the number of used symbols with a smaller key
+/* Sort keys of the small alphabets (distance, precode), one thread per symbol: a used symbol's place is the number of used symbols with a smaller key
  * (keys are distinct: the symbol is part of the key).  Returns true for a used symbol (the caller counts them). */
 BG_HD bool bg_rank_key(const uint32_t *freq, uint32_t nsym, uint32_t sym, uint32_t *keys)
 {
