@@ -697,10 +697,12 @@ __global__ void bgzf_index_finish_kernel(const uint8_t *in, uint64_t n, const ui
 extern "C" cudaError_t bgzf_launch_inflate(const BgzfInflateArgs *a, cudaStream_t stream)
 {
     if (a->nblocks == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};     /* per device, once (function attributes are per device) */
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    if (!((configured.load() >> dev0) & 1ull)) {
         cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        configured.fetch_or(1ull << dev0);
     }
     bgzf_inflate_kernel<<<a->nblocks, 32 * INF_WARPS_PER_CTA, 0, stream>>>(*a);
     if (a->verify_crc) {
