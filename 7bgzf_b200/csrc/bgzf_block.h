@@ -138,7 +138,7 @@ BG_HD uint32_t bg_ld32(const uint32_t *w, uint32_t p)
     uint32_t i = p >> 2, s = (p & 3u) * 8u;
     uint32_t lo = w[i], hi = w[i + 1];
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, s);
+    return __funnelshift_r(lo, hi, p << 3);      /* (the shift count is taken modulo 32: no need to mask it first) */
 #else
     return s ? (lo >> s) | (hi << (32u - s)) : lo;
 #endif
@@ -402,6 +402,10 @@ BG_HD uint32_t bg_match_len(const uint32_t *dw, uint32_t p, uint32_t q, uint32_t
     return l > maxl ? maxl : l;
 }
 
+/* is q a candidate for p: an earlier position at most 32768 back?  One unsigned compare covers "no link" as well:
+ * BG_NOPOS is 65535 >= p, so p - q - 1 wraps around for it (as it does for q == p). */
+BG_HD bool bg_in_window(uint32_t p, uint32_t q) { return p - q - 1u < 32768u; }
+
 /* phase 6: all-position search.
  * For position p: follow the chain of earlier positions with the same hash (nearest first, at most `depth`
  * of them, offsets <= 32768), keep the longest match (first found wins ties, i.e. the nearest), stop at
@@ -422,7 +426,7 @@ BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
     uint32_t maxl = n - p;
     if (maxl > 258) maxl = 258;
     uint32_t q = maxl >= (uint32_t)BG_MIN_LOOKUP ? (uint32_t)c.prev[p] : (uint32_t)BG_NOPOS;
-    if (q != BG_NOPOS && p - q <= 32768u) {
+    if (bg_in_window(p, q)) {
         const uint32_t *dw = c.dataw;
         uint32_t best = 3, ptail = bg_ld32(dw, p);
         int depth = (int)c.scal[BG_S_DEPTH];
@@ -439,7 +443,7 @@ BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
             }
             if (--depth <= 0) break;
             q = c.prev[q];
-            if (q == BG_NOPOS || p - q > 32768u) break;
+            if (!bg_in_window(p, q)) break;
         }
     }
     uint32_t *cd = c.cand + 4u * p;
@@ -457,7 +461,7 @@ BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
     if (maxl > 258) maxl = 258;
     if (maxl < (uint32_t)BG_MIN_LOOKUP) return 0;
     uint32_t q = c.prev[p];
-    if (q == BG_NOPOS || p - q > 32768u) return 0;
+    if (!bg_in_window(p, q)) return 0;
     const uint32_t *dw = c.dataw;
     uint32_t best = 3, boff = 0, ptail = bg_ld32(dw, p);
     int depth = (int)c.scal[BG_S_DEPTH];
@@ -475,7 +479,7 @@ BG_HD uint32_t bg_search_one(const BgCtx &c, uint32_t p)
         }
         if (--depth <= 0) break;
         q = qn;
-        if (q == BG_NOPOS || p - q > 32768u) break;
+        if (!bg_in_window(p, q)) break;
     }
     return best > 3 ? (best << 16) | boff : 0;
 }
