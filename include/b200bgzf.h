@@ -64,7 +64,10 @@ int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, u
 /*
  * Compress nblocks independent payloads (src[i], slen[i] <= 65536) into dst[i]; dlen[i] holds the capacity on
  * entry and the member size on return; status[i] gets the per-block code of bgzf_compress().  This is the
- * batch form of bgzf_compress.c:39-198 that the LD_PRELOAD hook funnels concurrent callers into.
+ * batch form of bgzf_compress.c:39-198.  nblocks == 1 is what the LD_PRELOAD hook calls for every htslib block:
+ * that case takes a dedicated low-latency path (one copy in, one kernel, one copy out, one synchronisation) on
+ * one of 128 independent lanes, so concurrent callers each drive their own stream and SM; callers beyond the
+ * host's core count wait by sleeping, not spinning.
  */
 int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, const uint32_t *slen, void *const *dst,
                                   size_t *dlen, int *status, uint32_t nblocks, int level);
