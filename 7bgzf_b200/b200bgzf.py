@@ -22,7 +22,7 @@ EXPORTS = [
     "b200bgzf_create", "b200bgzf_destroy", "b200bgzf_strerror", "b200bgzf_last_error", "b200bgzf_compress_bound",
     "b200bgzf_compress_device", "b200bgzf_compress_host", "b200bgzf_compress_blocks_host", "b200bgzf_inflate_size_host",
     "b200bgzf_inflate_device", "b200bgzf_inflate_host", "b200bgzf_profile", "b200bgzf_launch_count", "b200bgzf_parse_method",
-    "b200bgzf_host_alloc", "b200bgzf_host_free", "b200bgzf_member_header",
+    "b200bgzf_host_alloc", "b200bgzf_host_free", "b200bgzf_member_header", "b200bgzf_compress_host_index", "b200bgzf_gzi_format",
 ]
 
 
@@ -49,6 +49,9 @@ def load(path=LIB_PATH):
     lib.b200bgzf_compress_bound.restype = sz
     lib.b200bgzf_compress_device.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint, vp]
     lib.b200bgzf_compress_host.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint]
+    lib.b200bgzf_compress_host_index.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), sz]
+    lib.b200bgzf_gzi_format.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), sz, vp, sz]
+    lib.b200bgzf_gzi_format.restype = sz
     lib.b200bgzf_compress_blocks_host.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(vp), psz,
                                                   ctypes.POINTER(i32), u32, i32]
     lib.b200bgzf_inflate_size_host.argtypes = [vp, sz, psz, psz]
@@ -114,6 +117,16 @@ class Codec:
                                                     _addr(out), len(out), ctypes.byref(n), APPEND_EOF if eof else 0))
         return bytes(out[: n.value])
 
+    def compress_indexed(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
+        """(stream, member offsets) — b200bgzf_compress_host_index"""
+        nb = (len(data) + block_size - 1) // block_size
+        out = bytearray(self.bound(len(data), block_size))
+        off = (ctypes.c_uint64 * max(nb, 1))()
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_compress_host_index(self.h, _addr(data) if len(data) else None, len(data), block_size, level,
+                                                          _addr(out), len(out), ctypes.byref(n), APPEND_EOF if eof else 0, off, nb))
+        return bytes(out[: n.value]), list(off[:nb])
+
     def compress_into(self, src_addr, nbytes, dst_addr, dst_cap, level=6, block_size=BLOCK_SIZE, eof=True):
         n = ctypes.c_size_t()
         self._check(self.lib.b200bgzf_compress_host(self.h, src_addr, nbytes, block_size, level, dst_addr, dst_cap, ctypes.byref(n),
@@ -172,3 +185,13 @@ def member_header(data, lib=None):
     n = ctypes.c_uint64()
     h = lib.b200bgzf_member_header(_addr(data), len(data), ctypes.byref(n))
     return h, n.value
+
+
+def gzi_format(caddr, uaddr, lib=None):
+    """bytes of the .gzi for members starting at (caddr[i], uaddr[i]) — b200bgzf_gzi_format"""
+    lib = lib or load()
+    n = len(caddr)
+    ca, ua = (ctypes.c_uint64 * max(n, 1))(*caddr), (ctypes.c_uint64 * max(n, 1))(*uaddr)
+    buf = bytearray(8 + 16 * max(n - 1, 0))
+    w = lib.b200bgzf_gzi_format(ca, ua, n, _addr(buf), len(buf))
+    return bytes(buf[:w])

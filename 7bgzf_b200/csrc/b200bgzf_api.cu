@@ -49,6 +49,8 @@ struct Lane {
     /* bookkeeping of an in-flight host batch */
     bool pending = false;
     size_t pend_out_off = 0;
+    uint64_t pend_first = 0;      /* first block and block count of the batch in flight (member offsets) */
+    uint32_t pend_nb = 0;
     bool busy = false;
     int scratch_ctas = 0;
     cudaEvent_t done = nullptr;   /* hook lanes: polled with short sleeps when callers outnumber the host's cores */
@@ -328,12 +330,14 @@ extern "C" int b200bgzf_compress_device(b200bgzf_ctx *ctx, const void *d_in, siz
     return l.h_total[1] ? B200BGZF_E_NOFIT : B200BGZF_OK;
 }
 
-extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
-                                      size_t out_cap, size_t *out_bytes, unsigned flags)
+/* member_off (optional): where every member starts in `out` — the offsets the device scan computes anyway */
+extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                                            size_t out_cap, size_t *out_bytes, unsigned flags, uint64_t *member_off, size_t member_cap)
 {
     if (!ctx || !out || !out_bytes || (!in && in_bytes) || block_size == 0 || block_size > B200BGZF_MAX_BLOCK_SIZE || !level_ok(level))
         return B200BGZF_E_ARG;
     if (out_cap < b200bgzf_compress_bound(in_bytes, block_size)) return B200BGZF_E_NOSPACE;
+    if (member_off && member_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const uint64_t nb_total = (in_bytes + block_size - 1) / block_size;
@@ -350,6 +354,8 @@ extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t 
         CK(cudaStreamSynchronize(l.stream));
         const size_t total = (size_t)l.h_total[0];
         if (l.h_total[1]) nofit = true;
+        if (member_off)
+            for (uint32_t k = 0; k < l.pend_nb; k++) member_off[l.pend_first + k] = host_off + l.h_meta[k];
         CK(cudaMemcpyAsync((uint8_t *)out + host_off, l.d_out, total, cudaMemcpyDeviceToHost, l.stream));
         host_off += total;
         l.pending = false;
@@ -368,6 +374,12 @@ extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t 
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
         if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream))) return r;
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+        if (member_off) {
+            CK(grow(&l.h_meta, &l.meta_cap, (size_t)batch, true));
+            CK(cudaMemcpyAsync(l.h_meta, l.d_off, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+            l.pend_first = done;
+            l.pend_nb = nb;
+        }
         l.pending = true;
         done += nb;
         i++;
@@ -387,6 +399,25 @@ extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t 
     }
     *out_bytes = host_off;
     return nofit ? B200BGZF_E_NOFIT : B200BGZF_OK;
+}
+
+extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                                      size_t out_cap, size_t *out_bytes, unsigned flags)
+{
+    return b200bgzf_compress_host_index(ctx, in, in_bytes, block_size, level, out, out_cap, out_bytes, flags, nullptr, 0);
+}
+
+/* .gzi as bgzip -i / bgzf_index_dump write it: u64 count, then (compressed offset, uncompressed offset) of every member
+ * but the first, all little endian */
+extern "C" size_t b200bgzf_gzi_format(const uint64_t *caddr, const uint64_t *uaddr, size_t nmembers, void *dst, size_t cap)
+{
+    const size_t entries = nmembers ? nmembers - 1 : 0, need = 8 + 16 * entries;
+    if (!dst || cap < need || (nmembers && (!caddr || !uaddr))) return 0;
+    uint8_t *o = (uint8_t *)dst;
+    auto put = [&](uint64_t v) { for (int k = 0; k < 8; k++) *o++ = (uint8_t)(v >> (8 * k)); };
+    put(entries);
+    for (size_t i = 1; i < nmembers; i++) { put(caddr[i]); put(uaddr[i]); }
+    return need;
 }
 
 namespace {

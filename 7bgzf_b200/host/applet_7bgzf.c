@@ -60,6 +60,7 @@ static void usage(const char *argv0)
             "  -T, --store[=level]       1-1 (default 1) store\n"
             "  -@, --threads=threads     threads\n"
             "  -d, --decompress          decompress\n"
+            "      --gzi=FILE            (extension) also write a bgzip-style .gzi index of the members to FILE\n"
             "\nNote: every method runs on the B200 BGZF codec (libdeflate level classes 1-12).\n",
             argv0);
 }
@@ -210,8 +211,45 @@ static void *writer_main(void *arg)
     }
 }
 
-static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t block)
+/* ---- member index (--gzi): (compressed, uncompressed) start of every member, from the codec's own offsets ---- */
+struct gzi_acc {
+    uint64_t *caddr, *uaddr, *slot_off;
+    size_t n, cap, slot_cap;
+    uint64_t cbase, ubase;
+};
+static int gzi_add_slot(struct gzi_acc *g, size_t in_len, size_t out_len, uint32_t blk, int had_eof)
 {
+    const size_t nb = (in_len + blk - 1) / blk;
+    if (g->n + nb > g->cap) {
+        g->cap = (g->n + nb) * 2;
+        g->caddr = (uint64_t *)realloc(g->caddr, g->cap * sizeof(uint64_t));
+        g->uaddr = (uint64_t *)realloc(g->uaddr, g->cap * sizeof(uint64_t));
+        if (!g->caddr || !g->uaddr) return -1;
+    }
+    for (size_t b = 0; b < nb; b++) {
+        g->caddr[g->n] = g->cbase + g->slot_off[b];
+        g->uaddr[g->n++] = g->ubase + (uint64_t)b * blk;
+    }
+    g->cbase += out_len - (had_eof ? B200BGZF_EOF_BYTES : 0);
+    g->ubase += in_len;
+    return 0;
+}
+static int gzi_write(const struct gzi_acc *g, const char *path)
+{
+    const size_t need = 8 + 16 * (g->n ? g->n - 1 : 0);
+    unsigned char *buf = (unsigned char *)malloc(need);
+    FILE *f = buf ? fopen(path, "wb") : NULL;
+    int ok = f && b200bgzf_gzi_format(g->caddr, g->uaddr, g->n, buf, need) == need && fwrite(buf, 1, need, f) == need;
+    if (f && fclose(f) != 0) ok = 0;
+    free(buf);
+    if (!ok) fprintf(stderr, "cannot write the index %s\n", path);
+    return ok ? 0 : 1;
+}
+
+static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t block, const char *gzi_path)
+{
+    struct gzi_acc gzi;
+    memset(&gzi, 0, sizeof gzi);
     struct pipe_state ps;
     memset(&ps, 0, sizeof ps);
     pthread_mutex_init(&ps.mu, NULL);
@@ -233,6 +271,11 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
         if (!ps.s[i].in || !ps.s[i].out) { fprintf(stderr, "out of memory\n"); return 1; }
     }
     g_t_alloc = now_s() - ta;
+    if (gzi_path && !decompress) {
+        gzi.slot_cap = (ps.in_cap + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE;
+        gzi.slot_off = (uint64_t *)malloc(gzi.slot_cap * sizeof(uint64_t));
+        if (!gzi.slot_off) { fprintf(stderr, "out of memory\n"); return 1; }
+    }
     pthread_t rd, wr;
     pthread_create(&rd, NULL, reader_main, &ps);
     pthread_create(&wr, NULL, writer_main, &ps);
@@ -251,19 +294,22 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
                 if (r != 0) { fprintf(stderr, "inflate %d\n", r); ret = 1; }
                 units += (long)sl->members;
             } else {
-                r = b200bgzf_compress_host(ctx, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len,
-                                           sl->last ? B200BGZF_APPEND_EOF : 0);
+                uint32_t used_block = block;
+                r = b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len,
+                                                 sl->last ? B200BGZF_APPEND_EOF : 0, gzi.slot_off, gzi.slot_cap);
                 if (r == B200BGZF_E_NOFIT && block > B200BGZF_BLOCK_SIZE) {
                     /* a 65536-byte payload that does not compress cannot fit a member: the reference's single-thread path
                      * shrinks the block and redoes it (7bgzf.c:135-147,256-262); here the slot is redone in 0xff00-byte
                      * blocks, which always fit */
-                    r = b200bgzf_compress_host(ctx, sl->in, sl->in_len, B200BGZF_BLOCK_SIZE, level, sl->out, ps.out_cap, &sl->out_len,
-                                               sl->last ? B200BGZF_APPEND_EOF : 0);
+                    used_block = B200BGZF_BLOCK_SIZE;
+                    r = b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, used_block, level, sl->out, ps.out_cap, &sl->out_len,
+                                                     sl->last ? B200BGZF_APPEND_EOF : 0, gzi.slot_off, gzi.slot_cap);
                     units += (long)((sl->in_len + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE) - (long)((sl->in_len + block - 1) / block);
                 }
                 if (r == B200BGZF_E_NOFIT) { fprintf(stderr, "libdeflate_deflate %d\n", 1); ret = 1; }
                 else if (r != 0) { fprintf(stderr, "b200bgzf: %s (%s)\n", b200bgzf_strerror(r), b200bgzf_last_error(ctx)); ret = 1; }
                 units += (long)((sl->in_len + block - 1) / block);
+                if (!r && gzi.slot_off && gzi_add_slot(&gzi, sl->in_len, sl->out_len, used_block, sl->last)) { fprintf(stderr, "out of memory\n"); ret = 1; }
             }
         } else if (!decompress && sl->last) {
             /* empty tail slot: still owe the EOF marker (7bgzf.c:283-289) */
@@ -281,6 +327,8 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
     pthread_join(rd, NULL);
     pthread_join(wr, NULL);
     if (ps.failed && !ret) ret = decompress ? -1 : 1;
+    if (!ret && gzi.slot_off) ret = gzi_write(&gzi, gzi_path);
+    free(gzi.caddr); free(gzi.uaddr); free(gzi.slot_off);
     if (!ret) fprintf(stderr, "%ld done.\n", units);
     if (getenv("B200BGZF_DEBUG"))
         fprintf(stderr, "stage seconds: pinned alloc %.3f, read %.3f, codec %.3f, write %.3f\n", g_t_alloc, g_t_read, g_t_codec, g_t_write);
@@ -295,6 +343,7 @@ int main(int argc, char **argv)
 {
     int levels[NFLAGS];
     int decompress = 0, nthreads = 1, bad = 0;
+    const char *gzi_path = NULL;
     memset(levels, 0, sizeof levels);
     /* allow `cielbox 7bgzf ...` style invocation */
     if (argc > 1 && !strcmp(argv[1], "7bgzf")) { argv++; argc--; }
@@ -307,13 +356,15 @@ int main(int argc, char **argv)
         { "igzip", optional_argument, 0, 'i' },  { "kzip", optional_argument, 0, 'K' },
         { "zopfli", required_argument, 0, 'Z' }, { "store", optional_argument, 0, 'T' },
         { "threads", required_argument, 0, '@' }, { "decompress", no_argument, 0, 'd' },
-        { "help", no_argument, 0, 'h' },         { 0, 0, 0, 0 },
+        { "help", no_argument, 0, 'h' },         { "gzi", required_argument, 0, 1000 },
+        { 0, 0, 0, 0 },
     };
     int opt;
     while ((opt = getopt_long(argc, argv, "cz::m::s::l::S::n::C::i::K::Z:T::@:dh", longopts, NULL)) != -1) {
         if (opt == 'c') continue;
         if (opt == 'd') { decompress = 1; continue; }
         if (opt == '@') { nthreads = atoi(optarg); continue; }
+        if (opt == 1000) { gzi_path = optarg; continue; }
         if (opt == 'h' || opt == '?') { bad = 1; continue; }
         for (size_t k = 0; k < NFLAGS; k++)
             if (k_flags[k].short_opt == opt)
@@ -342,7 +393,7 @@ int main(int argc, char **argv)
     const double t_created = now_s();
     int ret;
     if (decompress) {
-        ret = run_pipeline(ctx, 1, 0, 0);
+        ret = run_pipeline(ctx, 1, 0, 0, NULL);
     } else {
         int level = level_sum;
         fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
@@ -350,7 +401,7 @@ int main(int argc, char **argv)
         if (level > 12) level = 12;
         /* block size rule of the reference (7bgzf.c:141-147): 0x10000 with one thread, 0xff00 with -@N; the thread count has
          * no other meaning here (the GPU works on all blocks of a slot at once) */
-        ret = run_pipeline(ctx, 0, level, nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE);
+        ret = run_pipeline(ctx, 0, level, nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE, gzi_path);
     }
     fflush(stdout);
     const double t_piped = now_s();

@@ -62,6 +62,21 @@ int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, u
                            size_t out_cap, size_t *out_bytes, unsigned flags);
 
 /*
+ * SURVEY §8(f) rank 2 — the index side-product.  Same as b200bgzf_compress_host, and also reports where every member
+ * starts: member_off[b] = byte offset in `out` of the member that carries block b (member_cap >= number of blocks;
+ * the EOF marker is not listed).  These are the offsets the device scan computes for the compaction anyway, copied
+ * back with each batch.  Together with b*block_size they are the (compressed, uncompressed) address pairs of
+ * htslib's .gzi index and the upper 48 bits of BAM virtual offsets.  The reference has no counterpart (its applet
+ * writes no index: applet/7bgzf.c:133-293); the .gzi layout follows htslib's bgzf_index_dump (not in the reference
+ * tree, so parity with htslib is unpinned — tests check the index against a header walk of the stream).
+ */
+int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                                 size_t out_cap, size_t *out_bytes, unsigned flags, uint64_t *member_off, size_t member_cap);
+/* Serialise a .gzi: u64 entry count, then (caddr, uaddr) for every member except the first (which is 0,0 by
+ * definition), little endian.  Needs 8 + 16*(nmembers-1) bytes; returns the bytes written or 0 if cap is too small. */
+size_t b200bgzf_gzi_format(const uint64_t *caddr, const uint64_t *uaddr, size_t nmembers, void *dst, size_t cap);
+
+/*
  * Compress nblocks independent payloads (src[i], slen[i] <= 65536) into dst[i]; dlen[i] holds the capacity on
  * entry and the member size on return; status[i] gets the per-block code of bgzf_compress().  This is the
  * batch form of bgzf_compress.c:39-198.  nblocks == 1 is what the LD_PRELOAD hook calls for every htslib block:

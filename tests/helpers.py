@@ -127,6 +127,18 @@ def members(stream):
     return out
 
 
+def gzi_of(stream):
+    """the .gzi htslib writes next to a stream it compressed itself: u64 count, then (compressed, uncompressed) offset of
+    every member that carries data except the first — from a header walk (oracle for b200bgzf_gzi_format / --gzi)"""
+    pairs, u = [], 0
+    for off, _size, isize, _crc in members(stream):
+        if isize:
+            pairs.append((off, u))
+        u += isize
+    body = b"".join(struct.pack("<QQ", c, a) for c, a in pairs[1:])
+    return struct.pack("<Q", max(len(pairs) - 1, 0)) + body
+
+
 def have_ref():
     return os.path.exists(REF_SO)
 

@@ -181,3 +181,24 @@ def test_member_header_parser_matches_the_oracle_and_the_reference_decoder(tmp_p
         stream = b"".join(_gz_member(payload, f) for f in ("migz", "mgzip2", "mgzip1")) + _gz_member(payload[:30000], "bgzf")
         r = subprocess.run([os.path.join(H.ROOT, "oracle", "_ref", "7bgzf"), "-d"], input=stream, capture_output=True)
         assert r.returncode == 0 and r.stdout == payload * 3 + payload[:30000]
+
+
+def test_gzi_formatter_layout():
+    """b200bgzf_gzi_format: u64 count then (caddr, uaddr) of every member but the first, little endian (htslib .gzi)"""
+    import struct
+    assert b200bgzf.gzi_format([], []) == struct.pack("<Q", 0)
+    assert b200bgzf.gzi_format([0], [0]) == struct.pack("<Q", 0)
+    ca, ua = [0, 1234, 70000, 2**33 + 5], [0, 65280, 130560, 2**34 + 7]
+    want = struct.pack("<Q", 3) + b"".join(struct.pack("<QQ", c, u) for c, u in zip(ca[1:], ua[1:]))
+    assert b200bgzf.gzi_format(ca, ua) == want
+    # too small a destination writes nothing
+    lib = b200bgzf.load()
+    import ctypes
+    a = (ctypes.c_uint64 * 4)(*ca)
+    b = (ctypes.c_uint64 * 4)(*ua)
+    buf = bytearray(8 + 16 * 3 - 1)
+    assert lib.b200bgzf_gzi_format(a, b, 4, b200bgzf._addr(buf), len(buf)) == 0
+    # and the header-walk oracle of tests/helpers.py agrees on a hand-made stream (zlib-made members)
+    stream = b"".join(H.zlib_member(pl) for pl in (b"a" * 100, b"b" * 7, b"c" * 5000)) + b200bgzf.EOF_BLOCK
+    offs = [m[0] for m in H.members(stream)][:3]
+    assert H.gzi_of(stream) == b200bgzf.gzi_format(offs, [0, 100, 107])

@@ -350,6 +350,37 @@ def test_applet_roundtrip_and_stderr_contract():
     assert rn.returncode == 0 and H.gunzip(rn.stdout) == noisy and rn.stdout == H.emul_stream(noisy, 6)
 
 
+def test_member_offsets_and_gzi_index(codec, tmp_path):
+    """SURVEY §8(f) rank 2: the member offsets of the device scan, as an ABI output and as the applet's --gzi file;
+    checked against a header walk of the stream, and used for random access"""
+    data = H.synth("fastq", 5 * 1024 * 1024 + 321) + H.lcg_noise(70000) + bytes(100000)
+    for blk in (0xFF00, 0x10000 - 64):
+        stream, offs = codec.compress_indexed(data, 6, blk)
+        assert stream == codec.compress(data, 6, blk)
+        mem = H.members(stream)
+        assert offs == [m[0] for m in mem[:-1]]
+        nb = len(offs)
+        gzi = b200bgzf.gzi_format(offs, [b * blk for b in range(nb)])
+        assert gzi == H.gzi_of(stream)
+        # random access through the index: one member inflated on its own is the payload at its uncompressed address
+        for b in (0, 1, nb // 2, nb - 1):
+            one = stream[offs[b] : offs[b] + mem[b][1]]
+            assert codec.inflate(one) == data[b * blk : (b + 1) * blk]
+    # more blocks than one pipelined batch (512) and than one lane rotation
+    big = H.synth("sam", 48 << 20)
+    stream, offs = codec.compress_indexed(big, 1)
+    assert offs == [m[0] for m in H.members(stream)[:-1]] and H.gunzip(stream) == big
+    assert codec.compress_indexed(b"", 6) == (b200bgzf.EOF_BLOCK, [])
+    # the applet writes the same index (-@4: 0xff00-byte blocks; default: 0x10000, with a slot redone at 0xff00)
+    for args, src in ((["-@", "4"], data), ([], data), ([], big[: 40 << 20])):
+        path = tmp_path / "x.gzi"
+        r = subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6", "--gzi=%s" % path] + args, input=src, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6"] + args, input=src, capture_output=True).stdout
+        assert path.read_bytes() == H.gzi_of(r.stdout)
+        os.unlink(path)
+
+
 def test_full_size_properties_1gib(codec):
     """BASELINE configs[0]/[1] size: 1 GiB FASTQ-like.  Size-independent properties: round trip through our
     inflate, ISIZE sum, per-block CRC32 against zlib on a sample, combined CRC of the whole payload."""
