@@ -4,6 +4,8 @@ Golden content:
   ref_<kind>_L<level>.bgz   the reference's bgzf_compress output for 2 blocks (2*0xff00 bytes) of synthetic data
   known_answers.json        sizes / CRC32 / return codes of the reference on the SURVEY 8(c) edge inputs
   malformed.json            corrupted DEFLATE payloads with the reference decoder's verdict (0 ok / non-zero error)
+  isal_std_vects.json       the reference tree's own negative fixture (lib/isa-l/igzip/inflate_std_vects.h: 151 malformed raw
+                            DEFLATE streams), each framed as a BGZF member, with the reference decoder's verdict
 """
 import ctypes, json, os, random, sys, zlib
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -54,4 +56,27 @@ for level, maker in ((6, lambda p: H.zlib_member(p, 6)), (1, lambda p: H.zlib_me
         rc, outb, _ = ref.inflate_stream(bytes(m))
         cases.append({"hex": bytes(m).hex(), "ref_rc": rc, "ref_ok": rc == 0 and outb == base_payload, "ref_out_crc": "%08x" % zlib.crc32(outb)})
 json.dump({"payload_len": len(base_payload), "cases": cases}, open(os.path.join(out, "malformed.json"), "w"))
+
+# the reference's own malformed-stream vectors (parsed where they lie; only their bytes + the verdict are kept)
+import re, struct
+vects_h = "/root/reference/lib/isa-l/igzip/inflate_std_vects.h"
+if os.path.exists(vects_h):
+    text = open(vects_h).read()
+    cases = []
+    for name, body in re.findall(r"uint8_t\s+(std_vect_\d+)\[\]\s*=\s*\{([^}]*)\}", text):
+        raw = bytes(int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]{1,2})", body))
+        if len(raw) + 26 > 65536:
+            continue
+        # ISIZE: what the stream really inflates to when it is in fact decodable, else the largest payload
+        try:
+            d = zlib.decompressobj(-15)
+            plain = d.decompress(raw, 65537)
+            isize = len(plain) if d.eof and len(plain) <= 65536 else 65536
+        except zlib.error:
+            isize = 65536
+        m = (bytes.fromhex("1f8b08040000000000ff060042430200") + struct.pack("<H", len(raw) + 25) + raw + struct.pack("<II", 0, isize))
+        rc, outb, _ = ref.inflate_stream(m)
+        cases.append({"name": name, "hex": m.hex(), "ref_rc": rc, "ref_out_crc": "%08x" % zlib.crc32(outb)})
+    json.dump({"cases": cases}, open(os.path.join(out, "isal_std_vects.json"), "w"))
+    print("isa-l vectors:", len(cases), "accepted by the reference:", sum(c["ref_rc"] == 0 for c in cases))
 print("golden written:", sorted(os.listdir(out)))

@@ -189,6 +189,25 @@ def test_malformed_members_same_verdict_as_reference_decoder(codec):
         codec.inflate(b"\x1f\x8b\x08\x00" + bytes(40))          # plain gzip is "not BGZF or corrupted" (7bgzf.c:313-316)
 
 
+def test_reference_trees_malformed_vectors_are_rejected(codec):
+    """the 151 malformed DEFLATE streams of lib/isa-l/igzip/inflate_std_vects.h, one BGZF member each: same
+    verdict as the reference decoder (it rejects every one), alone and in the middle of a batch of good members"""
+    cases = json.load(open(os.path.join(H.GOLDEN, "isal_std_vects.json")))["cases"]
+    assert len(cases) == 151
+    good = codec.compress(H.synth("fastq", 3 * H.BLOCK), 6, eof=False)
+    for c in cases:
+        m = bytes.fromhex(c["hex"])
+        for stream in (m, good + m + good):
+            try:
+                codec.inflate(stream)
+                accepted = True
+            except b200bgzf.B200BgzfError as e:
+                assert e.code == -3
+                accepted = False
+            assert accepted == (c["ref_rc"] == 0), c["name"]
+    assert codec.inflate(good + good) == H.synth("fastq", 3 * H.BLOCK) * 2     # the context is still healthy
+
+
 def test_device_resident_api_roundtrip(codec):
     import torch
     data = H.synth("sam", 5 * H.BLOCK + 999)

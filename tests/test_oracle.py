@@ -83,6 +83,18 @@ def test_oracle_inflates_reference_golden_streams(kind, level):
     assert H.gunzip(stream) == data
 
 
+def test_oracle_inflate_rejects_the_reference_trees_malformed_vectors():
+    """lib/isa-l/igzip/inflate_std_vects.h (SURVEY 8c negative fixture), framed as BGZF members by tests/golden/make_golden.py:
+    the reference's decoder rejects all 151, so must the restatement"""
+    cases = json.load(open(os.path.join(H.GOLDEN, "isal_std_vects.json")))["cases"]
+    assert len(cases) == 151
+    for c in cases:
+        m = bytes.fromhex(c["hex"])
+        isize = struct.unpack_from("<I", m, len(m) - 4)[0]
+        rc, out = H.oracle_inflate_raw(m[18:-8], isize)
+        assert (rc == 0 and len(out) == isize) == (c["ref_rc"] == 0), c["name"]
+
+
 def test_oracle_inflate_matches_reference_verdict_on_malformed():
     """every corrupted member: same accept/reject as the reference's libdeflate decoder, same bytes when accepted"""
     n_ok = 0
