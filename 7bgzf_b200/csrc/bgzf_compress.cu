@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstring>
 
 #include "bgzf_block.h"
 #include "bgzf_kernels.h"
@@ -178,6 +179,32 @@ __device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
         c.R[p] = bg_search_one(c, p);
 }
 
+/* the same, for one CTA of a cluster that shares the search of ONE block: CTA `rank` of `parts` takes every
+ * parts-th tile of 1024 positions and writes to the match scratch of the cluster's first CTA */
+__device__ __forceinline__ void search_positions_part(const BgCtx &c, uint32_t t, uint32_t rank, uint32_t parts)
+{
+    for (uint32_t p = rank * BG_THREADS + t; p < c.n; p += parts * BG_THREADS)
+        c.R[p] = bg_search_one(c, p);
+}
+
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_size()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+/* all threads of all CTAs of the cluster; global-memory writes before it are visible after it */
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 /* ---- near-optimal class: one backward min-cost pass, warp w owning segment w.  Same arithmetic as bg_phase_dp().
  * Positions are taken in tiles of 32: each lane fetches the four matches of ITS position of the tile (one coalesced
  * 16-byte load per lane, issued a tile ahead), prices their offsets and its literal, and parks the packed result in a
@@ -316,8 +343,14 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t *v, uint3
         }                                                                   \
     } while (0)
 
-__global__ void __launch_bounds__(BG_THREADS, 1)
-bgzf_compress_kernel(BgzfCompressArgs a)
+/* SPLIT = false: the persistent kernel, CTA i takes blocks i, i + grid, ...
+ * SPLIT = true : one block, one cluster (the hook's one-member calls, where latency is everything).  Every CTA of the
+ *                cluster stages the payload and builds the same chains (same inputs, same code: same tables), then
+ *                searches every size-th tile of positions into the first CTA's match scratch; after the cluster barrier
+ *                the first CTA carries on alone.  The search is half the time of a block, so a cluster of 4 cuts the
+ *                latency of a member by about 40 % at the price of three SMs doing redundant set-up work. */
+template <bool SPLIT>
+__device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t t = threadIdx.x, T = BG_THREADS;
@@ -337,8 +370,9 @@ bgzf_compress_kernel(BgzfCompressArgs a)
     c.crctab = (uint32_t *)(smem + SM_CRCTAB);
     c.litflag = smem + SM_LITFLAG;
     c.scal = (uint32_t *)(smem + SM_SCAL);
-    c.R = a.scratch + (size_t)blockIdx.x * BGZF_SCRATCH_WORDS;
-    c.cand = a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr;
+    const uint32_t crank = SPLIT ? cluster_rank() : 0u, csize = SPLIT ? cluster_size() : 1u;
+    c.R = SPLIT ? a.scratch : a.scratch + (size_t)blockIdx.x * BGZF_SCRATCH_WORDS;
+    c.cand = SPLIT ? nullptr : (a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr);
     c.crcpow = a.crcpow;
     c.prm = a.prm;
 
@@ -350,7 +384,7 @@ bgzf_compress_kernel(BgzfCompressArgs a)
     __syncthreads();
     uint32_t parity = 0;
 
-    for (uint32_t b = blockIdx.x; b < a.nblocks; b += gridDim.x) {
+    for (uint32_t b = SPLIT ? 0u : blockIdx.x; b < a.nblocks; b += SPLIT ? a.nblocks : gridDim.x) {
         const uint8_t *src;
         uint32_t n;
         if (a.in_off) {
@@ -396,13 +430,20 @@ bgzf_compress_kernel(BgzfCompressArgs a)
         __syncthreads();
         PROF_MARK(2);
         uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build commands live behind the match scratch */
+        if (SPLIT && crank) hi = (uint4 *)(a.scratch + BGZF_SCRATCH_WORDS + (size_t)(crank - 1u) * BGZF_NOTE_WORDS);   /* (own notes) */
         build_peers_phase(c, hi, t);
         __syncthreads();
         PROF_MARK(3);
         if (t < 32u * BG_LINKERS) build_link_phase(c, hi, t >> 5, t & 31u, &c.scal[BG_S_WLIST]);   /* the other warps wait at the barrier */
         __syncthreads();
         PROF_MARK(10);
-        search_positions(c, t);
+        if (SPLIT) {
+            search_positions_part(c, t, crank, csize);
+            cluster_sync();
+            if (crank) return;
+        } else {
+            search_positions(c, t);
+        }
         __syncthreads();
         PROF_MARK(4);
         for (int pass = 0; pass <= c.prm.opt_passes; pass++) {
@@ -502,6 +543,18 @@ bgzf_compress_kernel(BgzfCompressArgs a)
     }
 }
 
+__global__ void __launch_bounds__(BG_THREADS, 1)
+bgzf_compress_kernel(BgzfCompressArgs a)
+{
+    compress_blocks<false>(a);
+}
+
+__global__ void __launch_bounds__(BG_THREADS, 1)
+bgzf_compress_split_kernel(BgzfCompressArgs a)
+{
+    compress_blocks<true>(a);
+}
+
 /* ---- sizes -> exclusive offsets (single CTA, tiles of 1024 with a running carry).
  * count_dev (optional) overrides the element count, base_dev (optional) seeds the carry: both live on the
  * device so that batches chain without a host round trip. ---- */
@@ -573,6 +626,35 @@ extern "C" cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid,
     }
     bgzf_compress_kernel<<<grid, BG_THREADS, SM_TOTAL, stream>>>(*a);
     return cudaGetLastError();
+}
+
+/* one block (a->nblocks == 1, a lazy/greedy level) on a cluster of `csize` CTAs; a->scratch holds BGZF_SCRATCH_WORDS +
+ * (csize - 1) * BGZF_NOTE_WORDS words */
+extern "C" cudaError_t bgzf_launch_compress_split(const BgzfCompressArgs *a, int csize, cudaStream_t stream)
+{
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured.load() >> dev) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(bgzf_compress_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(1ull << dev);
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)csize);
+    cfg.blockDim = dim3(BG_THREADS);
+    cfg.dynamicSmemBytes = SM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof at);
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = (unsigned)csize;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, bgzf_compress_split_kernel, *a);
 }
 
 extern "C" cudaError_t bgzf_launch_scan(const uint32_t *len, uint64_t *off, uint32_t nmax, const uint64_t *count_dev,

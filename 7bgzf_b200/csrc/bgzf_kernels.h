@@ -7,6 +7,8 @@
 #include "bgzf_block.h"
 
 #define BGZF_SCRATCH_WORDS (65536u + 32u + 16384u + 32u)   /* per-CTA scratch: u32 match per position + u8 build notes */
+#define BGZF_NOTE_WORDS (16384u + 32u)                      /* the build notes alone (extra CTAs of a split launch) */
+#define BGZF_SPLIT_MAX 8                                    /* largest cluster bgzf_launch_compress_split takes */
 #define BGZF_PROF_SLOTS 32
 
 struct BgzfCompressArgs {
@@ -49,6 +51,7 @@ extern "C" {
 #endif
 size_t bgzf_compress_smem_bytes(void);
 cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid, cudaStream_t stream);
+cudaError_t bgzf_launch_compress_split(const BgzfCompressArgs *a, int csize, cudaStream_t stream);
 cudaError_t bgzf_launch_scan(const uint32_t *len, uint64_t *off, uint32_t nmax, const uint64_t *count_dev,
                              const uint64_t *base_dev, uint64_t *total_out, cudaStream_t stream);
 cudaError_t bgzf_launch_compact(const uint8_t *slots, const uint32_t *len, uint64_t *off, uint32_t nblocks, uint8_t *out,

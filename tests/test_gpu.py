@@ -339,6 +339,39 @@ def test_hook_from_many_threads(codec, tmp_path):
     assert r.returncode != 0                                   # out-of-range level: every call fails with -1, nothing crashes
 
 
+SPLIT_DRIVER = r"""
+import sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import helpers as H, b200bgzf
+c = b200bgzf.Codec(0)
+fq, sam = H.synth("fastq", 3 * H.BLOCK), H.synth("sam", 0x10000)
+cases = [fq[:H.BLOCK], fq[H.BLOCK:2 * H.BLOCK], sam, sam[:8192], sam[:8191], sam[:20001], H.lcg_noise(H.BLOCK), bytes(H.BLOCK),
+         H.acgt(H.BLOCK), H.bamlike(H.BLOCK), fq[:1025], fq[:4 * 1024 + 1]]
+for level in (1, 4, 6, 9, 10):
+    for pl in cases:
+        got, st = c.compress_blocks([pl], level)
+        assert st == [0], (level, len(pl), st)
+        sys.stdout.buffer.write(got[0])
+"""
+
+
+def test_one_member_calls_on_a_cluster_give_the_same_bytes(codec):
+    """the hook's one-block path lets a cluster of 2/4/8 CTAs share the search of the block: every size must give the
+    bytes of the one-CTA kernel (= the emulator's), for all classes that split (greedy/lazy) and one that does not (10)"""
+    fq, sam = H.synth("fastq", 3 * H.BLOCK), H.synth("sam", 0x10000)
+    cases = [fq[:H.BLOCK], fq[H.BLOCK:2 * H.BLOCK], sam, sam[:8192], sam[:8191], sam[:20001], H.lcg_noise(H.BLOCK), bytes(H.BLOCK),
+             H.acgt(H.BLOCK), H.bamlike(H.BLOCK), fq[:1025], fq[:4 * 1024 + 1]]
+    want = b"".join(codec.compress(pl, level, 0x10000, eof=False) for level in (1, 4, 6, 9, 10) for pl in cases)
+    e0 = H.emul_block(cases[0], 1)[1]
+    assert want[: len(e0)] == e0
+    for split in ("1", "2", "4", "8", ""):
+        env = dict(os.environ, B200BGZF_SPLIT=split)
+        r = subprocess.run(["python", "-c", SPLIT_DRIVER, os.path.join(H.ROOT, "tests"), os.path.join(H.ROOT, "7bgzf_b200")],
+                           capture_output=True, env=env)
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout == want, split
+
+
 def test_applet_roundtrip_and_stderr_contract():
     data = H.synth("fastq", 3 << 20)
     r = subprocess.run([b200bgzf.APPLET_PATH, "-c", "-l6", "-@", "4"], input=data, capture_output=True)
