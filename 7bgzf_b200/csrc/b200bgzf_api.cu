@@ -479,7 +479,7 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     /* first use of the lane: a stream and two slabs (each allocation is a device-wide synchronisation, and a pool of
      * callers hits this at the same moment) */
     constexpr size_t kIn = BG_SLOT_BYTES + 64, kSlot = BG_SLOT_BYTES + 64,
-                     kScratch = ((size_t)BGZF_SCRATCH_WORDS + (size_t)(BGZF_SPLIT_MAX - 1) * BGZF_NOTE_WORDS) * sizeof(uint32_t);
+                     kScratch = ((size_t)BGZF_SCRATCH_WORDS + BGZF_SPLIT_EXTRA_WORDS) * sizeof(uint32_t);
     if (!l.stream) CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     if (!l.one_dev) {
         CK(cudaMalloc((void **)&l.one_dev, kIn + kSlot + kScratch));
@@ -564,12 +564,12 @@ extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *cons
             l->busy = true;
         }
         static const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
-        /* one-member calls share the GPU between the callers in flight: up to 4 of them get a cluster of 8 SMs each, up
-         * to 32 a cluster of 4, beyond that one SM each (B200BGZF_SPLIT=1/2/4/8 forces a size; for measurements).
-         * Measured, MB/s with 1 / 8 / 16 callers: one SM 129 / 1020 / 2000, clusters 253 / 1700-1850 / 3330 */
+        /* one-member calls share the GPU between the callers in flight: up to 18 of them get a cluster of 8 SMs each (144
+         * of the 148 SMs), up to 36 a cluster of 4, beyond that one SM each (B200BGZF_SPLIT=1/2/4/8 forces a size; for
+         * measurements).  Measured, MB/s with 1 / 8 / 16 callers: one SM 130 / 1020 / 2000, clusters of 8: 291 / 2130 / 3500 */
         static const int forced = [] { const char *e = getenv("B200BGZF_SPLIT"); return e && *e ? atoi(e) : 0; }();
         const int callers = in_flight + 1;
-        int split = forced > 0 ? std::min(forced, BGZF_SPLIT_MAX) : callers <= 4 ? 8 : callers <= 32 ? 4 : 1;
+        int split = forced > 0 ? std::min(forced, BGZF_SPLIT_MAX) : callers <= 18 ? 8 : callers <= 36 ? 4 : 1;
         if (split == 3) split = 2;
         if (split > 4 && split < 8) split = 4;
         int r = nblocks == 1 ? compress_one_on_lane(ctx, *l, src[0], slen[0], dst[0], dlen, status, level, in_flight + 1 > cores, split)

@@ -95,12 +95,14 @@ __device__ __forceinline__ unsigned hash_peers(uint32_t h, bool valid)
 
 /* notes layout: tile = 16 consecutive groups (512 positions); tile i holds 32 lanes x 16 bytes, so that in phase
  * B each lane fetches the notes of its next 16 groups with one coalesced 16-byte load, a whole tile ahead. */
-__device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, uint32_t t)
+/* (first, step, xprev): a CTA of a cluster takes tiles first, first + step, ... and also leaves each finished tile of
+ * prev[] in global memory for the other CTAs (import_peer_tiles); the one-CTA kernel passes 0, 1, nullptr */
+__device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, uint32_t t, uint32_t first, uint32_t step, uint4 *xprev)
 {
     const uint32_t n = c.n, lane = t & 31u, warp = t >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t ntiles = (n + 511u) >> 9;
-    for (uint32_t tile = warp; tile < ntiles; tile += BG_THREADS / 32) {
+    for (uint32_t tile = first + step * warp; tile < ntiles; tile += step * (BG_THREADS / 32)) {
         uint32_t w[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
 #pragma unroll
         for (uint32_t g = 0; g < 16; g++) {
@@ -121,7 +123,22 @@ __device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, 
             }
         }
         notes[tile * 32u + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (xprev) {
+            __syncwarp();
+            const uint4 *ts = (const uint4 *)(c.prev + tile * 512u);      /* 1 KiB of links: two 16-byte pieces per lane */
+            xprev[tile * 64u + lane] = ts[lane];
+            xprev[tile * 64u + 32u + lane] = ts[32u + lane];
+        }
     }
+}
+
+/* the other CTAs' tiles of prev[], after the cluster barrier: 64 pieces of 16 bytes per tile */
+__device__ __forceinline__ void import_peer_tiles(const BgCtx &c, const uint4 *xprev, uint32_t t, uint32_t rank, uint32_t parts)
+{
+    const uint32_t pieces = ((c.n + 511u) >> 9) * 64u;
+    uint4 *dst = (uint4 *)c.prev;
+    for (uint32_t i = t; i < pieces; i += BG_THREADS)
+        if ((i >> 6) % parts != rank) dst[i] = __ldcg(xprev + i);
 }
 
 /* Phase B, a relay of BG_LINKERS warps: warp k takes tiles k, k+BG_LINKERS, ...  Only the head-table part of a tile
@@ -345,10 +362,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t *v, uint3
 
 /* SPLIT = false: the persistent kernel, CTA i takes blocks i, i + grid, ...
  * SPLIT = true : one block, one cluster (the hook's one-member calls, where latency is everything).  Every CTA of the
- *                cluster stages the payload and builds the same chains (same inputs, same code: same tables), then
- *                searches every size-th tile of positions into the first CTA's match scratch; after the cluster barrier
- *                the first CTA carries on alone.  The search is half the time of a block, so a cluster of 4 cuts the
- *                latency of a member by about 40 % at the price of three SMs doing redundant set-up work. */
+ *                cluster stages the payload and hashes it (same inputs, same code: same tables); the equal-hash peers
+ *                are found for every size-th tile by each CTA and exchanged through L2, the chains are linked by
+ *                everyone, then each CTA searches every size-th tile of positions into the first CTA's match scratch;
+ *                after the second cluster barrier the first CTA carries on alone.  The search is half the time of a
+ *                block, so a cluster of 4 cuts the latency of a member by about 45 % at the price of three SMs doing
+ *                redundant set-up work. */
 template <bool SPLIT>
 __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
 {
@@ -430,8 +449,15 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         __syncthreads();
         PROF_MARK(2);
         uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build commands live behind the match scratch */
-        if (SPLIT && crank) hi = (uint4 *)(a.scratch + BGZF_SCRATCH_WORDS + (size_t)(crank - 1u) * BGZF_NOTE_WORDS);   /* (own notes) */
-        build_peers_phase(c, hi, t);
+        if (SPLIT) {
+            /* every CTA has the same hashes; each finds the peers of its share of the tiles, the links travel through L2 */
+            uint4 *xprev = (uint4 *)(a.scratch + BGZF_SCRATCH_WORDS);
+            build_peers_phase(c, hi, t, crank, csize, xprev);
+            cluster_sync();
+            import_peer_tiles(c, xprev, t, crank, csize);
+        } else {
+            build_peers_phase(c, hi, t, 0u, 1u, nullptr);
+        }
         __syncthreads();
         PROF_MARK(3);
         if (t < 32u * BG_LINKERS) build_link_phase(c, hi, t >> 5, t & 31u, &c.scal[BG_S_WLIST]);   /* the other warps wait at the barrier */
@@ -629,7 +655,7 @@ extern "C" cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid,
 }
 
 /* one block (a->nblocks == 1, a lazy/greedy level) on a cluster of `csize` CTAs; a->scratch holds BGZF_SCRATCH_WORDS +
- * (csize - 1) * BGZF_NOTE_WORDS words */
+ * BGZF_SPLIT_EXTRA_WORDS words */
 extern "C" cudaError_t bgzf_launch_compress_split(const BgzfCompressArgs *a, int csize, cudaStream_t stream)
 {
     static std::atomic<unsigned long long> configured{0};

@@ -7,7 +7,7 @@
 #include "bgzf_block.h"
 
 #define BGZF_SCRATCH_WORDS (65536u + 32u + 16384u + 32u)   /* per-CTA scratch: u32 match per position + u8 build notes */
-#define BGZF_NOTE_WORDS (16384u + 32u)                      /* the build notes alone (extra CTAs of a split launch) */
+#define BGZF_SPLIT_EXTRA_WORDS 32768u                       /* split launch: the chain links of every tile, exchanged between the CTAs */
 #define BGZF_SPLIT_MAX 8                                    /* largest cluster bgzf_launch_compress_split takes */
 #define BGZF_PROF_SLOTS 32
 

@@ -8,7 +8,7 @@ python tools/level_sweep.py 256 > $O/levels_$R.jsonl 2>> $O/bench_$R.err
 python tools/pcie_probe.py > $O/pcie_$R.txt 2>&1
 python tools/e2e_probe.py 1024 >> $O/pcie_$R.txt 2>&1
 ./build/datagen sam 268435456 2 > /tmp/sam256.bin
-( export BGZF_METHOD=libdeflate6; for t in 1 16 64; do ./build/hook_mt 7bgzf_b200/7bgzf.so $t /tmp/sam256.bin 4; done; echo reference; for t in 1 16; do ./build/hook_mt oracle/_ref/7bgzf_ref.so $t /tmp/sam256.bin; done ) > $O/hook_$R.txt 2>&1
+( export BGZF_METHOD=libdeflate6; for t in 1 4 8 16 64; do ./build/hook_mt 7bgzf_b200/7bgzf.so $t /tmp/sam256.bin 4; done; echo one SM per call; for t in 1 16; do B200BGZF_SPLIT=1 ./build/hook_mt 7bgzf_b200/7bgzf.so $t /tmp/sam256.bin 4; done; echo reference; for t in 1 16; do ./build/hook_mt oracle/_ref/7bgzf_ref.so $t /tmp/sam256.bin; done ) > $O/hook_$R.txt 2>&1
 bash tools/applet_compare.sh 1024 > $O/applet_$R.txt 2>&1
 # launch list of the bench command (shares per kernel; times under ncu are cold-cache and serialised)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$R.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_bench_$R.log 2>&1
