@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box call that produces every measured artefact of a round under gpurun_out/ (then: tools/summarise_round.sh here).
+# One GPU-box call that produces every measured artefact of a round under gpurun_out/ (then summarise here: tools/launch_summary.py, tools/ncu_summary.py, tools/sass_summary.py).
 #   gpurun --timeout 1500 -- 'bash tools/capture_round.sh r01'
 R=${1:-r01}; O=gpurun_out; mkdir -p $O
 python bench.py --steps 5 --warmup 3 > $O/bench_$R.json 2> $O/bench_$R.err
