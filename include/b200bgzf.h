@@ -81,8 +81,10 @@ size_t b200bgzf_gzi_format(const uint64_t *caddr, const uint64_t *uaddr, size_t 
  * entry and the member size on return; status[i] gets the per-block code of bgzf_compress().  This is the
  * batch form of bgzf_compress.c:39-198.  nblocks == 1 is what the LD_PRELOAD hook calls for every htslib block:
  * that case takes a dedicated low-latency path (one copy in, one kernel, one copy out, one synchronisation) on
- * one of 128 independent lanes, so concurrent callers each drive their own stream and SM; callers beyond the
- * host's core count wait by sleeping, not spinning.
+ * one of 128 independent lanes, so concurrent callers each drive their own stream; while few callers are in
+ * flight the kernel of a call runs on a thread-block cluster of 8 (or 4) SMs that share the block's match search
+ * (same output bytes, less than half the latency); callers beyond the host's core count wait by sleeping, not
+ * spinning.
  */
 int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, const uint32_t *slen, void *const *dst,
                                   size_t *dlen, int *status, uint32_t nblocks, int level);
