@@ -77,6 +77,7 @@ struct b200bgzf_ctx {
     size_t idx_cap = 0, idx_tiles = 0;
     uint64_t *h_idx = nullptr;
     std::atomic<unsigned long long> launches{0};   /* hook callers bump it concurrently */
+    std::atomic<bool> no_clusters{false};          /* set when a cluster launch was refused once */
     char err[256] = { 0 };
 };
 
@@ -511,8 +512,15 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     a.crcpow = ctx->d_crcpow;
     a.prof = nullptr;
     /* few callers, many idle SMs: let a cluster of CTAs share the search of this one block (same bytes out) */
-    if (split > 1 && a.prm.opt_passes == 0 && slen >= 8192u) CK(bgzf_launch_compress_split(&a, split, l.stream));
-    else CK(bgzf_launch_compress(&a, 1, l.stream));
+    bool launched = false;
+    if (split > 1 && a.prm.opt_passes == 0 && slen >= 8192u && !ctx->no_clusters.load(std::memory_order_relaxed)) {
+        launched = bgzf_launch_compress_split(&a, split, l.stream) == cudaSuccess;
+        if (!launched) {               /* a device or partition that cannot place the cluster: stay on the one-SM kernel */
+            cudaGetLastError();
+            ctx->no_clusters.store(true, std::memory_order_relaxed);
+        }
+    }
+    if (!launched) CK(bgzf_launch_compress(&a, 1, l.stream));
     ctx->launches += 1;
     CK(cudaMemcpyAsync(h_out, d_slot, (size_t)BG_SLOT_BYTES + 8, cudaMemcpyDeviceToHost, l.stream));
     if (sleep_wait) {
