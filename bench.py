@@ -160,7 +160,7 @@ def main():
     config = {"workload": f"{args.mib} MiB synthetic {args.kind.upper()}-like text (SURVEY App. B, seed {1 if args.kind == 'fastq' else 2}) per GPU, "
                           f"BGZF_METHOD=libdeflate{args.level} class, 0xff00-byte blocks; compress is the headline value, inflate of the same stream reported beside it",
               "block_bytes": BLOCK, "level": args.level, "bytes_per_gpu": nbytes, "parallelism": f"block-range sharding x{world}, no collective",
-              "l2": "inputs (1 GiB) are larger than the 126 MB L2; no explicit flush"}
+              "l2": f"inputs ({args.mib} MiB) are larger than the 126 MB L2; no explicit flush"}
 
     gen = load_gen()
     if args.impl == "reference":
