@@ -513,7 +513,7 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     a.prof = nullptr;
     /* few callers, many idle SMs: let a cluster of CTAs share the search of this one block (same bytes out) */
     bool launched = false;
-    if (split > 1 && a.prm.opt_passes == 0 && slen >= 8192u && !ctx->no_clusters.load(std::memory_order_relaxed)) {
+    if (split > 1 && slen >= 8192u && !ctx->no_clusters.load(std::memory_order_relaxed)) {
         launched = bgzf_launch_compress_split(&a, split, l.stream) == cudaSuccess;
         if (!launched) {               /* a device or partition that cannot place the cluster: stay on the one-SM kernel */
             cudaGetLastError();

@@ -200,6 +200,11 @@ __device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
  * parts-th tile of 1024 positions and writes to the match scratch of the cluster's first CTA */
 __device__ __forceinline__ void search_positions_part(const BgCtx &c, uint32_t t, uint32_t rank, uint32_t parts)
 {
+    if (c.prm.opt_passes > 0) {
+        for (uint32_t p = rank * BG_THREADS + t; p < c.n; p += parts * BG_THREADS)
+            c.R[p] = bg_search_one_multi(c, p);
+        return;
+    }
     for (uint32_t p = rank * BG_THREADS + t; p < c.n; p += parts * BG_THREADS)
         c.R[p] = bg_search_one(c, p);
 }
@@ -391,7 +396,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
     c.scal = (uint32_t *)(smem + SM_SCAL);
     const uint32_t crank = SPLIT ? cluster_rank() : 0u, csize = SPLIT ? cluster_size() : 1u;
     c.R = SPLIT ? a.scratch : a.scratch + (size_t)blockIdx.x * BGZF_SCRATCH_WORDS;
-    c.cand = SPLIT ? nullptr : (a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr);
+    c.cand = SPLIT ? a.cand : (a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr);
     c.crcpow = a.crcpow;
     c.prm = a.prm;
 
@@ -654,7 +659,7 @@ extern "C" cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid,
     return cudaGetLastError();
 }
 
-/* one block (a->nblocks == 1, a lazy/greedy level) on a cluster of `csize` CTAs; a->scratch holds BGZF_SCRATCH_WORDS +
+/* one block (a->nblocks == 1) on a cluster of `csize` CTAs; a->scratch holds BGZF_SCRATCH_WORDS +
  * BGZF_SPLIT_EXTRA_WORDS words */
 extern "C" cudaError_t bgzf_launch_compress_split(const BgzfCompressArgs *a, int csize, cudaStream_t stream)
 {
