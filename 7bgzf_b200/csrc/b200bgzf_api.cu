@@ -54,6 +54,7 @@ struct Lane {
     uint32_t pend_nb = 0;
     bool busy = false;
     int scratch_ctas = 0;
+    int cand_ctas = 0;            /* CTAs d_cand is sized for (near-optimal levels) */
     cudaEvent_t done = nullptr;   /* hook lanes: polled with short sleeps when callers outnumber the host's cores */
     uint8_t *one_dev = nullptr, *one_host = nullptr;   /* one-block fast path: everything it needs in one device and one pinned slab */
 };
@@ -73,7 +74,9 @@ struct b200bgzf_ctx {
     Lane hook_lanes[kHookLanes];
     /* device-resident inflate index workspaces */
     uint64_t *d_idx_inoff = nullptr, *d_idx_outoff = nullptr, *d_idx_tileoff = nullptr, *d_idx_counts = nullptr;
+    uint64_t *d_idx_cand = nullptr, *d_idx_pick = nullptr;
     uint32_t *d_idx_tilecount = nullptr, *d_idx_isize = nullptr, *d_idx_status = nullptr, *d_inf_status = nullptr;
+    uint32_t *d_idx_jump = nullptr, *d_idx_jump2 = nullptr, *d_idx_reach = nullptr;
     size_t idx_cap = 0, idx_tiles = 0;
     uint64_t *h_idx = nullptr;
     std::atomic<unsigned long long> launches{0};   /* hook callers bump it concurrently */
@@ -111,6 +114,33 @@ cudaError_t grow(T **p, size_t *cap, size_t need, bool pinned = false)
     return e;
 }
 
+/* near-optimal levels: four matches per position and CTA; (re)sized for the largest grid the lane launches */
+cudaError_t ensure_cand(Lane &l, int ctas)
+{
+    if (l.d_cand && l.cand_ctas >= ctas) return cudaSuccess;
+    if (l.d_cand) { cudaFree(l.d_cand); l.d_cand = nullptr; l.cand_ctas = 0; }
+    cudaError_t e = cudaMalloc((void **)&l.d_cand, (size_t)ctas * 4u * BG_MAX_BLOCK * sizeof(uint32_t));
+    if (e == cudaSuccess) l.cand_ctas = ctas;
+    return e;
+}
+
+/* Every exit of a pipelined host call (error exits included) leaves no batch in flight: a stale `pending` lane would be
+ * "completed" by the next call with the old batch's sizes. */
+struct PendingGuard {
+    Lane *lanes;
+    int n;
+    PendingGuard(Lane *l, int count) : lanes(l), n(count) { settle(); }
+    ~PendingGuard() { settle(); }
+    void settle()
+    {
+        for (int i = 0; i < n; i++)
+            if (lanes[i].pending) {
+                if (lanes[i].stream) cudaStreamSynchronize(lanes[i].stream);
+                lanes[i].pending = false;
+            }
+    }
+};
+
 void lane_free(Lane &l)
 {
     cudaFree(l.d_in); cudaFree(l.d_slots); cudaFree(l.d_out); cudaFree(l.d_len); cudaFree(l.d_status);
@@ -142,7 +172,8 @@ int lane_reserve(b200bgzf_ctx *ctx, Lane &l, uint32_t blocks, size_t in_bytes, s
     if (blocks > l.cap_blocks || (slots && !l.d_slots)) {
         cudaFree(l.d_slots); cudaFree(l.d_len); cudaFree(l.d_status); cudaFree(l.d_off);
         cudaFree(l.d_inoff); cudaFree(l.d_outoff); cudaFree(l.d_inlen);
-        l.d_slots = nullptr; l.cap_blocks = 0;
+        l.d_slots = nullptr; l.d_len = l.d_status = l.d_inlen = nullptr; l.d_off = l.d_inoff = l.d_outoff = nullptr;
+        l.cap_blocks = 0;
         if (slots) CK(cudaMalloc((void **)&l.d_slots, (size_t)blocks * BG_SLOT_BYTES + 64));
         CK(cudaMalloc((void **)&l.d_len, (size_t)blocks * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&l.d_status, (size_t)blocks * sizeof(uint32_t)));
@@ -177,7 +208,7 @@ int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint6
         a.status = l.d_status;
         a.scratch = l.d_scratch;
         if (a.prm.opt_passes > 0) {
-            if (!l.d_cand) CK(cudaMalloc((void **)&l.d_cand, (size_t)l.scratch_ctas * 4u * BG_MAX_BLOCK * sizeof(uint32_t)));
+            CK(ensure_cand(l, l.scratch_ctas));
             a.cand = l.d_cand;
         }
         a.crctab = ctx->d_crctab;
@@ -280,6 +311,7 @@ extern "C" void b200bgzf_destroy(b200bgzf_ctx *ctx)
         cudaFree(ctx->d_crctab); cudaFree(ctx->d_crcpow); cudaFree(ctx->d_prof);
         cudaFree(ctx->d_idx_inoff); cudaFree(ctx->d_idx_outoff); cudaFree(ctx->d_idx_tileoff); cudaFree(ctx->d_idx_counts);
         cudaFree(ctx->d_idx_tilecount); cudaFree(ctx->d_idx_isize); cudaFree(ctx->d_idx_status); cudaFree(ctx->d_inf_status);
+        cudaFree(ctx->d_idx_cand); cudaFree(ctx->d_idx_pick); cudaFree(ctx->d_idx_jump); cudaFree(ctx->d_idx_jump2); cudaFree(ctx->d_idx_reach);
         if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
     }
     delete ctx;
@@ -342,6 +374,7 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     if (member_off && member_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PendingGuard pg(ctx->lanes, kLanes);
     const uint64_t nb_total = (in_bytes + block_size - 1) / block_size;
     /* batches rotate through the lanes (H2D, kernels, D2H on the lane's stream).  Measured: 400-512 blocks per batch is
      * best; multiples of the SM count are 5 % WORSE — when every CTA of a launch finishes at the same moment nothing of the
@@ -697,28 +730,41 @@ extern "C" int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size
         CK(cudaMalloc((void **)&ctx->d_idx_tileoff, tiles * sizeof(uint64_t)));
         ctx->idx_tiles = tiles;
     }
-    /* first guess: members average >= 1 KiB; retry with the 28-byte worst case if there are more */
+    /* first guess: signature hits average >= 1 KiB apart; retry with the 28-byte worst case if there are more */
     size_t guess = in_bytes / 1024 + 4096;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (guess > ctx->idx_cap) {
             cudaFree(ctx->d_idx_inoff); cudaFree(ctx->d_idx_outoff); cudaFree(ctx->d_idx_isize); cudaFree(ctx->d_inf_status);
+            cudaFree(ctx->d_idx_cand); cudaFree(ctx->d_idx_pick); cudaFree(ctx->d_idx_jump); cudaFree(ctx->d_idx_jump2); cudaFree(ctx->d_idx_reach);
+            ctx->d_idx_inoff = ctx->d_idx_outoff = ctx->d_idx_cand = ctx->d_idx_pick = nullptr;
+            ctx->d_idx_isize = ctx->d_inf_status = ctx->d_idx_jump = ctx->d_idx_jump2 = ctx->d_idx_reach = nullptr;
             ctx->idx_cap = 0;
             CK(cudaMalloc((void **)&ctx->d_idx_inoff, guess * sizeof(uint64_t)));
             CK(cudaMalloc((void **)&ctx->d_idx_outoff, guess * sizeof(uint64_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_cand, guess * sizeof(uint64_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_pick, guess * sizeof(uint64_t)));
             CK(cudaMalloc((void **)&ctx->d_idx_isize, guess * sizeof(uint32_t)));
             CK(cudaMalloc((void **)&ctx->d_inf_status, guess * sizeof(uint32_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_jump, (guess + 2) * sizeof(uint32_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_jump2, (guess + 2) * sizeof(uint32_t)));
+            CK(cudaMalloc((void **)&ctx->d_idx_reach, (guess + 2) * sizeof(uint32_t)));
             ctx->idx_cap = guess;
         }
         CK(cudaMemsetAsync(ctx->d_idx_status, 0, 4 * sizeof(uint32_t), stream));
-        CK(bgzf_launch_index((const uint8_t *)d_in, in_bytes, ctx->d_idx_inoff, ctx->d_idx_outoff, (uint32_t)ctx->idx_cap,
-                             ctx->d_idx_tilecount, ctx->d_idx_tileoff, ctx->d_idx_isize, ctx->d_idx_counts, ctx->d_idx_counts + 1,
-                             ctx->d_idx_status, stream));
-        ctx->launches += 5;
+        BgzfIndexWork w;
+        w.max_blocks = (uint32_t)std::min<size_t>(ctx->idx_cap, 0xfffffff0u);
+        w.tile_count = ctx->d_idx_tilecount; w.tile_off = ctx->d_idx_tileoff; w.cand_off = ctx->d_idx_cand;
+        w.jump = ctx->d_idx_jump; w.jump2 = ctx->d_idx_jump2; w.reach = ctx->d_idx_reach; w.pick_idx = ctx->d_idx_pick;
+        w.in_off = ctx->d_idx_inoff; w.out_off = ctx->d_idx_outoff; w.isize = ctx->d_idx_isize;
+        w.ncand = ctx->d_idx_counts + 2; w.nmembers = ctx->d_idx_counts; w.out_bytes = ctx->d_idx_counts + 1;
+        w.status = ctx->d_idx_status;
+        CK(bgzf_launch_index((const uint8_t *)d_in, in_bytes, &w, stream));
+        ctx->launches += BGZF_INDEX_LAUNCHES;
         CK(cudaMemcpyAsync(ctx->h_idx, ctx->d_idx_counts, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemcpyAsync(ctx->h_idx + 2, ctx->d_idx_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         const uint32_t st = (uint32_t)ctx->h_idx[2];
-        if (st & 2u) { guess = in_bytes / 28 + 1; continue; }
+        if ((st & 2u) && attempt == 0) { guess = in_bytes / 28 + 1; continue; }
         if (st) return B200BGZF_E_FORMAT;
         break;
     }
@@ -753,6 +799,7 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
     const uint8_t *p = (const uint8_t *)in;
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    PendingGuard pg(ctx->lanes, kLanes);
     /* Batches of members rotate through the lanes (H2D, kernel, D2H on the lane's stream).  The host walk of the
      * member headers (applet/7bgzf.c:306-330) is done batch by batch, between submissions, so the GPU starts on the
      * first members while the host is still finding the later ones; the first batches are small so that the D2H

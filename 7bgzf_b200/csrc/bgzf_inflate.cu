@@ -670,27 +670,86 @@ bgzf_index_scan_kernel(const uint8_t *in, uint64_t n, uint32_t *tile_count, cons
     }
 }
 
-/* validates the BSIZE chain and collects ISIZE per member */
-__global__ void bgzf_index_finish_kernel(const uint8_t *in, uint64_t n, const uint64_t *in_off, const uint64_t *count,
-                                         uint32_t max_blocks, uint32_t *isize, uint32_t *status)
+/* ---- which candidates are members?  The reference walks the headers strictly one after the other (applet/7bgzf.c:306-330):
+ * a member starts at offset 0, the next one where BSIZE says this one ends.  A signature hit that is not on that chain is
+ * payload (a stored member that carries BGZF data: bgzip of a .bam, a tar of .bgz files) and must be ignored, not
+ * rejected.  On the device the walk is a reachability question over the sorted candidate list:
+ *   next   nxt[k] = index of the candidate that starts exactly where candidate k's member ends (binary search);
+ *          nc = "ends exactly at the end of the stream", nc + 1 = "ends nowhere" (both absorbing)
+ *   chain  pointer doubling from candidate 0 (one CTA; log2(nc) rounds): reach[k] = 1 for every candidate on the chain
+ *   pick   ordered compaction of the reached candidates (scan of reach[]) + their ISIZE                           ---- */
+__global__ void __launch_bounds__(256)
+bgzf_index_next_kernel(const uint8_t *in, uint64_t n, const uint64_t *cand_off, const uint64_t *count, uint32_t max_blocks,
+                       uint32_t *nxt, uint32_t *reach, uint32_t *status)
 {
-    const uint64_t nm = *count;
-    if (nm > max_blocks || nm == 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, nm == 0 ? 1u : 2u);
+    const uint64_t nc64 = *count;
+    if (nc64 > max_blocks || nc64 == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, nc64 == 0 ? 1u : 2u);
         return;
     }
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nm; k += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t o = in_off[k];
+    const uint32_t nc = (uint32_t)nc64;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nc + 2; k += gridDim.x * blockDim.x) {
+        reach[k] = 0;
+        if (k >= nc) { nxt[k] = k; continue; }
+        const uint64_t o = cand_off[k];
         const uint64_t next = o + ((uint32_t)in[o + 16] | ((uint32_t)in[o + 17] << 8)) + 1u;
-        const uint64_t expect = k + 1 < nm ? in_off[k + 1] : n;
-        if ((k == 0 && o != 0) || next != expect || next > n) {
-            atomicOr(status, 1u);
-            isize[k] = 0;
-            continue;
+        uint32_t r = nc + 1;
+        if (next == n) r = nc;
+        else if (next < n) {
+            uint32_t lo = k + 1, hi = nc;                 /* first candidate at or past `next` */
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (cand_off[mid] < next) lo = mid + 1; else hi = mid;
+            }
+            if (lo < nc && cand_off[lo] == next) r = lo;
         }
+        nxt[k] = r;
+    }
+}
+
+/* one CTA.  jump[] starts as nxt[] and is squared every round (jump <- jump o jump); every reached node marks its jump
+ * target, so after round r everything within 2^(r+1) - 1 steps of the start is marked.  Marks only ever name true
+ * successors, so reading a mark that another thread sets in the same round is harmless. */
+__global__ void __launch_bounds__(1024, 1)
+bgzf_index_chain_kernel(const uint64_t *cand_off, const uint64_t *count, uint32_t max_blocks, uint32_t *jump, uint32_t *jump2,
+                        uint32_t *reach, uint32_t *status)
+{
+    const uint64_t nc64 = *count;
+    if (nc64 > max_blocks || nc64 == 0) return;            /* (reported by the kernel before) */
+    const uint32_t nc = (uint32_t)nc64, t = threadIdx.x;
+    if (t == 0) reach[0] = cand_off[0] == 0 ? 1u : 0u;
+    __syncthreads();
+    uint32_t *cur = jump, *nx = jump2;
+    for (uint32_t span = 1; span < nc + 1; span <<= 1) {
+        for (uint32_t k = t; k < nc; k += 1024)
+            if (reach[k]) reach[cur[k]] = 1u;
+        for (uint32_t k = t; k < nc + 2; k += 1024) nx[k] = cur[cur[k]];
+        __syncthreads();
+        uint32_t *tmp = cur; cur = nx; nx = tmp;
+    }
+    for (uint32_t k = t; k < nc; k += 1024)
+        if (reach[k]) reach[cur[k]] = 1u;
+    __syncthreads();
+    if (t == 0 && !reach[nc]) atomicOr(status, 1u);         /* the walk from offset 0 does not end at the end of the stream */
+}
+
+/* the reached candidates, in order, with their ISIZE; idx[] = exclusive scan of reach[] */
+__global__ void __launch_bounds__(256)
+bgzf_index_pick_kernel(const uint8_t *in, const uint64_t *cand_off, const uint64_t *count, uint32_t max_blocks, const uint32_t *reach,
+                       const uint64_t *idx, uint64_t *in_off, uint32_t *isize, uint32_t *status)
+{
+    const uint64_t nc64 = *count;
+    if (nc64 > max_blocks || nc64 == 0) return;
+    const uint32_t nc = (uint32_t)nc64;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nc; k += gridDim.x * blockDim.x) {
+        if (!reach[k]) continue;
+        const uint64_t o = cand_off[k];
+        const uint64_t next = o + ((uint32_t)in[o + 16] | ((uint32_t)in[o + 17] << 8)) + 1u;
         const uint8_t *tr = in + next - 4;
-        isize[k] = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
-        if (isize[k] > 65536u) atomicOr(status, 1u);
+        const uint32_t v = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        in_off[idx[k]] = o;
+        isize[idx[k]] = v;
+        if (v > 65536u) atomicOr(status, 1u);
     }
 }
 
@@ -719,18 +778,21 @@ extern "C" cudaError_t bgzf_launch_inflate(const BgzfInflateArgs *a, cudaStream_
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, uint64_t *in_off, uint64_t *out_off, uint32_t max_blocks,
-                                         uint32_t *tile_count, uint64_t *tile_off, uint32_t *isize, uint64_t *nmembers,
-                                         uint64_t *out_bytes, uint32_t *status, cudaStream_t stream)
+extern "C" cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, const BgzfIndexWork *w, cudaStream_t stream)
 {
     const uint32_t tiles = (uint32_t)((in_bytes + IDX_TILE - 1) / IDX_TILE);
     if (tiles == 0) return cudaErrorInvalidValue;
-    bgzf_index_scan_kernel<<<tiles, IDX_THREADS, 0, stream>>>(in, in_bytes, tile_count, nullptr, nullptr, max_blocks, 0);
-    bgzf_launch_scan(tile_count, tile_off, tiles, nullptr, nullptr, nmembers, stream);
-    bgzf_index_scan_kernel<<<tiles, IDX_THREADS, 0, stream>>>(in, in_bytes, tile_count, tile_off, in_off, max_blocks, 1);
-    bgzf_index_finish_kernel<<<64, 256, 0, stream>>>(in, in_bytes, in_off, nmembers, max_blocks, isize, status);
-    /* out_off = exclusive scan of ISIZE over the members found (count read on the device) */
-    bgzf_launch_scan(isize, out_off, max_blocks, nmembers, nullptr, out_bytes, stream);
+    /* candidates: every position that carries the 16-byte BGZF signature, in order */
+    bgzf_index_scan_kernel<<<tiles, IDX_THREADS, 0, stream>>>(in, in_bytes, w->tile_count, nullptr, nullptr, w->max_blocks, 0);
+    bgzf_launch_scan(w->tile_count, w->tile_off, tiles, nullptr, nullptr, w->ncand, stream);
+    bgzf_index_scan_kernel<<<tiles, IDX_THREADS, 0, stream>>>(in, in_bytes, w->tile_count, w->tile_off, w->cand_off, w->max_blocks, 1);
+    /* members: the candidates on the BSIZE chain from offset 0 */
+    bgzf_index_next_kernel<<<64, 256, 0, stream>>>(in, in_bytes, w->cand_off, w->ncand, w->max_blocks, w->jump, w->reach, w->status);
+    bgzf_index_chain_kernel<<<1, 1024, 0, stream>>>(w->cand_off, w->ncand, w->max_blocks, w->jump, w->jump2, w->reach, w->status);
+    bgzf_launch_scan(w->reach, w->pick_idx, w->max_blocks, w->ncand, nullptr, w->nmembers, stream);
+    bgzf_index_pick_kernel<<<64, 256, 0, stream>>>(in, w->cand_off, w->ncand, w->max_blocks, w->reach, w->pick_idx, w->in_off, w->isize, w->status);
+    /* out_off = exclusive scan of ISIZE over the members (count read on the device) */
+    bgzf_launch_scan(w->isize, w->out_off, w->max_blocks, w->nmembers, nullptr, w->out_bytes, stream);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,22 @@ struct BgzfInflateArgs {
     const uint32_t *crcpow;    /* device u32[1024] (verify) */
 };
 
+/* workspaces of the device-side member index (all device memory) */
+struct BgzfIndexWork {
+    uint32_t max_blocks;       /* capacity of the per-candidate / per-member arrays below */
+    uint32_t *tile_count;      /* [tiles] signature hits per 32 KiB tile */
+    uint64_t *tile_off;        /* [tiles] their exclusive scan */
+    uint64_t *cand_off;        /* [max_blocks] offsets of all signature hits, ascending */
+    uint32_t *jump, *jump2;    /* [max_blocks + 2] successor links of the candidates, squared in place (pointer doubling) */
+    uint32_t *reach;           /* [max_blocks + 2] 1 = on the BSIZE chain from offset 0 */
+    uint64_t *pick_idx;        /* [max_blocks] exclusive scan of reach[] */
+    uint64_t *in_off;          /* [max_blocks] out: offset of every member */
+    uint64_t *out_off;         /* [max_blocks] out: offset of every member's payload in the output */
+    uint32_t *isize;           /* [max_blocks] out: ISIZE of every member */
+    uint64_t *ncand, *nmembers, *out_bytes;   /* three consecutive u64 */
+    uint32_t *status;          /* bit 0: not a BGZF stream, bit 1: more candidates than max_blocks */
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -57,9 +73,8 @@ cudaError_t bgzf_launch_scan(const uint32_t *len, uint64_t *off, uint32_t nmax, 
 cudaError_t bgzf_launch_compact(const uint8_t *slots, const uint32_t *len, uint64_t *off, uint32_t nblocks, uint8_t *out,
                                 uint64_t *total, int append_eof, cudaStream_t stream);
 size_t bgzf_index_tiles(uint64_t in_bytes);
-cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, uint64_t *in_off, uint64_t *out_off, uint32_t max_blocks,
-                              uint32_t *tile_count, uint64_t *tile_off, uint32_t *isize, uint64_t *nmembers,
-                              uint64_t *out_bytes, uint32_t *status, cudaStream_t stream);
+#define BGZF_INDEX_LAUNCHES 8
+cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, const BgzfIndexWork *w, cudaStream_t stream);
 cudaError_t bgzf_launch_inflate(const BgzfInflateArgs *a, cudaStream_t stream);
 #ifdef __cplusplus
 }

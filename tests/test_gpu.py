@@ -62,8 +62,10 @@ def test_known_answers_of_the_reference(codec):
 
 
 @pytest.mark.parametrize("kind", ["fastq", "sam"])
-@pytest.mark.parametrize("level", [1, 6, 9, 12])
+@pytest.mark.parametrize("level", list(range(1, 13)))
 def test_stream_parity_size_crc_and_reference_decoder(codec, kind, level):
+    """every level class against the reference at the SAME level: decodes through the reference's libdeflate decoder,
+    CRC32/ISIZE exact, size within 3 % of the reference's (BASELINE north_star tolerance)"""
     data = H.synth(kind, (8 << 20) if level < 10 else (2 << 20))     # the reference's level 12 runs at ~1 MB/s per core
     got = codec.compress(data, level)
     assert got[: 20 * 16384].startswith(H.emul_stream(data[: 4 * H.BLOCK], level, eof=False))
@@ -225,6 +227,65 @@ def test_device_resident_api_roundtrip(codec):
     bad[16] = (int(bad[16]) + 1) % 256
     with pytest.raises(b200bgzf.B200BgzfError):
         codec.inflate_device(bad.data_ptr(), n, back.data_ptr(), back.numel(), stream=s)
+
+
+def test_device_index_ignores_signatures_inside_payloads(codec):
+    """A stream whose payload holds BGZF headers (bgzip of a .bam / of a tar of .bgz files: incompressible, so it sits
+    raw in stored members) must inflate on the device-resident path too: the member list is the BSIZE chain from offset 0
+    (the reference's strictly sequential header walk, applet/7bgzf.c:306-330), not every signature hit."""
+    import torch
+    inner = codec.compress(H.synth("fastq", 40 * H.BLOCK + 77), 6)
+    tiny = b"".join(codec.compress(b"x" * k, 6, eof=False) for k in range(1, 600))      # ~600 signatures within 20 KB
+    tarlike = bytes(512) + inner + bytes(1024) + tiny + H.EOF_BLOCK * 3 + inner[:100000]
+    s = torch.cuda.current_stream().cuda_stream
+    for payload in (inner, tarlike):
+        for level in (1, 6):
+            outer = codec.compress(payload, level)
+            nsig = outer.count(bytes.fromhex("1f8b08040000000000ff0600424302"))
+            assert nsig > len(H.members(outer)) + 30                                        # embedded headers survive verbatim
+            assert codec.inflate(outer) == payload                                          # host header walk
+            d = torch.frombuffer(bytearray(outer), dtype=torch.uint8).cuda()
+            back = torch.empty(len(payload) + 64, dtype=torch.uint8, device="cuda")
+            m = codec.inflate_device(d.data_ptr(), len(outer), back.data_ptr(), back.numel(), stream=s)
+            assert m == len(payload) and bytes(back[:m].cpu().numpy()) == payload
+            m = codec.inflate_device(d.data_ptr(), len(outer), back.data_ptr(), back.numel(), flags=b200bgzf.VERIFY, stream=s)
+            assert m == len(payload)
+            if H.have_ref():
+                rc, out, _ = H.Ref(6).inflate_stream(outer)
+                assert rc == 0 and out == payload
+            # a stream that does not start with a member, or whose chain stops short of the end, is still refused
+            for bad in (b"\0" + outer, outer + b"\0", outer[:-1]):
+                d2 = torch.frombuffer(bytearray(bad), dtype=torch.uint8).cuda()
+                with pytest.raises(b200bgzf.B200BgzfError) as e:
+                    codec.inflate_device(d2.data_ptr(), len(bad), back.data_ptr(), back.numel(), stream=s)
+                assert e.value.code == b200bgzf.E_FORMAT
+    # three levels deep
+    deep = codec.compress(codec.compress(codec.compress(H.synth("sam", 1 << 20), 6), 6), 6)
+    d = torch.frombuffer(bytearray(deep), dtype=torch.uint8).cuda()
+    back = torch.empty(len(deep) + 64, dtype=torch.uint8, device="cuda")
+    m = codec.inflate_device(d.data_ptr(), len(deep), back.data_ptr(), back.numel(), stream=s)
+    assert bytes(back[:m].cpu().numpy()) == codec.inflate(deep)
+
+
+def test_near_optimal_block_list_calls_of_growing_size(codec):
+    """hook lanes serve 1-block and 2-4-block calls alike: the four-candidate scratch of the near-optimal levels must be
+    sized for the larger grid whichever comes first (out-of-bounds writes with 1 then 3 payloads at level 12)"""
+    c2 = b200bgzf.Codec(0)
+    try:
+        data = H.synth("fastq", 4 * H.BLOCK)
+        blocks = [data[o : o + H.BLOCK] for o in range(0, len(data), H.BLOCK)]
+        for level in (12, 10):
+            one, st = c2.compress_blocks(blocks[:1], level)
+            assert st == [0]
+            three, st = c2.compress_blocks(blocks[1:4], level)
+            assert st == [0, 0, 0]
+            four, st = c2.compress_blocks(blocks, level)
+            assert st == [0] * 4 and four[:1] == one and four[1:] == three
+            assert b"".join(four) + H.EOF_BLOCK == codec.compress(data, level)
+            for m, b in zip(four, blocks):
+                assert H.gunzip(m) == b
+    finally:
+        c2.close()
 
 
 def test_verify_flag_checks_crc32_of_every_member(codec):
@@ -460,3 +521,31 @@ def test_full_size_properties_1gib(codec):
             assert crc == zlib.crc32(hb[i * H.BLOCK : i * H.BLOCK + isize].tobytes())
         crc_all = o.oracle_crc32_combine(crc_all, crc, isize)
     assert crc_all == zlib.crc32(hb)
+    if H.have_ref():
+        # the whole 1 GiB stream through the reference's own libdeflate decoder (all host threads), bit-exact
+        o2 = H.oracle()
+        n_out, rc = ctypes.c_size_t(), ctypes.c_int()
+        back.zero_()
+        t = o2.refh_inflate(H.Ref(6).h, out.data_ptr(), clen, os.cpu_count() or 1, back.data_ptr(), n, ctypes.byref(n_out), ctypes.byref(rc))
+        assert t >= 0 and rc.value == 0 and n_out.value == n and torch.equal(back, host)
+
+
+def test_full_size_near_optimal_256mib_through_reference_decoder(codec):
+    """BASELINE config 4's class at 256 MiB: the level-12 stream decodes bit-exactly through the reference's decoder and
+    stays within 3 % of the reference's level-12 size (the reference compresses a 4 MiB sample: ~1 MB/s per core)"""
+    import torch
+    if not H.have_ref():
+        pytest.skip("oracle/_ref not built")
+    n = 256 << 20
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    H._gen().b200gen_fill(0, 1, host.data_ptr(), n)
+    out = torch.empty(codec.bound(n), dtype=torch.uint8, pin_memory=True)
+    clen = codec.compress_into(host.data_ptr(), n, out.data_ptr(), out.numel(), 12)
+    back = torch.zeros(n, dtype=torch.uint8, pin_memory=True)
+    n_out, rc = ctypes.c_size_t(), ctypes.c_int()
+    t = H.oracle().refh_inflate(H.Ref(12).h, out.data_ptr(), clen, os.cpu_count() or 1, back.data_ptr(), n, ctypes.byref(n_out), ctypes.byref(rc))
+    assert t >= 0 and rc.value == 0 and n_out.value == n and torch.equal(back, host)
+    sample = 4 << 20
+    _, ref_sizes, _ = H.Ref(12).compress_stream(ctypes.string_at(host.data_ptr(), sample), keep=False, threads=os.cpu_count() or 1)
+    ours = sum(m[1] for m in H.members(ctypes.string_at(out.data_ptr(), clen))[: (sample + H.BLOCK - 1) // H.BLOCK])
+    assert ours <= 1.03 * sum(ref_sizes), (ours, sum(ref_sizes))
