@@ -35,7 +35,8 @@
 #define SM_MBAR (SM_SCAL + 4u * BG_S_COUNT)
 #define SM_FRONTIER (SM_MBAR + 8u)
 #define SM_SCAN (SM_MBAR + 16u)
-#define SM_TOTAL (SM_SCAN + 4u * 36u)
+#define SM_READY (SM_SCAN + 4u * 36u)       /* u8[128]: tile k's peers are found (the peers -> link pipeline) */
+#define SM_TOTAL (SM_READY + 128u)
 
 extern "C" size_t bgzf_compress_smem_bytes(void) { return SM_TOTAL; }
 
@@ -97,12 +98,16 @@ __device__ __forceinline__ unsigned hash_peers(uint32_t h, bool valid)
  * B each lane fetches the notes of its next 16 groups with one coalesced 16-byte load, a whole tile ahead. */
 /* (first, step, xprev): a CTA of a cluster takes tiles first, first + step, ... and also leaves each finished tile of
  * prev[] in global memory for the other CTAs (import_peer_tiles); the one-CTA kernel passes 0, 1, nullptr */
-__device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, uint32_t t, uint32_t first, uint32_t step, uint4 *xprev)
+/* (warp, nwarps): the producer warps share the tiles, warp k of nwarps taking tiles first + step * (k, k + nwarps, ...);
+ * ready (optional): one flag per tile in shared memory, raised when the tile's links and notes are out — the linking
+ * relay (build_link_phase) runs at the same time on other warps and waits for it */
+__device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, uint32_t lane, uint32_t warp, uint32_t nwarps, uint32_t first,
+                                                  uint32_t step, uint4 *xprev, volatile uint8_t *ready)
 {
-    const uint32_t n = c.n, lane = t & 31u, warp = t >> 5;
+    const uint32_t n = c.n;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t ntiles = (n + 511u) >> 9;
-    for (uint32_t tile = first + step * warp; tile < ntiles; tile += step * (BG_THREADS / 32)) {
+    for (uint32_t tile = first + step * warp; tile < ntiles; tile += step * nwarps) {
         uint32_t w[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
 #pragma unroll
         for (uint32_t g = 0; g < 16; g++) {
@@ -129,6 +134,11 @@ __device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, 
             xprev[tile * 64u + lane] = ts[lane];
             xprev[tile * 64u + 32u + lane] = ts[32u + lane];
         }
+        if (ready) {
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) ready[tile] = 1;
+        }
     }
 }
 
@@ -148,12 +158,17 @@ __device__ __forceinline__ void import_peer_tiles(const BgCtx &c, const uint4 *x
  * leaders' hashes before, and storing the links after, overlap with the other warps' turns.  head[] reads and
  * writes go out back to back; the links they return are parked in registers until the turn has been passed on. */
 #define BG_LINKERS 4u
-__device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *notes, uint32_t warp, uint32_t lane, volatile uint32_t *turn)
+__device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *notes, uint32_t warp, uint32_t lane, volatile uint32_t *turn,
+                                                 volatile uint8_t *ready)
 {
     const uint32_t n = c.n;
     const uint32_t ntiles = (n + 511u) >> 9;
     volatile uint16_t *vhead = c.head;
     for (uint32_t tile = warp; tile < ntiles; tile += BG_LINKERS) {
+        if (ready) {
+            while (!ready[tile]) __nanosleep(40);
+            __threadfence_block();
+        }
         const uint4 cur = __ldcg(notes + tile * 32u + lane);
         const uint32_t w[4] = { cur.x, cur.y, cur.z, cur.w };
         /* the hash slots of this tile's leaders are untouched until their links are stored below: fetch them all now */
@@ -184,29 +199,145 @@ __device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *no
     }
 }
 
-/* ---- all-position search: thread t takes positions t, t+1024, ... ---- */
-__device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
+/* ---- the search of the greedy / lazy classes (bgzf_block.h: "the search in three passes").  `own`/`parts`: CTA `own` of
+ * a cluster of `parts` that shares ONE block keeps every parts-th group of 32 positions (the one-CTA kernel: 0, 1). ---- */
+
+/* pass 1: nearest-candidate match of every position; landing marks and eligibility bits with one ballot per 32 positions */
+__device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
-    if (c.prm.opt_passes > 0) {
-        for (uint32_t p = t; p < c.n; p += BG_THREADS)
-            c.R[p] = bg_search_one_multi(c, p);       /* near-optimal class: up to four matches per position */
+    const uint32_t n = c.n, lane = t & 31u;
+    uint32_t *elig = (uint32_t *)(c.regb + BG_B_TODO), *mark = (uint32_t *)(c.regb + BG_B_MARK);
+    if (c.scal[BG_S_DEPTH] <= 1) {                                  /* depth 1 (level 1): the nearest candidate is the whole search */
+        for (uint32_t p = t; p < n; p += BG_THREADS) {
+            bool deep;
+            uint32_t target;
+            const uint32_t r = bg_nearest(c, p, &deep, &target);
+            if ((p >> 5) % parts == own) c.R[p] = r;
+        }
         return;
     }
+    if (t == 0) atomicOr(&mark[0], 1u);
+    for (uint32_t p0 = t - lane; p0 < n; p0 += BG_THREADS) {       /* (warp-uniform trip count) */
+        const uint32_t p = p0 + lane;
+        bool deep = false;
+        uint32_t target = p + 1, r = 0;
+        if (p < n) {
+            r = bg_nearest(c, p, &deep, &target);
+            if ((p0 >> 5) % parts == own) c.R[p] = r;
+        }
+        const bool lit = p < n && target == p + 1;
+        const unsigned lm = __ballot_sync(0xffffffffu, lit), em = __ballot_sync(0xffffffffu, deep);
+        const uint32_t before = __shfl_up_sync(0xffffffffu, target, 1);
+        if (lane == 0) {
+            elig[p0 >> 5] = em;
+            if (lm << 1) atomicOr(&mark[p0 >> 5], lm << 1);
+            if (lm >> 31) atomicOr(&mark[(p0 >> 5) + 1], 1u);
+        }
+        /* consecutive positions inside one match land on the same position: one of them marks it */
+        if (p < n && !lit && (lane == 0 || before != target)) atomicOr(&mark[target >> 5], 1u << (target & 31u));
+    }
+}
+
+/* pass 3: up to 32 queued candidates, one per lane: full extension, merged into the position's match word */
+__device__ __forceinline__ void drain_queue(const BgCtx &c, const uint32_t *queue, uint32_t from, uint32_t count, uint32_t lane)
+{
+    if (lane < count) {
+        const uint32_t e = queue[from + lane];
+        const uint32_t p = e >> 16, q = e & 0xffffu;
+        const uint32_t v = bg_deep_extend(c, p, q);
+        if (v) atomicMax(&c.R[p], v);
+    }
+}
+
+/* pass 2 for a batch of todo positions (one per lane): walk the chain beyond the nearest candidate; candidates that agree on
+ * the 4 bytes ending just past the nearest match go to the warp's queue (one ballot per chain step places them), which is
+ * drained whenever it holds a full batch.  cnt = entries waiting in the queue (warp-uniform, < 32 on entry and on exit). */
+__device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint32_t &cnt, uint32_t p, bool active, uint32_t lane)
+{
+    uint32_t q = BG_NOPOS, b1 = 3, tail = 0;
+    int depth = (int)c.scal[BG_S_DEPTH] - 1;
+    const unsigned lt = (1u << lane) - 1u;
+    if (active) {
+        const uint32_t r1 = __ldcg(c.R + p);
+        b1 = r1 ? r1 >> 16 : 3u;
+        tail = bg_ld32(c.dataw, p + b1 - 3u);
+        q = c.prev[c.prev[p]];
+    }
+    bool live = active && depth > 0 && bg_in_window(p, q);
+    while (__any_sync(0xffffffffu, live)) {
+#pragma unroll
+        for (uint32_t k = 0; k < BG_SCAN_CHUNK; k++) {
+            bool pass = false;
+            const uint32_t qc = q;
+            if (live) {
+                const uint32_t qn = c.prev[q];
+                pass = bg_ld32(c.dataw, q + b1 - 3u) == tail;
+                depth--;
+                q = qn;
+                live = depth > 0 && bg_in_window(p, q);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                if (pass) queue[cnt + __popc(m & lt)] = (p << 16) | qc;
+                cnt += __popc(m);
+            }
+        }
+        if (cnt >= 32u) {
+            __syncwarp();
+            do {
+                cnt -= 32u;
+                drain_queue(c, queue, cnt, 32u, lane);
+            } while (cnt >= 32u);
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
+{
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    const uint32_t *todo = (const uint32_t *)(c.regb + BG_B_TODO);
+    uint32_t *queue = (uint32_t *)(c.regb + BG_B_QUEUE) + warp * BG_QUEUE_WORDS;
+    volatile uint16_t *gather = (volatile uint16_t *)(c.regb + BG_B_GATHER) + warp * 64u;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t nwords = (c.n + 31u) >> 5;
+    uint32_t fill = 0, cnt = 0;                                  /* todo positions waiting in gather[], candidates in queue[] (warp-uniform) */
+    /* warp w takes every 32nd of this CTA's words (32 positions each): records alternate between cheap (sequence) and
+     * deep (quality) stretches, so the work spreads evenly */
+    for (uint32_t i = own + parts * warp; i < nwords; i += parts * (BG_THREADS / 32u)) {
+        const uint32_t w = todo[i];
+        if (w == 0) continue;
+        if ((w >> lane) & 1u) gather[fill + __popc(w & lt)] = (uint16_t)(i * 32u + lane);
+        fill += __popc(w);
+        __syncwarp();
+        if (fill >= 32u) {
+            const uint32_t p = gather[lane];
+            const uint32_t rest = lane + 32u < fill ? gather[lane + 32u] : 0u;
+            __syncwarp();
+            if (lane + 32u < fill) gather[lane] = (uint16_t)rest;
+            fill -= 32u;
+            deep_batch(c, queue, cnt, p, true, lane);
+        }
+    }
+    __syncwarp();
+    if (fill) deep_batch(c, queue, cnt, lane < fill ? gather[lane] : 0u, lane < fill, lane);
+    __syncwarp();
+    drain_queue(c, queue, 0u, cnt, lane);
+}
+
+/* ---- near-optimal class: all-position search keeping four matches per position ---- */
+__device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
+{
     for (uint32_t p = t; p < c.n; p += BG_THREADS)
-        c.R[p] = bg_search_one(c, p);
+        c.R[p] = bg_search_one_multi(c, p);
 }
 
 /* the same, for one CTA of a cluster that shares the search of ONE block: CTA `rank` of `parts` takes every
  * parts-th tile of 1024 positions and writes to the match scratch of the cluster's first CTA */
 __device__ __forceinline__ void search_positions_part(const BgCtx &c, uint32_t t, uint32_t rank, uint32_t parts)
 {
-    if (c.prm.opt_passes > 0) {
-        for (uint32_t p = rank * BG_THREADS + t; p < c.n; p += parts * BG_THREADS)
-            c.R[p] = bg_search_one_multi(c, p);
-        return;
-    }
     for (uint32_t p = rank * BG_THREADS + t; p < c.n; p += parts * BG_THREADS)
-        c.R[p] = bg_search_one(c, p);
+        c.R[p] = bg_search_one_multi(c, p);
 }
 
 __device__ __forceinline__ uint32_t cluster_rank()
@@ -303,7 +434,7 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
             } else {
                 const uint32_t off = (k == 0 ? mine.x : k == 1 ? mine.y : k == 2 ? mine.z : mine.w) & 0xffffu;
                 c.stepcode[q] = (uint8_t)(l <= 256 ? l - 2 : 255);
-                c.R[q] = (l << 16) | off;
+                c.R[q] = bg_mw(l, off);
             }
         }
         if (!more) break;
@@ -457,23 +588,41 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         if (SPLIT) {
             /* every CTA has the same hashes; each finds the peers of its share of the tiles, the links travel through L2 */
             uint4 *xprev = (uint4 *)(a.scratch + BGZF_SCRATCH_WORDS);
-            build_peers_phase(c, hi, t, crank, csize, xprev);
+            build_peers_phase(c, hi, t & 31u, t >> 5, BG_THREADS / 32u, crank, csize, xprev, nullptr);
             cluster_sync();
             import_peer_tiles(c, xprev, t, crank, csize);
+            __syncthreads();
+            PROF_MARK(3);
+            if (t < 32u * BG_LINKERS) build_link_phase(c, hi, t >> 5, t & 31u, &c.scal[BG_S_WLIST], nullptr);   /* the other warps wait at the barrier */
         } else {
-            build_peers_phase(c, hi, t, 0u, 1u, nullptr);
+            /* peers and links at the same time: warps 0..3 are the linking relay, the other 28 find the peers tile by tile
+             * and raise a flag per tile; the relay's ordered head-table section hides behind the ballots of the producers */
+            volatile uint8_t *ready = (volatile uint8_t *)(smem + SM_READY);
+            if (t < 128u) ready[t] = 0;
+            __syncthreads();
+            if (t < 32u * BG_LINKERS) build_link_phase(c, hi, t >> 5, t & 31u, &c.scal[BG_S_WLIST], ready);
+            else build_peers_phase(c, hi, t & 31u, (t >> 5) - BG_LINKERS, BG_THREADS / 32u - BG_LINKERS, 0u, 1u, nullptr, ready);
         }
         __syncthreads();
-        PROF_MARK(3);
-        if (t < 32u * BG_LINKERS) build_link_phase(c, hi, t >> 5, t & 31u, &c.scal[BG_S_WLIST]);   /* the other warps wait at the barrier */
-        __syncthreads();
         PROF_MARK(10);
+        if (c.prm.opt_passes > 0) {
+            if (SPLIT) search_positions_part(c, t, crank, csize);
+            else search_positions(c, t);
+        } else {
+            bg_phase_search_clear(c, t, T);
+            __syncthreads();
+            search_nearest(c, t, crank, csize);
+            __syncthreads();
+            PROF_MARK(21);
+            if (c.scal[BG_S_DEPTH] > 1) {                        /* (uniform for the CTA) */
+                bg_phase_search_todo(c, t, T, crank, csize);
+                __syncthreads();
+                search_deep(c, t, crank, csize);
+            }
+        }
         if (SPLIT) {
-            search_positions_part(c, t, crank, csize);
             cluster_sync();
             if (crank) return;
-        } else {
-            search_positions(c, t);
         }
         __syncthreads();
         PROF_MARK(4);

@@ -11,7 +11,7 @@ c.profile(True, True)
 out = c.compress(data, level)
 prof = c.profile(False, True)
 nblk = (mib << 20) / 0xff00
-names = {0: "load", 1: "crc+census", 2: "hash", 3: "peers", 10: "link", 4: "search", 15: "accept/dp", 5: "jump", 16: "walk clear+mark+list", 17: "walk a", 18: "walk b", 6: "walk c",
+names = {0: "load", 1: "crc+census", 2: "hash", 3: "peers", 10: "link", 21: "search: nearest", 4: "search: todo+deep", 15: "accept/dp", 5: "jump", 16: "walk clear+mark+list", 17: "walk a", 18: "walk b", 6: "walk c",
          7: "tally", 11: "sort", 12: "trees", 13: "header", 8: "codes+tabs", 19: "sizes", 20: "scans", 14: "zero", 9: "emit"}
 tot = sum(prof)
 print(f"level {level} {kind} {mib} MiB: ratio {len(out)/len(data):.4f}, {tot/nblk:.0f} cycles/block")
