@@ -23,6 +23,8 @@ EXPORTS = [
     "b200bgzf_compress_device", "b200bgzf_compress_host", "b200bgzf_compress_blocks_host", "b200bgzf_inflate_size_host",
     "b200bgzf_inflate_device", "b200bgzf_inflate_host", "b200bgzf_profile", "b200bgzf_launch_count", "b200bgzf_parse_method",
     "b200bgzf_host_alloc", "b200bgzf_host_free", "b200bgzf_member_header", "b200bgzf_compress_host_index", "b200bgzf_gzi_format",
+    "b200bgzf_multi_create", "b200bgzf_multi_destroy", "b200bgzf_multi_count", "b200bgzf_multi_ctx", "b200bgzf_shard_blocks",
+    "b200bgzf_multi_compress_bound", "b200bgzf_multi_compress_host", "b200bgzf_multi_inflate_host",
 ]
 
 
@@ -63,6 +65,18 @@ def load(path=LIB_PATH):
     lib.b200bgzf_parse_method.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32), ctypes.c_char_p, sz]
     lib.b200bgzf_member_header.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64)]
     lib.b200bgzf_member_header.restype = u32
+    lib.b200bgzf_multi_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(i32), i32]
+    lib.b200bgzf_multi_destroy.argtypes = [vp]
+    lib.b200bgzf_multi_destroy.restype = None
+    lib.b200bgzf_multi_count.argtypes = [vp]
+    lib.b200bgzf_multi_ctx.argtypes = [vp, i32]
+    lib.b200bgzf_multi_ctx.restype = vp
+    lib.b200bgzf_shard_blocks.argtypes = [ctypes.c_uint64, i32, i32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    lib.b200bgzf_shard_blocks.restype = None
+    lib.b200bgzf_multi_compress_bound.argtypes = [vp, sz, u32]
+    lib.b200bgzf_multi_compress_bound.restype = sz
+    lib.b200bgzf_multi_compress_host.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint]
+    lib.b200bgzf_multi_inflate_host.argtypes = [vp, vp, sz, vp, sz, psz, ctypes.c_uint]
     return lib
 
 
@@ -177,6 +191,64 @@ class Codec:
 
     def launches(self):
         return self.lib.b200bgzf_launch_count(self.h)
+
+
+class MultiCodec:
+    """Several GPU contexts behind one host-buffer call (b200bgzf_multi_*): contiguous block ranges, no collective."""
+
+    def __init__(self, devices, path=LIB_PATH):
+        self.lib = load(path)
+        h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        rc = self.lib.b200bgzf_multi_create(ctypes.byref(h), arr, len(devices))
+        if rc != 0:
+            raise B200BgzfError(rc, self.lib.b200bgzf_strerror(rc).decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.b200bgzf_multi_destroy(self.h)
+            self.h = None
+
+    def count(self):
+        return self.lib.b200bgzf_multi_count(self.h)
+
+    def bound(self, n, block_size=BLOCK_SIZE):
+        return self.lib.b200bgzf_multi_compress_bound(self.h, n, block_size)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200BgzfError(rc, self.lib.b200bgzf_strerror(rc).decode())
+
+    def compress_into(self, src_addr, nbytes, dst_addr, dst_cap, level=6, block_size=BLOCK_SIZE, eof=True):
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_multi_compress_host(self.h, src_addr, nbytes, block_size, level, dst_addr, dst_cap, ctypes.byref(n),
+                                                          APPEND_EOF if eof else 0))
+        return n.value
+
+    def compress(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
+        out = bytearray(self.bound(len(data), block_size))
+        n = self.compress_into(_addr(data) if len(data) else None, len(data), _addr(out), len(out), level, block_size, eof)
+        return bytes(out[:n])
+
+    def inflate_into(self, src_addr, nbytes, dst_addr, dst_cap, flags=0):
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_multi_inflate_host(self.h, src_addr, nbytes, dst_addr, dst_cap, ctypes.byref(n), flags))
+        return n.value
+
+    def inflate(self, data, flags=0):
+        total, nm = ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_inflate_size_host(_addr(data), len(data), ctypes.byref(total), ctypes.byref(nm)))
+        out = bytearray(max(total.value, 1))
+        n = self.inflate_into(_addr(data), len(data), _addr(out), len(out), flags)
+        return bytes(out[:n])
+
+
+def shard_blocks(nblocks, shard, nshards, lib=None):
+    lib = lib or load()
+    a, b = ctypes.c_uint64(), ctypes.c_uint64()
+    lib.b200bgzf_shard_blocks(nblocks, shard, nshards, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
 
 
 def member_header(data, lib=None):

@@ -61,6 +61,7 @@ static void usage(const char *argv0)
             "  -@, --threads=threads     threads\n"
             "  -d, --decompress          decompress\n"
             "      --gzi=FILE            (extension) also write a bgzip-style .gzi index of the members to FILE\n"
+            "      --devices=N           (extension) spread the blocks over N GPUs (contiguous block ranges, same output)\n"
             "\nNote: every method runs on the B200 BGZF codec (libdeflate level classes 1-12).\n",
             argv0);
 }
@@ -246,7 +247,19 @@ static int gzi_write(const struct gzi_acc *g, const char *path)
     return ok ? 0 : 1;
 }
 
-static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t block, const char *gzi_path)
+/* member starts of a stream by a header walk (the multi-GPU call reports no offsets) */
+static size_t walk_member_offsets(const unsigned char *buf, size_t len, uint64_t *off, size_t cap)
+{
+    size_t n = 0, pos = 0;
+    while (pos + 28 <= len && n < cap) {
+        const size_t sz = ((size_t)buf[pos + 16] | ((size_t)buf[pos + 17] << 8)) + 1;
+        off[n++] = pos;
+        pos += sz;
+    }
+    return n;
+}
+
+static int run_pipeline(b200bgzf_ctx *ctx, b200bgzf_multi *multi, int decompress, int level, uint32_t block, const char *gzi_path)
 {
     struct gzi_acc gzi;
     memset(&gzi, 0, sizeof gzi);
@@ -262,7 +275,7 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
         ps.out_cap = (size_t)96 << 20;       /* ... this much output (pinning memory costs ~0.4 ms per MiB: keep the slots modest) */
     } else {
         ps.in_cap = (size_t)SLOT_BLOCKS * block;
-        ps.out_cap = b200bgzf_compress_bound(ps.in_cap, B200BGZF_BLOCK_SIZE);   /* (the bound of the smaller block size is the larger one) */
+        ps.out_cap = b200bgzf_compress_bound(ps.in_cap, B200BGZF_BLOCK_SIZE) + 64 * B200BGZF_EOF_BYTES;   /* (the bound of the smaller block size is the larger one; room for the multi-GPU placement) */
     }
     const double ta = now_s();
     for (int i = 0; i < NSLOTS; i++) {
@@ -290,22 +303,25 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
         if (sl->in_len) {
             int r;
             if (decompress) {
-                r = b200bgzf_inflate_host(ctx, sl->in, sl->in_len, sl->out, ps.out_cap, &sl->out_len, 0);
+                r = multi ? b200bgzf_multi_inflate_host(multi, sl->in, sl->in_len, sl->out, ps.out_cap, &sl->out_len, 0)
+                          : b200bgzf_inflate_host(ctx, sl->in, sl->in_len, sl->out, ps.out_cap, &sl->out_len, 0);
                 if (r != 0) { fprintf(stderr, "inflate %d\n", r); ret = 1; }
                 units += (long)sl->members;
             } else {
                 uint32_t used_block = block;
-                r = b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len,
-                                                 sl->last ? B200BGZF_APPEND_EOF : 0, gzi.slot_off, gzi.slot_cap);
+                const unsigned fl = sl->last ? B200BGZF_APPEND_EOF : 0;
+                r = multi ? b200bgzf_multi_compress_host(multi, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len, fl)
+                          : b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len, fl, gzi.slot_off, gzi.slot_cap);
                 if (r == B200BGZF_E_NOFIT && block > B200BGZF_BLOCK_SIZE) {
                     /* a 65536-byte payload that does not compress cannot fit a member: the reference's single-thread path
                      * shrinks the block and redoes it (7bgzf.c:135-147,256-262); here the slot is redone in 0xff00-byte
                      * blocks, which always fit */
                     used_block = B200BGZF_BLOCK_SIZE;
-                    r = b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, used_block, level, sl->out, ps.out_cap, &sl->out_len,
-                                                     sl->last ? B200BGZF_APPEND_EOF : 0, gzi.slot_off, gzi.slot_cap);
+                    r = multi ? b200bgzf_multi_compress_host(multi, sl->in, sl->in_len, used_block, level, sl->out, ps.out_cap, &sl->out_len, fl)
+                              : b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, used_block, level, sl->out, ps.out_cap, &sl->out_len, fl, gzi.slot_off, gzi.slot_cap);
                     units += (long)((sl->in_len + B200BGZF_BLOCK_SIZE - 1) / B200BGZF_BLOCK_SIZE) - (long)((sl->in_len + block - 1) / block);
                 }
+                if (!r && multi && gzi.slot_off) walk_member_offsets(sl->out, sl->out_len, gzi.slot_off, gzi.slot_cap);
                 if (r == B200BGZF_E_NOFIT) { fprintf(stderr, "libdeflate_deflate %d\n", 1); ret = 1; }
                 else if (r != 0) { fprintf(stderr, "b200bgzf: %s (%s)\n", b200bgzf_strerror(r), b200bgzf_last_error(ctx)); ret = 1; }
                 units += (long)((sl->in_len + block - 1) / block);
@@ -314,7 +330,7 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
         } else if (!decompress && sl->last) {
             /* empty tail slot: still owe the EOF marker (7bgzf.c:283-289) */
             size_t n = 0;
-            b200bgzf_compress_host(ctx, NULL, 0, block, level, sl->out, ps.out_cap, &n, B200BGZF_APPEND_EOF);
+            b200bgzf_compress_host(multi ? b200bgzf_multi_ctx(multi, 0) : ctx, NULL, 0, block, level, sl->out, ps.out_cap, &n, B200BGZF_APPEND_EOF);
             sl->out_len = n;
         }
         g_t_codec += now_s() - tc;
@@ -342,7 +358,7 @@ static int run_pipeline(b200bgzf_ctx *ctx, int decompress, int level, uint32_t b
 int main(int argc, char **argv)
 {
     int levels[NFLAGS];
-    int decompress = 0, nthreads = 1, bad = 0;
+    int decompress = 0, nthreads = 1, bad = 0, ndevices = 1;
     const char *gzi_path = NULL;
     memset(levels, 0, sizeof levels);
     /* allow `cielbox 7bgzf ...` style invocation */
@@ -357,6 +373,7 @@ int main(int argc, char **argv)
         { "zopfli", required_argument, 0, 'Z' }, { "store", optional_argument, 0, 'T' },
         { "threads", required_argument, 0, '@' }, { "decompress", no_argument, 0, 'd' },
         { "help", no_argument, 0, 'h' },         { "gzi", required_argument, 0, 1000 },
+        { "devices", required_argument, 0, 1001 },
         { 0, 0, 0, 0 },
     };
     int opt;
@@ -365,6 +382,7 @@ int main(int argc, char **argv)
         if (opt == 'd') { decompress = 1; continue; }
         if (opt == '@') { nthreads = atoi(optarg); continue; }
         if (opt == 1000) { gzi_path = optarg; continue; }
+        if (opt == 1001) { ndevices = atoi(optarg); if (ndevices < 1 || ndevices > 64) bad = 1; continue; }
         if (opt == 'h' || opt == '?') { bad = 1; continue; }
         for (size_t k = 0; k < NFLAGS; k++)
             if (k_flags[k].short_opt == opt)
@@ -384,8 +402,9 @@ int main(int argc, char **argv)
     struct timeval t0, t1;
     gettimeofday(&t0, NULL);
     b200bgzf_ctx *ctx = NULL;
+    b200bgzf_multi *multi = NULL;
     const char *dev = getenv("B200BGZF_DEVICE");
-    int r = b200bgzf_create(&ctx, dev && *dev ? atoi(dev) : -1);
+    int r = ndevices > 1 ? b200bgzf_multi_create(&multi, NULL, ndevices) : b200bgzf_create(&ctx, dev && *dev ? atoi(dev) : -1);
     if (r != 0) {
         fprintf(stderr, "b200bgzf: cannot initialise the GPU codec: %s\n", b200bgzf_strerror(r));
         return 1;
@@ -393,7 +412,7 @@ int main(int argc, char **argv)
     const double t_created = now_s();
     int ret;
     if (decompress) {
-        ret = run_pipeline(ctx, 1, 0, 0, NULL);
+        ret = run_pipeline(ctx, multi, 1, 0, 0, NULL);
     } else {
         int level = level_sum;
         fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
@@ -401,11 +420,12 @@ int main(int argc, char **argv)
         if (level > 12) level = 12;
         /* block size rule of the reference (7bgzf.c:141-147): 0x10000 with one thread, 0xff00 with -@N; the thread count has
          * no other meaning here (the GPU works on all blocks of a slot at once) */
-        ret = run_pipeline(ctx, 0, level, nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE, gzi_path);
+        ret = run_pipeline(ctx, multi, 0, level, nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE, gzi_path);
     }
     fflush(stdout);
     const double t_piped = now_s();
     b200bgzf_destroy(ctx);
+    b200bgzf_multi_destroy(multi);
     gettimeofday(&t1, NULL);
     if (getenv("B200BGZF_DEBUG"))
         fprintf(stderr, "seconds: create %.3f, pipeline %.3f, destroy %.3f\n", t_created - (t0.tv_sec + t0.tv_usec * 1e-6), t_piped - t_created,

@@ -25,11 +25,11 @@ $(OBJ)/%.o: $(HOST)/%.c include/b200bgzf.h
 	$(CC) $(CFLAGS) -c $< -o $@
 
 # the codec library: kernels + C ABI (+ the BGZF_METHOD parser)
-$(PKG)/lib7bgzf_b200.so: $(CU_OBJS) $(OBJ)/method.o
+$(PKG)/lib7bgzf_b200.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(HOST)/exports.map -lpthread
 
 # the LD_PRELOAD object: the same plus htslib's bgzf_compress
-$(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/hook.o
+$(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/hook.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(HOST)/exports.map -lpthread
 
 # the applet

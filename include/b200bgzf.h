@@ -107,6 +107,26 @@ int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size_t in_bytes
 int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
                           unsigned flags);
 
+/*
+ * Several GPUs behind one call (the reference's fan-out over blocks: applet/7bgzf.c:159-227).  GPU g of G takes
+ * the contiguous block range [B*g/G, B*(g+1)/G) of the input (b200bgzf_shard_blocks), runs its own pipelined host-buffer
+ * call on its own context and host thread, and the shard outputs are joined at host-known offsets: no collective, and the
+ * stream is byte-identical for every G.  devices == NULL: ordinals 0..ndevices-1 (an ordinal may repeat: two contexts on
+ * one GPU).  The output buffer must hold b200bgzf_multi_compress_bound() bytes (28 more per extra shard than the
+ * single-GPU bound: every shard is placed behind the worst case of the ones before it, then moved down).
+ */
+typedef struct b200bgzf_multi b200bgzf_multi;
+int b200bgzf_multi_create(b200bgzf_multi **m, const int *devices, int ndevices);
+void b200bgzf_multi_destroy(b200bgzf_multi *m);
+int b200bgzf_multi_count(const b200bgzf_multi *m);
+b200bgzf_ctx *b200bgzf_multi_ctx(b200bgzf_multi *m, int i);
+void b200bgzf_shard_blocks(uint64_t nblocks, int shard, int nshards, uint64_t *first, uint64_t *last);
+size_t b200bgzf_multi_compress_bound(const b200bgzf_multi *m, size_t in_bytes, uint32_t block_size);
+int b200bgzf_multi_compress_host(b200bgzf_multi *m, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                                 size_t out_cap, size_t *out_bytes, unsigned flags);
+int b200bgzf_multi_inflate_host(b200bgzf_multi *m, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
+                                unsigned flags);
+
 /* Page-locked host memory for the *_host entry points (pageable buffers work too, but are copied at a fraction of
  * the PCIe rate).  The applet reads stdin straight into such buffers. */
 void *b200bgzf_host_alloc(size_t bytes);

@@ -202,3 +202,22 @@ def test_gzi_formatter_layout():
     stream = b"".join(H.zlib_member(pl) for pl in (b"a" * 100, b"b" * 7, b"c" * 5000)) + b200bgzf.EOF_BLOCK
     offs = [m[0] for m in H.members(stream)][:3]
     assert H.gzi_of(stream) == b200bgzf.gzi_format(offs, [0, 100, 107])
+
+
+def test_shard_blocks_partition_is_contiguous_and_complete():
+    """b200bgzf_shard_blocks (the rule of SURVEY 8e: GPU g of G takes blocks [B*g/G, B*(g+1)/G)) == shard.block_range"""
+    import shard
+    for nb in (0, 1, 7, 16449, 1052689, (1 << 40) + 12345):
+        for world in (1, 2, 3, 4, 8, 64):
+            cuts = [b200bgzf.shard_blocks(nb, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == nb
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+            assert cuts == [shard.block_range(nb, r, world) for r in range(world)]
+
+
+def test_multi_create_without_gpu_fails_loudly():
+    if HAVE_GPU:
+        pytest.skip("GPU present")
+    with pytest.raises(b200bgzf.B200BgzfError) as e:
+        b200bgzf.MultiCodec([0, 1])
+    assert e.value.code == b200bgzf.E_CUDA

@@ -289,6 +289,26 @@ def test_near_optimal_block_list_calls_of_growing_size(codec):
         c2.close()
 
 
+def test_multi_context_sharding_gives_the_single_gpu_stream(codec):
+    """b200bgzf_multi_*: one host buffer fanned over G contexts as contiguous block ranges, shards joined at host-known
+    offsets.  On a one-GPU box the contexts share device 0; the stream must not depend on G."""
+    data = H.synth("sam", 37 * H.BLOCK + 4321)
+    want = codec.compress(data, 6)
+    for devs in ([0], [0, 0], [0, 0, 0], [0] * 8):
+        m = b200bgzf.MultiCodec(devs)
+        try:
+            assert m.count() == len(devs)
+            assert m.compress(data, 6) == want
+            assert m.compress(data[: 3 * H.BLOCK], 6) == codec.compress(data[: 3 * H.BLOCK], 6)    # fewer blocks than contexts
+            assert m.compress(b"", 6) == H.EOF_BLOCK
+            assert m.inflate(want) == data
+            assert m.inflate(H.EOF_BLOCK) == b""
+            with pytest.raises(b200bgzf.B200BgzfError):
+                m.inflate(want[:-40] + b"garbage" + want[-33:])
+        finally:
+            m.close()
+
+
 def test_verify_flag_checks_crc32_of_every_member(codec):
     """B200BGZF_VERIFY: CRC32 of the inflated payload against the trailer (the reference's decompress loop does not
     check it, applet/7bgzf.c:350-354): a flipped trailer byte is caught with the flag and ignored without."""
