@@ -12,6 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -55,7 +58,11 @@ struct Lane {
     bool busy = false;
     int scratch_ctas = 0;
     int cand_ctas = 0;            /* CTAs d_cand is sized for (near-optimal levels) */
-    cudaEvent_t done = nullptr;   /* hook lanes: polled with short sleeps when callers outnumber the host's cores */
+    cudaEvent_t done = nullptr;   /* hook lanes: the context's completion thread polls it when callers outnumber the host's cores */
+    std::atomic<uint32_t> wait_state{0};   /* 0 idle, 1 in flight (the caller sleeps on this word), 2 done */
+    cudaError_t wait_result = cudaSuccess;
+    volatile uint32_t *h_flag = nullptr;   /* pinned: set by a 4-byte copy queued behind the member's copy (no driver call needed to see it) */
+    uint32_t *d_one = nullptr;             /* device word holding 1: the source of that copy */
     uint8_t *one_dev = nullptr, *one_host = nullptr;   /* one-block fast path: everything it needs in one device and one pinned slab */
 };
 
@@ -79,6 +86,14 @@ struct b200bgzf_ctx {
     uint32_t *d_idx_jump = nullptr, *d_idx_jump2 = nullptr, *d_idx_reach = nullptr;
     size_t idx_cap = 0, idx_tiles = 0;
     uint64_t *h_idx = nullptr;
+    /* Completion thread (hook callers beyond the host's core count): callers neither spin nor poll, they sleep on their
+     * lane's futex word; this one thread polls the events of the lanes in flight and wakes each caller as its member is back */
+    std::thread waiter;
+    std::mutex waiter_mu;
+    std::condition_variable waiter_cv;
+    std::atomic<int> waiter_inflight{0};
+    std::atomic<bool> waiter_stop{false};
+    bool waiter_started = false;
     std::atomic<unsigned long long> launches{0};   /* hook callers bump it concurrently */
     std::atomic<bool> no_clusters{false};          /* set when a cluster launch was refused once */
     char err[256] = { 0 };
@@ -91,6 +106,15 @@ struct DeviceGuard {
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+void futex_wait_while(std::atomic<uint32_t> *word, uint32_t value)
+{
+    while (word->load(std::memory_order_acquire) == value)
+        syscall(SYS_futex, (uint32_t *)word, FUTEX_WAIT_PRIVATE, value, nullptr, nullptr, 0);
+}
+void futex_wake_one(std::atomic<uint32_t> *word) { syscall(SYS_futex, (uint32_t *)word, FUTEX_WAKE_PRIVATE, 1, nullptr, nullptr, 0); }
+
+void waiter_main(b200bgzf_ctx *ctx);
 
 int fail(b200bgzf_ctx *c, cudaError_t e, const char *where)
 {
@@ -154,7 +178,8 @@ void lane_free(Lane &l)
     cudaFree(l.one_dev);
     if (l.one_host) cudaFreeHost(l.one_host);
     if (l.stream) cudaStreamDestroy(l.stream);
-    l = Lane();
+    l.~Lane();
+    new (&l) Lane();
 }
 
 /* make sure a lane can process `blocks` compress blocks (device side); staging is grown on demand elsewhere */
@@ -303,6 +328,14 @@ extern "C" int b200bgzf_create(b200bgzf_ctx **out, int device)
 extern "C" void b200bgzf_destroy(b200bgzf_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->waiter_started) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->waiter_mu);
+            ctx->waiter_stop.store(true);
+        }
+        ctx->waiter_cv.notify_all();
+        ctx->waiter.join();
+    }
     {
         DeviceGuard g(ctx->device);
         cudaDeviceSynchronize();
@@ -516,8 +549,13 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
                      kScratch = ((size_t)BGZF_SCRATCH_WORDS + BGZF_SPLIT_EXTRA_WORDS) * sizeof(uint32_t);
     if (!l.stream) CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     if (!l.one_dev) {
-        CK(cudaMalloc((void **)&l.one_dev, kIn + kSlot + kScratch));
-        CK(cudaMallocHost((void **)&l.one_host, kIn + kSlot));
+        CK(cudaMalloc((void **)&l.one_dev, kIn + kSlot + kScratch + 64));
+        CK(cudaMallocHost((void **)&l.one_host, kIn + kSlot + 64));
+        l.d_one = (uint32_t *)(l.one_dev + kIn + kSlot + kScratch);
+        l.h_flag = (volatile uint32_t *)(l.one_host + kIn + kSlot);
+        const uint32_t one = 1;
+        CK(cudaMemcpyAsync(l.d_one, &one, sizeof one, cudaMemcpyHostToDevice, l.stream));
+        CK(cudaStreamSynchronize(l.stream));
     }
     uint8_t *d_in = l.one_dev, *d_slot = l.one_dev + kIn, *h_in = l.one_host, *h_out = l.one_host + kIn;
     uint32_t *d_scratch = (uint32_t *)(l.one_dev + kIn + kSlot);
@@ -558,14 +596,26 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     CK(cudaMemcpyAsync(h_out, d_slot, (size_t)BG_SLOT_BYTES + 8, cudaMemcpyDeviceToHost, l.stream));
     if (sleep_wait) {
         /* more callers in flight than host cores (samtools -@64 on a 16-core box): a spinning wait would starve the
-         * others, so poll with short sleeps instead */
+         * others and a pool of sleep-pollers is at the mercy of the scheduler (1-5 GB/s run to run), so the caller sleeps
+         * on its lane's futex word and the context's ONE completion thread wakes it (a blocking-sync event costs about a
+         * millisecond per wake-up here: not used) */
         if (!l.done) CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        *l.h_flag = 0;
+        CK(cudaMemcpyAsync((void *)l.h_flag, l.d_one, sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
         CK(cudaEventRecord(l.done, l.stream));
-        /* (a blocking-sync event costs about a millisecond per wake-up here; short sleeps between polls cost ~0.1 ms) */
-        const struct timespec nap = { 0, 30000 };
-        cudaError_t q;
-        while ((q = cudaEventQuery(l.done)) == cudaErrorNotReady) nanosleep(&nap, nullptr);
-        CK(q);
+        {
+            std::lock_guard<std::mutex> lk(ctx->waiter_mu);
+            if (!ctx->waiter_started) {
+                ctx->waiter = std::thread(waiter_main, ctx);
+                ctx->waiter_started = true;
+            }
+            l.wait_state.store(1, std::memory_order_release);
+            ctx->waiter_inflight.fetch_add(1);
+        }
+        ctx->waiter_cv.notify_one();
+        futex_wait_while(&l.wait_state, 1u);
+        l.wait_state.store(0, std::memory_order_relaxed);
+        CK(l.wait_result);
     } else {
         CK(cudaStreamSynchronize(l.stream));
     }
@@ -575,6 +625,37 @@ int compress_one_on_lane(b200bgzf_ctx *ctx, Lane &l, const void *src, uint32_t s
     else { memcpy(dst, h_out, n); *dlen = n; }
     if (status) *status = st;
     return st;
+}
+
+void waiter_main(b200bgzf_ctx *ctx)
+{
+    cudaSetDevice(ctx->device);
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(ctx->waiter_mu);
+            ctx->waiter_cv.wait(lk, [&] { return ctx->waiter_stop.load() || ctx->waiter_inflight.load() > 0; });
+            if (ctx->waiter_stop.load()) return;
+        }
+        /* the lanes' flags are plain pinned memory: polling them takes no driver lock away from the callers that are
+         * launching at the same time; the event is only asked now and then, to notice a failed stream */
+        unsigned spins = 0;
+        while (ctx->waiter_inflight.load(std::memory_order_acquire) > 0 && !ctx->waiter_stop.load(std::memory_order_relaxed)) {
+            const bool ask = (++spins & 0x3fffu) == 0;
+            for (auto &h : ctx->hook_lanes) {
+                if (h.wait_state.load(std::memory_order_acquire) != 1u) continue;
+                cudaError_t q = cudaSuccess;
+                if (!*h.h_flag) {
+                    if (!ask) continue;
+                    q = cudaEventQuery(h.done);
+                    if (q == cudaErrorNotReady) continue;
+                }
+                h.wait_result = q;
+                ctx->waiter_inflight.fetch_sub(1);
+                h.wait_state.store(2u, std::memory_order_release);
+                futex_wake_one(&h.wait_state);
+            }
+        }
+    }
 }
 
 }  // namespace

@@ -74,6 +74,8 @@
 #define BG_B_END 15968
 #define BG_B_SENTRY 16000     /* u32[32]   where the parse enters each super-chunk */
 #define BG_B_XTAB 16384       /* u16[31*258] super-chunk exit offset for every possible entry offset */
+#define BG_B_PERM 20480       /* u16[1024]   chunk order of the token passes (the walk tables are dead by then; IOFF ends at 20480) */
+#define BG_B_CLASSCNT 4448    /* u32[8*32]   chunks per (class, warp), then their exclusive scan (tree space: written between the walk list's last use and the tally) */
 
 /* scalars kept in the always-live misc area (u32 each) */
 enum {
@@ -126,6 +128,8 @@ struct BgCtx {
     uint32_t *cand;     /* global scratch u32[4*BG_MAX_BLOCK] or NULL: up to 4 matches per position (near-optimal class) */
     uint32_t *out;      /* global: this block's output slot, BG_SLOT_BYTES, 16-byte aligned */
     const uint32_t *crcpow; /* global u32[BG_THREADS]: x^(8*4*BG_CRC_WORDS*k) mod P */
+    const uint16_t *perm;   /* smem u16[BG_MAX_CHUNKS] or NULL: which chunk thread i walks in the token passes (tally, sizes, emit).
+                               Any permutation gives the same bytes; the kernel groups chunks of similar make-up into one warp. */
     uint32_t n;         /* payload bytes */
     BgParams prm;
 };
@@ -891,7 +895,9 @@ BG_HD void bg_phase_tally(const BgCtx &c, uint32_t t, uint32_t T)
     uint32_t *lfreq = (uint32_t *)(c.regb + BG_B_LFREQ);
     uint32_t *dfreq = (uint32_t *)(c.regb + BG_B_DFREQ);
     const uint16_t *entry = (const uint16_t *)(c.regb + BG_B_ENTRY);
-    for (uint32_t ch = t; ch * BG_CHUNK < n; ch += T) {
+    for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
+        const uint32_t ch = c.perm ? c.perm[i] : i;
+        if (ch * BG_CHUNK >= n) continue;
         uint32_t p = entry[ch];
         if (p == BG_NOPOS) continue;
         p += ch * BG_CHUNK;
@@ -1550,7 +1556,8 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
     const uint16_t *entry = (const uint16_t *)(rb + BG_B_ENTRY);
     uint32_t *cbits = (uint32_t *)(rb + BG_B_CBITS);
     const bool coded = c.scal[BG_S_BTYPE] != 0;
-    for (uint32_t ch = t; ch < BG_MAX_CHUNKS; ch += T) {
+    for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
+        const uint32_t ch = c.perm ? c.perm[i] : i;
         uint32_t bits = 0;
         uint32_t p = ch * BG_CHUNK < n ? entry[ch] : BG_NOPOS;
         if (coded && p != BG_NOPOS) {
@@ -1729,7 +1736,9 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
             bg_w_flush(w);
         }
     }
-    for (uint32_t ch = t; ch * BG_CHUNK < n; ch += T) {
+    for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
+        const uint32_t ch = c.perm ? c.perm[i] : i;
+        if (ch * BG_CHUNK >= n) continue;
         uint32_t p = entry[ch];
         if (p == BG_NOPOS) continue;
         p += ch * BG_CHUNK;

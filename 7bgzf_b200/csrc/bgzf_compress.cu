@@ -104,7 +104,7 @@ __device__ __forceinline__ unsigned hash_peers(uint32_t h, bool valid)
 __device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, uint32_t lane, uint32_t warp, uint32_t nwarps, uint32_t first,
                                                   uint32_t step, uint4 *xprev, volatile uint8_t *ready)
 {
-    const uint32_t n = c.n;
+    const uint32_t n = c.n, hb = c.scal[BG_S_HBYTES];
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t ntiles = (n + 511u) >> 9;
     for (uint32_t tile = first + step * warp; tile < ntiles; tile += step * nwarps) {
@@ -114,18 +114,21 @@ __device__ __forceinline__ void build_peers_phase(const BgCtx &c, uint4 *notes, 
             const uint32_t base = tile * 512u + g * 32u;
             if (base >= n) break;               /* uniform for the warp */
             const uint32_t p = base + lane;
-            const uint32_t h = p < n ? c.prev[p] : BG_NOPOS;
-            const bool valid = h != BG_NOPOS;
+            /* (the hash phase proper is folded in: a position's hash goes straight from the multiply into the ballots) */
+            const bool valid = p + hb <= n;
+            const uint32_t h = valid ? bg_hash(c.dataw, p, hb) : BG_NOPOS;
             const unsigned peers = hash_peers(h, valid);
+            uint32_t link = h;                                            /* a leader keeps its hash for the relay; no hash window: BG_NOPOS */
             if (valid) {
                 const unsigned lower = peers & lt;
                 if (lower) {
-                    c.prev[p] = (uint16_t)(base + (31u - (uint32_t)__clz(lower)));
+                    link = base + (31u - (uint32_t)__clz(lower));
                 } else {
                     const uint32_t note = 31u - (uint32_t)__clz(peers);   /* lane of the highest position with this hash */
                     w[g >> 2] = (w[g >> 2] & ~(0xffu << (8 * (g & 3)))) | (note << (8 * (g & 3)));
                 }
             }
+            if (p < n) c.prev[p] = (uint16_t)link;
         }
         notes[tile * 32u + lane] = make_uint4(w[0], w[1], w[2], w[3]);
         if (xprev) {
@@ -202,39 +205,58 @@ __device__ __forceinline__ void build_link_phase(const BgCtx &c, const uint4 *no
 /* ---- the search of the greedy / lazy classes (bgzf_block.h: "the search in three passes").  `own`/`parts`: CTA `own` of
  * a cluster of `parts` that shares ONE block keeps every parts-th group of 32 positions (the one-CTA kernel: 0, 1). ---- */
 
-/* pass 1: nearest-candidate match of every position; landing marks and eligibility bits with one ballot per 32 positions */
+/* a bit of the landing bitmap of CTA `owner` of this cluster (distributed shared memory: mapa + red.or) */
+__device__ __forceinline__ void mark_remote(uint32_t *local_word, uint32_t owner, uint32_t bits)
+{
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_word)), "r"(owner));
+    asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(raddr), "r"(bits) : "memory");
+}
+
+/* pass 1: nearest-candidate match of every position; landing marks and eligibility bits with one ballot per 32 positions.
+ * SPLIT: a cluster shares ONE block; CTA `own` of `parts` takes every parts-th group of 32 positions, and a landing
+ * mark goes to the bitmap of the CTA that owns the landing position's group (it alone reads that word afterwards). */
+template <bool SPLIT>
 __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
     const uint32_t n = c.n, lane = t & 31u;
     uint32_t *elig = (uint32_t *)(c.regb + BG_B_TODO), *mark = (uint32_t *)(c.regb + BG_B_MARK);
     if (c.scal[BG_S_DEPTH] <= 1) {                                  /* depth 1 (level 1): the nearest candidate is the whole search */
         for (uint32_t p = t; p < n; p += BG_THREADS) {
+            if (SPLIT && (p >> 5) % parts != own) continue;
             bool deep;
             uint32_t target;
-            const uint32_t r = bg_nearest(c, p, &deep, &target);
-            if ((p >> 5) % parts == own) c.R[p] = r;
+            c.R[p] = bg_nearest(c, p, &deep, &target);
         }
         return;
     }
-    if (t == 0) atomicOr(&mark[0], 1u);
+    if (t == 0 && own == 0) atomicOr(&mark[0], 1u);
     for (uint32_t p0 = t - lane; p0 < n; p0 += BG_THREADS) {       /* (warp-uniform trip count) */
+        const uint32_t word = p0 >> 5;
+        if (SPLIT && word % parts != own) continue;
         const uint32_t p = p0 + lane;
         bool deep = false;
         uint32_t target = p + 1, r = 0;
         if (p < n) {
             r = bg_nearest(c, p, &deep, &target);
-            if ((p0 >> 5) % parts == own) c.R[p] = r;
+            c.R[p] = r;
         }
         const bool lit = p < n && target == p + 1;
         const unsigned lm = __ballot_sync(0xffffffffu, lit), em = __ballot_sync(0xffffffffu, deep);
         const uint32_t before = __shfl_up_sync(0xffffffffu, target, 1);
         if (lane == 0) {
-            elig[p0 >> 5] = em;
-            if (lm << 1) atomicOr(&mark[p0 >> 5], lm << 1);
-            if (lm >> 31) atomicOr(&mark[(p0 >> 5) + 1], 1u);
+            elig[word] = em;
+            if (lm << 1) atomicOr(&mark[word], lm << 1);
+            if (lm >> 31) {
+                if (SPLIT) mark_remote(&mark[word + 1], (word + 1) % parts, 1u);
+                else atomicOr(&mark[word + 1], 1u);
+            }
         }
         /* consecutive positions inside one match land on the same position: one of them marks it */
-        if (p < n && !lit && (lane == 0 || before != target)) atomicOr(&mark[target >> 5], 1u << (target & 31u));
+        if (p < n && !lit && (lane == 0 || before != target)) {
+            if (SPLIT) mark_remote(&mark[target >> 5], (target >> 5) % parts, 1u << (target & 31u));
+            else atomicOr(&mark[target >> 5], 1u << (target & 31u));
+        }
     }
 }
 
@@ -442,6 +464,63 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
     }
 }
 
+/* ---- chunk order of the token passes.  A thread walks the tokens of one 68-byte chunk in tally, sizes and emit; a warp
+ * pays for its longest walk and for every kind of token its lanes meet.  Sequence stretches are literal runs (17 steps of
+ * four literals), quality stretches a handful of matches: chunks are therefore classed by how many of their positions
+ * carry a literal step code, and each warp gets chunks of one class (a stable 8-way partition: ballots per warp, one scan
+ * of the 8 x 32 counts).  Only the execution order changes; every chunk's bits are what they would be anyway. ---- */
+__device__ __forceinline__ uint32_t chunk_class(const BgCtx &c, uint32_t ch)
+{
+    if (ch * BG_CHUNK >= c.n) return 0u;
+    const uint32_t *sc = (const uint32_t *)(c.stepcode + ch * BG_CHUNK);
+    uint32_t zeros = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < BG_CHUNK / 4u; k++) {
+        const uint32_t v = sc[k];
+        /* bytes equal to zero: the classic (v - 0x01010101) & ~v & 0x80808080, exact enough for a classification */
+        zeros += __popc((v - 0x01010101u) & ~v & 0x80808080u);
+    }
+    return zeros >= 64u ? 7u : zeros >> 3;
+}
+
+__device__ __forceinline__ void chunk_order_count(const BgCtx &c, uint32_t t, uint32_t &cls, uint32_t &rank)
+{
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    uint32_t *cnt = (uint32_t *)(c.regb + BG_B_CLASSCNT);
+    cls = chunk_class(c, t);
+    rank = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8u; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+        if (cls == k) rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == k) cnt[k * 32u + warp] = __popc(m);
+    }
+}
+
+/* (warp 0) exclusive scan of the 256 counts, class-major: class k of warp w starts after all smaller classes and after class k of the warps before */
+__device__ __forceinline__ void chunk_order_scan(const BgCtx &c, uint32_t t)
+{
+    if (t >= 32u) return;
+    uint32_t *cnt = (uint32_t *)(c.regb + BG_B_CLASSCNT);
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8u; k++) { v[k] = cnt[t * 8u + k]; sum += v[k]; }
+    uint32_t inc = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (t >= (uint32_t)d) inc += y;
+    }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < 8u; k++) { cnt[t * 8u + k] = run; run += v[k]; }
+}
+
+__device__ __forceinline__ void chunk_order_place(const BgCtx &c, uint32_t t, uint32_t cls, uint32_t rank)
+{
+    const uint32_t *cnt = (const uint32_t *)(c.regb + BG_B_CLASSCNT);
+    ((uint16_t *)(c.regb + BG_B_PERM))[cnt[cls * 32u + (t >> 5)] + rank] = (uint16_t)t;
+}
+
 /* ---- 512-key bitonic sort in shared memory (ascending); all threads call it ---- */
 __device__ __forceinline__ void bitonic_sort_512(uint32_t *keys, uint32_t t)
 {
@@ -530,6 +609,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
     c.cand = SPLIT ? a.cand : (a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr);
     c.crcpow = a.crcpow;
     c.prm = a.prm;
+    c.perm = (const uint16_t *)(smem + SM_REGB + BG_B_PERM);
 
     if (t < 256) c.crctab[t] = a.crctab[t];
     if (t == 0) {
@@ -581,8 +661,6 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         bg_phase_settle(c, t, T);
         __syncthreads();
         PROF_MARK(1);
-        bg_phase_hash(c, t, T);
-        __syncthreads();
         PROF_MARK(2);
         uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build commands live behind the match scratch */
         if (SPLIT) {
@@ -610,9 +688,11 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
             else search_positions(c, t);
         } else {
             bg_phase_search_clear(c, t, T);
-            __syncthreads();
-            search_nearest(c, t, crank, csize);
-            __syncthreads();
+            if (SPLIT) cluster_sync();                           /* every CTA's bitmap is clear before anyone's marks arrive */
+            else __syncthreads();
+            search_nearest<SPLIT>(c, t, crank, csize);
+            if (SPLIT) cluster_sync();                           /* ... and complete before it is read */
+            else __syncthreads();
             PROF_MARK(21);
             if (c.scal[BG_S_DEPTH] > 1) {                        /* (uniform for the CTA) */
                 bg_phase_search_todo(c, t, T, crank, csize);
@@ -651,9 +731,14 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
             __syncthreads();
             PROF_MARK(17);
             bg_phase_walk_b(c, t, T);
+            uint32_t ccls, crnk;
+            chunk_order_count(c, t, ccls, crnk);             /* (the step codes are final; the counts go where the walk list was) */
             __syncthreads();
             PROF_MARK(18);
             bg_phase_walk_c(c, t, T);
+            chunk_order_scan(c, t);
+            __syncthreads();
+            chunk_order_place(c, t, ccls, crnk);
             __syncthreads();
             PROF_MARK(6);
             bg_phase_tally(c, t, T);

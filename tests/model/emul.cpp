@@ -69,6 +69,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     c.cand = e->cand.data();
     c.out = e->out.data();
     c.crcpow = e->crcpow.data();
+    c.perm = nullptr;
     c.n = n;
     c.prm = bg_level_params(level);
     uint32_t k = 0;

@@ -5,9 +5,13 @@
  * generator, not part of the codec.
  *
  *   library:  size_t b200gen_fill(int kind, uint64_t seed, uint8_t *dst, size_t nbytes)
- *             kind 0 = FASTQ-like, 1 = SAM-like; writes exactly nbytes (the stream is cut mid-record).
- *   cli:      datagen fastq|sam <bytes> <seed>   (stops after the first record reaching <bytes>,
+ *             kind 0 = FASTQ-like, 1 = SAM-like, 2 = BAM-like; writes exactly nbytes (the stream is cut mid-record).
+ *   cli:      datagen fastq|sam|bam <bytes> <seed>   (stops after the first record reaching <bytes>,
  *             like the survey probe, so the md5 sums in SURVEY.md Appendix B reproduce)
+ * BAM-like (BASELINE config 5: what htslib hands to bgzf_compress when samtools writes BAM): the SAM-like records in
+ * BAM's binary layout — u32 block size, 32-byte little-endian core, NUL-terminated name, one CIGAR word, 4-bit packed
+ * bases, raw Phred bytes, NM/AS/RG tags.  Not a valid BAM file (no header, no bin/index fields of any meaning); it has
+ * BAM's byte statistics.
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -70,6 +74,33 @@ static void make_read(gen_t *g, char *seq, char *qual, uint32_t pos)
 /* Emits records through sink() until it returns non-zero. */
 typedef int (*sink_fn)(void *ctx, const char *rec, size_t len);
 
+static void put32(unsigned char *p, uint32_t v) { p[0] = (unsigned char)v; p[1] = (unsigned char)(v >> 8); p[2] = (unsigned char)(v >> 16); p[3] = (unsigned char)(v >> 24); }
+static void put16(unsigned char *p, uint32_t v) { p[0] = (unsigned char)v; p[1] = (unsigned char)(v >> 8); }
+
+static int bam_record(char *rec, const char *name, int flag, uint32_t pos, int mapq, uint32_t pnext, int tlen, const char *seq, const char *qual,
+                      uint32_t nm, uint32_t as)
+{
+    unsigned char *o = (unsigned char *)rec + 4;
+    const uint32_t lname = (uint32_t)strlen(name) + 1;
+    put32(o, 0); put32(o + 4, pos); o[8] = (unsigned char)lname; o[9] = (unsigned char)mapq; put16(o + 10, 4681); put16(o + 12, 1);
+    put16(o + 14, (uint32_t)flag); put32(o + 16, READ_LEN); put32(o + 20, 0); put32(o + 24, pnext); put32(o + 28, (uint32_t)tlen);
+    o += 32;
+    memcpy(o, name, lname); o += lname;
+    put32(o, (uint32_t)READ_LEN << 4); o += 4;
+    for (int i = 0; i < READ_LEN; i += 2) {
+        int a = seq[i] == 'A' ? 1 : seq[i] == 'C' ? 2 : seq[i] == 'G' ? 4 : seq[i] == 'T' ? 8 : 15;
+        int b = i + 1 < READ_LEN ? (seq[i + 1] == 'A' ? 1 : seq[i + 1] == 'C' ? 2 : seq[i + 1] == 'G' ? 4 : seq[i + 1] == 'T' ? 8 : 15) : 0;
+        *o++ = (unsigned char)((a << 4) | b);
+    }
+    for (int i = 0; i < READ_LEN; i++) *o++ = (unsigned char)(qual[i] - 33);
+    memcpy(o, "NMC", 3); o[3] = (unsigned char)nm; o += 4;
+    memcpy(o, "ASC", 3); o[3] = (unsigned char)as; o += 4;
+    memcpy(o, "RGZgrp1", 8); o += 8;
+    const uint32_t n = (uint32_t)(o - (unsigned char *)rec);
+    put32((unsigned char *)rec, n - 4);
+    return (int)n;
+}
+
 static void generate(int sam, uint64_t seed, sink_fn sink, void *ctx)
 {
     gen_t g;
@@ -79,7 +110,7 @@ static void generate(int sam, uint64_t seed, sink_fn sink, void *ctx)
     uint64_t i = 0;
     uint32_t pos = 0;
     int stop = 0;
-    if (sam) {
+    if (sam == 1) {
         int n = snprintf(rec, sizeof rec,
                          "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chrSim\tLN:%u\n@PG\tID:b200sim\tPN:b200sim\n",
                          GENOME_LEN);
@@ -107,6 +138,11 @@ static void generate(int sam, uint64_t seed, sink_fn sink, void *ctx)
             if (flag == 147)
                 tlen = -tlen;
             uint32_t pnext = flag == 99 ? pos + tlen - READ_LEN : pos + tlen + READ_LEN;
+            if (sam == 2) {
+                char name[96];
+                snprintf(name, sizeof name, "B200SIM:7:HXXCCXY22:%u:%u:%u:%u", lane, tile, x, y);
+                n = bam_record(rec, name, flag, pos, mapq, pnext, tlen, seq, qual, (r >> 24) & 3, READ_LEN - ((r >> 24) & 3) * 5);
+            } else
             n = snprintf(rec, sizeof rec,
                          "B200SIM:7:HXXCCXY22:%u:%u:%u:%u\t%d\tchrSim\t%u\t%d\t%dM\t=\t%u\t%d\t%.*s\t%.*s\t"
                          "NM:i:%u\tMD:Z:%d\tAS:i:%u\tXS:i:%u\tRG:Z:grp%u\n",
@@ -138,7 +174,7 @@ size_t b200gen_fill(int kind, uint64_t seed, uint8_t *dst, size_t nbytes)
 {
     fill_ctx f = { dst, nbytes, 0 };
     if (nbytes)
-        generate(kind != 0, seed, fill_sink, &f);
+        generate(kind, seed, fill_sink, &f);
     return f.n;
 }
 
@@ -158,12 +194,12 @@ static int cli_sink(void *c, const char *rec, size_t len)
 int main(int argc, char **argv)
 {
     if (argc < 4) {
-        fprintf(stderr, "usage: %s fastq|sam <bytes> <seed>\n", argv[0]);
+        fprintf(stderr, "usage: %s fastq|sam|bam <bytes> <seed>\n", argv[0]);
         return 2;
     }
     cli_ctx c = { strtoull(argv[2], 0, 10), 0 };
     setvbuf(stdout, 0, _IOFBF, 1 << 22);
-    generate(!strcmp(argv[1], "sam"), strtoull(argv[3], 0, 10), cli_sink, &c);
+    generate(!strcmp(argv[1], "sam") ? 1 : !strcmp(argv[1], "bam") ? 2 : 0, strtoull(argv[3], 0, 10), cli_sink, &c);
     return 0;
 }
 #endif
