@@ -66,6 +66,47 @@ struct Lane {
     uint8_t *one_dev = nullptr, *one_host = nullptr;   /* one-block fast path: everything it needs in one device and one pinned slab */
 };
 
+/* ---- the hook's combiner: many synchronous one-block callers, ONE submitter --------------------------------------
+ * With more callers than host cores, every caller issuing its own copies and launch serialises on the driver's context
+ * lock (measured: 64 callers -> 1.2-1.5 ms per call, 3 GB/s).  Here a caller only copies its payload into its pinned
+ * slot, marks it ready and sleeps on the slot's futex word; the context's dispatcher thread gathers the ready slots into
+ * a batch — one kernel launch over all of them (the kernel reads the payloads straight from the pinned slots), one copy of
+ * the members back, one flag — and wakes each caller when its member is in host memory.  Four driver calls per BATCH. */
+constexpr int kCombSlots = 256;
+constexpr int kCombBatches = 8;
+constexpr int kCombBatchMax = 64;
+constexpr size_t kCombInStride = BG_SLOT_BYTES + 64;
+constexpr size_t kCombOutStride = BG_SLOT_BYTES + 64;   /* 16-byte header (member size) + the member */
+
+struct CombSlot {
+    std::atomic<uint32_t> state{0};     /* 0 free, 1 being filled, 2 ready, 3 in flight, 4 done (the caller sleeps while it is 2 or 3) */
+    uint32_t slen = 0, out_len = 0;
+    int level = 0, rc = 0;
+    int child[4] = { -1, -1, -1, -1 };   /* slots this caller wakes once it is awake itself (the wake-up fans out as a tree) */
+};
+struct CombBatch {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_slots = nullptr;
+    uint32_t *d_meta = nullptr, *h_meta = nullptr;      /* [0..M) member sizes, [M..2M) status, [2M] error flag, [2M+1] the constant 1 */
+    uint64_t *h_inoff = nullptr, *h_outoff = nullptr;   /* pinned, read by the kernels in place */
+    uint32_t *h_inlen = nullptr;
+    uint32_t *d_scratch = nullptr, *d_cand = nullptr;
+    volatile uint32_t *h_flag = nullptr;
+    int n = 0, slots[kCombBatchMax];
+    bool inflight = false;
+};
+struct Combiner {
+    bool up = false, failed = false;
+    uint8_t *h_in = nullptr, *h_out = nullptr;          /* pinned arenas: every caller slot's payload, and where its member comes back */
+    CombSlot slots[kCombSlots];
+    CombBatch batches[kCombBatches];
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<int> pending{0};                        /* slots in state 2 or 3 */
+    std::atomic<bool> stop{false}, sleeping{false};
+};
+
 }  // namespace
 
 struct b200bgzf_ctx {
@@ -94,6 +135,8 @@ struct b200bgzf_ctx {
     std::atomic<int> waiter_inflight{0};
     std::atomic<bool> waiter_stop{false};
     bool waiter_started = false;
+    Combiner comb;
+    std::atomic<int> one_block_callers{0};         /* threads inside a one-block call right now */
     std::atomic<unsigned long long> launches{0};   /* hook callers bump it concurrently */
     std::atomic<bool> no_clusters{false};          /* set when a cluster launch was refused once */
     char err[256] = { 0 };
@@ -115,6 +158,7 @@ void futex_wait_while(std::atomic<uint32_t> *word, uint32_t value)
 void futex_wake_one(std::atomic<uint32_t> *word) { syscall(SYS_futex, (uint32_t *)word, FUTEX_WAKE_PRIVATE, 1, nullptr, nullptr, 0); }
 
 void waiter_main(b200bgzf_ctx *ctx);
+void comb_stop(b200bgzf_ctx *ctx);
 
 int fail(b200bgzf_ctx *c, cudaError_t e, const char *where)
 {
@@ -338,6 +382,7 @@ extern "C" void b200bgzf_destroy(b200bgzf_ctx *ctx)
     }
     {
         DeviceGuard g(ctx->device);
+        comb_stop(ctx);
         cudaDeviceSynchronize();
         for (auto &l : ctx->lanes) lane_free(l);
         for (auto &l : ctx->hook_lanes) lane_free(l);
@@ -658,6 +703,245 @@ void waiter_main(b200bgzf_ctx *ctx)
     }
 }
 
+/* ---- combiner ---- */
+int comb_start(b200bgzf_ctx *ctx);
+
+void comb_fail_batch(b200bgzf_ctx *ctx, CombBatch &b, int rc)
+{
+    Combiner &cb = ctx->comb;
+    for (int k = 0; k < b.n; k++) {
+        CombSlot &sl = cb.slots[b.slots[k]];
+        sl.rc = rc;
+        sl.out_len = 0;
+        for (int j = 0; j < 4; j++) sl.child[j] = -1;
+        cb.pending.fetch_sub(1);
+        sl.state.store(4u, std::memory_order_release);
+        futex_wake_one(&sl.state);
+    }
+    b.n = 0;
+    b.inflight = false;
+}
+
+void comb_main(b200bgzf_ctx *ctx)
+{
+    Combiner &cb = ctx->comb;
+    cudaSetDevice(ctx->device);
+    uint64_t first_seen = 0;
+    unsigned spins = 0;
+    for (;;) {
+        if (cb.pending.load(std::memory_order_acquire) == 0) {
+            std::unique_lock<std::mutex> lk(cb.mu);
+            cb.sleeping.store(true);
+            cb.cv.wait(lk, [&] { return cb.stop.load() || cb.pending.load() > 0; });
+            cb.sleeping.store(false);
+        }
+        if (cb.stop.load()) return;
+        /* members that have arrived (the flags are plain pinned memory; the stream is only asked now and then, to notice a failure) */
+        const bool ask = (++spins & 0xffffu) == 0;
+        for (int bi = 0; bi < kCombBatches; bi++) {
+            CombBatch &b = cb.batches[bi];
+            if (!b.inflight) continue;
+            if (!*b.h_flag) {
+                if (ask) {
+                    const cudaError_t q = cudaStreamQuery(b.stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) {
+                        snprintf(ctx->err, sizeof ctx->err, "hook combiner: %s", cudaGetErrorString(q));
+                        comb_fail_batch(ctx, b, B200BGZF_E_CUDA);
+                    }
+                }
+                continue;
+            }
+            /* waking a sleeper is a system call of several microseconds: the dispatcher wakes four callers of the batch, each
+             * of them four more, and so on, instead of paying for all of them itself while new payloads wait */
+            for (int k = 0; k < b.n; k++) {
+                CombSlot &sl = cb.slots[b.slots[k]];
+                sl.rc = 0;
+                for (int j = 0; j < 4; j++) sl.child[j] = 4 * (k + 1) + j < b.n ? b.slots[4 * (k + 1) + j] : -1;
+            }
+            cb.pending.fetch_sub(b.n);
+            for (int k = 0; k < b.n; k++) cb.slots[b.slots[k]].state.store(4u, std::memory_order_release);
+            for (int k = 0; k < b.n && k < 4; k++) futex_wake_one(&cb.slots[b.slots[k]].state);
+            b.inflight = false;
+        }
+        /* ready payloads -> one batch */
+        CombBatch *nb = nullptr;
+        int busy = 0;
+        for (auto &b : cb.batches) {
+            if (b.inflight) busy++;
+            else if (!nb) nb = &b;
+        }
+        if (!nb) continue;
+        int n = 0, level = 0;
+        for (int i = 0; i < kCombSlots && n < kCombBatchMax; i++) {
+            CombSlot &sl = cb.slots[i];
+            if (sl.state.load(std::memory_order_acquire) != 2u) continue;
+            if (n == 0) level = sl.level;
+            else if (sl.level != level) continue;
+            nb->slots[n] = i;
+            nb->h_inoff[n] = (uint64_t)i * kCombInStride;
+            nb->h_outoff[n] = (uint64_t)i * kCombOutStride;
+            nb->h_inlen[n] = sl.slen;
+            n++;
+        }
+        if (n == 0) { first_seen = 0; continue; }
+        /* Fewer payloads than a batch is worth while other batches are still running: wait for the callers that are about to
+         * arrive (up to 120 us).  A batch costs this thread about 60 us of driver calls and wake-ups whatever its size; with
+         * payloads trickling in one by one it would otherwise spend all its time launching batches of two or three. */
+        const int want = std::min(32, std::max(1, ctx->one_block_callers.load(std::memory_order_relaxed) / 4));
+        if (n < want && busy > 0) {
+            struct timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            const uint64_t now = (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+            if (first_seen == 0) first_seen = now;
+            if (now - first_seen < 120000ull) continue;
+        }
+        first_seen = 0;
+        for (int k = 0; k < n; k++) cb.slots[nb->slots[k]].state.store(3u, std::memory_order_relaxed);
+        nb->n = n;
+        nb->inflight = true;
+        *nb->h_flag = 0;
+        BgzfCompressArgs a;
+        memset(&a, 0, sizeof a);
+        a.in = cb.h_in;
+        a.in_off = nb->h_inoff;
+        a.in_len = nb->h_inlen;
+        a.nblocks = (uint32_t)n;
+        a.prm = bg_level_params(level);
+        a.slots = nb->d_slots;
+        a.out_len = nb->d_meta;
+        a.status = nb->d_meta + kCombBatchMax;
+        a.err_flag = nb->d_meta + 2 * kCombBatchMax;
+        a.scratch = nb->d_scratch;
+        a.crctab = ctx->d_crctab;
+        a.crcpow = ctx->d_crcpow;
+        cudaError_t e = cudaSuccess;
+        if (a.prm.opt_passes > 0) {
+            if (!nb->d_cand) e = cudaMalloc((void **)&nb->d_cand, (size_t)kCombBatchMax * 4u * BG_MAX_BLOCK * sizeof(uint32_t));
+            a.cand = nb->d_cand;
+        }
+        /* (B200BGZF_COMB_SPLIT=1: let every block of a batch have a cluster of 2, 4 or 8 of the SMs the blocks in flight leave
+         * over.  Measured and left off: many clusters from several streams place badly — 64 callers fell from 5 to 1-2.6 GB/s,
+         * 16 callers from 490 to 707 us per call.) */
+        static const bool comb_split = [] { const char *e = getenv("B200BGZF_COMB_SPLIT"); return e && atoi(e) > 0; }();
+        int flying = n, split = 1;
+        bool small = false;
+        for (auto &b : cb.batches)
+            if (b.inflight && &b != nb) flying += b.n;
+        for (int k = 0; k < n; k++) small = small || nb->h_inlen[k] < 8192u;
+        if (comb_split && !small && !ctx->no_clusters.load(std::memory_order_relaxed)) split = flying <= 18 ? 8 : flying <= 37 ? 4 : flying <= 74 ? 2 : 1;
+        if (e == cudaSuccess && split > 1) {
+            e = bgzf_launch_compress_split(&a, split, nb->stream);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->no_clusters.store(true, std::memory_order_relaxed);
+                e = bgzf_launch_compress(&a, n, nb->stream);
+            }
+        } else if (e == cudaSuccess) {
+            e = bgzf_launch_compress(&a, n, nb->stream);
+        }
+        if (e == cudaSuccess) e = bgzf_launch_deliver(nb->d_slots, nb->d_meta, nb->h_outoff, cb.h_out, (uint32_t)n, nb->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((void *)nb->h_flag, nb->d_meta + 2 * kCombBatchMax + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, nb->stream);
+        ctx->launches += 2;
+        if (e != cudaSuccess) {
+            snprintf(ctx->err, sizeof ctx->err, "hook combiner: %s", cudaGetErrorString(e));
+            comb_fail_batch(ctx, *nb, B200BGZF_E_CUDA);
+        }
+    }
+}
+
+int comb_start(b200bgzf_ctx *ctx)
+{
+    Combiner &cb = ctx->comb;
+    std::lock_guard<std::mutex> lk(cb.mu);
+    if (cb.up) return 0;
+    if (cb.failed) return B200BGZF_E_CUDA;
+    cb.failed = true;                                   /* until everything below has worked */
+    CK(cudaMallocHost((void **)&cb.h_in, (size_t)kCombSlots * kCombInStride));
+    CK(cudaMallocHost((void **)&cb.h_out, (size_t)kCombSlots * kCombOutStride));
+    for (auto &b : cb.batches) {
+        CK(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+        CK(cudaMalloc((void **)&b.d_slots, (size_t)kCombBatchMax * BG_SLOT_BYTES + 64));
+        CK(cudaMalloc((void **)&b.d_meta, (2 * kCombBatchMax + 8) * sizeof(uint32_t)));
+        CK(cudaMallocHost((void **)&b.h_meta, (2 * kCombBatchMax + 8) * sizeof(uint32_t)));
+        CK(cudaMallocHost((void **)&b.h_inoff, 2 * kCombBatchMax * sizeof(uint64_t)));
+        b.h_outoff = b.h_inoff + kCombBatchMax;
+        CK(cudaMallocHost((void **)&b.h_inlen, kCombBatchMax * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&b.d_scratch, (size_t)kCombBatchMax * (BGZF_SCRATCH_WORDS + BGZF_SPLIT_EXTRA_WORDS) * sizeof(uint32_t)));
+        b.h_flag = b.h_meta + 2 * kCombBatchMax + 4;
+        const uint32_t one = 1;
+        CK(cudaMemcpy(b.d_meta + 2 * kCombBatchMax + 1, &one, sizeof one, cudaMemcpyHostToDevice));
+    }
+    cb.th = std::thread(comb_main, ctx);
+    cb.up = true;
+    cb.failed = false;
+    return 0;
+}
+
+void comb_stop(b200bgzf_ctx *ctx)
+{
+    Combiner &cb = ctx->comb;
+    if (cb.up) {
+        {
+            std::lock_guard<std::mutex> lk(cb.mu);
+            cb.stop.store(true);
+        }
+        cb.cv.notify_all();
+        cb.th.join();
+    }
+    if (cb.h_in) cudaFreeHost(cb.h_in);
+    if (cb.h_out) cudaFreeHost(cb.h_out);
+    for (auto &b : cb.batches) {
+        cudaFree(b.d_slots); cudaFree(b.d_meta); cudaFree(b.d_scratch); cudaFree(b.d_cand);
+        if (b.h_meta) cudaFreeHost(b.h_meta);
+        if (b.h_inoff) cudaFreeHost(b.h_inoff);
+        if (b.h_inlen) cudaFreeHost(b.h_inlen);
+        if (b.stream) cudaStreamDestroy(b.stream);
+    }
+}
+
+/* one payload through the combiner; returns 2 if it cannot take the call (no free slot, set-up failed): use a lane */
+int compress_one_combined(b200bgzf_ctx *ctx, const void *src, uint32_t slen, void *dst, size_t *dlen, int *status, int level)
+{
+    Combiner &cb = ctx->comb;
+    if (!cb.up && comb_start(ctx) != 0) return 2;
+    static thread_local int hint = -1;
+    int si = -1;
+    for (int k = 0; k < kCombSlots; k++) {
+        const int i = hint >= 0 ? (hint + k) % kCombSlots : (int)((std::hash<std::thread::id>()(std::this_thread::get_id()) + k) % kCombSlots);
+        uint32_t expect = 0;
+        if (cb.slots[i].state.compare_exchange_strong(expect, 1u, std::memory_order_acquire)) { si = i; break; }
+    }
+    if (si < 0) return 2;
+    hint = si;
+    CombSlot &sl = cb.slots[si];
+    memcpy(cb.h_in + (size_t)si * kCombInStride, src, slen);
+    sl.slen = slen;
+    sl.level = level;
+    cb.pending.fetch_add(1);
+    sl.state.store(2u, std::memory_order_release);
+    if (cb.sleeping.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(cb.mu);
+        cb.cv.notify_one();
+    }
+    for (;;) {
+        const uint32_t st = sl.state.load(std::memory_order_acquire);
+        if (st == 4u) break;
+        syscall(SYS_futex, (uint32_t *)&sl.state, FUTEX_WAIT_PRIVATE, st, nullptr, nullptr, 0);
+    }
+    for (int j = 0; j < 4; j++)
+        if (sl.child[j] >= 0) futex_wake_one(&cb.slots[sl.child[j]].state);
+    int rc = sl.rc;
+    if (rc == 0) {
+        const uint8_t *mine = cb.h_out + (size_t)si * kCombOutStride;
+        const uint32_t n = *(const volatile uint32_t *)mine;
+        if (n == 0 || n > *dlen) rc = B200BGZF_E_NOFIT;
+        else { memcpy(dst, mine + 16, n); *dlen = n; }
+    }
+    sl.state.store(0u, std::memory_order_release);
+    if (status) *status = rc > 0 ? rc : 0;
+    return rc;
+}
+
 }  // namespace
 
 extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *const *src, const uint32_t *slen, void *const *dst,
@@ -668,6 +952,16 @@ extern "C" int b200bgzf_compress_blocks_host(b200bgzf_ctx *ctx, const void *cons
         if (slen[b] > B200BGZF_MAX_BLOCK_SIZE || dlen[b] < 26) return B200BGZF_E_ARG;
     if (nblocks == 0) return 0;
     DeviceGuard g(ctx->device);
+    if (nblocks == 1) {
+        /* many concurrent one-block callers (htslib's pool with more threads than this host has cores): hand the payload to the
+         * combiner instead of driving the GPU from every caller (B200BGZF_HOOK_BATCH=0 / 1 forces the choice; for measurements) */
+        struct Count { std::atomic<int> &c; int now; explicit Count(std::atomic<int> &x) : c(x), now(x.fetch_add(1) + 1) {} ~Count() { c.fetch_sub(1); } } count(ctx->one_block_callers);
+        static const int forced_batch = [] { const char *e = getenv("B200BGZF_HOOK_BATCH"); return e && *e ? atoi(e) : -1; }();
+        if (forced_batch == 1 || (forced_batch < 0 && count.now > 36)) {
+            const int r = compress_one_combined(ctx, src[0], slen[0], dst[0], dlen, status, level);
+            if (r != 2) return r;
+        }
+    }
     if (nblocks <= kHookLaneBlocks) {
         /* small calls (the hook): grab any free one-block lane so concurrent callers run on different SMs */
         Lane *l = nullptr;

@@ -397,16 +397,22 @@ BG_HD uint32_t bg_match_len(const uint32_t *dw, uint32_t p, uint32_t q, uint32_t
 {
     if (l >= maxl) return maxl;
     const uint32_t sp = (p & 3u) * 8u, sq = (q & 3u) * 8u;
-    uint32_t ip = (p + l) >> 2, iq = (q + l) >> 2;
-    uint32_t plo = dw[ip], qlo = dw[iq];
+    const uint32_t *wp = dw + ((p + l) >> 2), *wq = dw + ((q + l) >> 2);
+    uint32_t plo = wp[0], qlo = wq[0];
+    /* eight bytes per turn: the four new words are requested together, so their shared-memory latencies overlap (the block is
+     * followed by 32 zero bytes: reading two words past the last compared byte stays inside the buffer) */
     for (;;) {
-        const uint32_t phi = dw[++ip], qhi = dw[++iq];
-        const uint32_t x = bg_funnel(plo, phi, sp) ^ bg_funnel(qlo, qhi, sq);
-        if (x) { l += (uint32_t)bg_ctz(x) >> 3; break; }
-        l += 4;
+        const uint32_t p1 = wp[1], q1 = wq[1], p2 = wp[2], q2 = wq[2];
+        const uint32_t x1 = bg_funnel(plo, p1, sp) ^ bg_funnel(qlo, q1, sq);
+        if (x1) { l += (uint32_t)bg_ctz(x1) >> 3; break; }
+        const uint32_t x2 = bg_funnel(p1, p2, sp) ^ bg_funnel(q1, q2, sq);
+        if (x2) { l += 4u + ((uint32_t)bg_ctz(x2) >> 3); break; }
+        l += 8;
         if (l >= maxl) break;
-        plo = phi;
-        qlo = qhi;
+        plo = p2;
+        qlo = q2;
+        wp += 2;
+        wq += 2;
     }
     return l > maxl ? maxl : l;
 }

@@ -213,6 +213,26 @@ __device__ __forceinline__ void mark_remote(uint32_t *local_word, uint32_t owner
     asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(raddr), "r"(bits) : "memory");
 }
 
+/* Landing marks for word `word` (32 positions).  One-CTA kernel: a shared-memory atomicOr.  Cluster: the bits go to the CTA
+ * that owns the word; its two highest bits also to the owner of the next word, which needs them for the positions the lazy
+ * rule looks at right after a landing (bg_phase_search_todo reads them from "the word before"). */
+template <bool SPLIT>
+__device__ __forceinline__ void mark_bits(uint32_t *mark, uint32_t word, uint32_t bits, uint32_t own, uint32_t parts)
+{
+    if (!SPLIT) {
+        atomicOr(&mark[word], bits);
+        return;
+    }
+    const uint32_t owner = word % parts;
+    if (owner == own) atomicOr(&mark[word], bits);
+    else mark_remote(&mark[word], owner, bits);
+    if (bits & 0xC0000000u) {
+        const uint32_t next = (word + 1u) % parts;
+        if (next == own) atomicOr(&mark[word], bits & 0xC0000000u);
+        else if (next != owner) mark_remote(&mark[word], next, bits & 0xC0000000u);
+    }
+}
+
 /* pass 1: nearest-candidate match of every position; landing marks and eligibility bits with one ballot per 32 positions.
  * SPLIT: a cluster shares ONE block; CTA `own` of `parts` takes every parts-th group of 32 positions, and a landing
  * mark goes to the bitmap of the CTA that owns the landing position's group (it alone reads that word afterwards). */
@@ -246,17 +266,11 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
         const uint32_t before = __shfl_up_sync(0xffffffffu, target, 1);
         if (lane == 0) {
             elig[word] = em;
-            if (lm << 1) atomicOr(&mark[word], lm << 1);
-            if (lm >> 31) {
-                if (SPLIT) mark_remote(&mark[word + 1], (word + 1) % parts, 1u);
-                else atomicOr(&mark[word + 1], 1u);
-            }
+            if (lm << 1) mark_bits<SPLIT>(mark, word, lm << 1, own, parts);
+            if (lm >> 31) mark_bits<SPLIT>(mark, word + 1, 1u, own, parts);
         }
         /* consecutive positions inside one match land on the same position: one of them marks it */
-        if (p < n && !lit && (lane == 0 || before != target)) {
-            if (SPLIT) mark_remote(&mark[target >> 5], (target >> 5) % parts, 1u << (target & 31u));
-            else atomicOr(&mark[target >> 5], 1u << (target & 31u));
-        }
+        if (p < n && !lit && (lane == 0 || before != target)) mark_bits<SPLIT>(mark, target >> 5, 1u << (target & 31u), own, parts);
     }
 }
 
@@ -311,6 +325,19 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
                 drain_queue(c, queue, cnt, 32u, lane);
             } while (cnt >= 32u);
             __syncwarp();
+            /* some of this position's candidates may have been measured by now: test the rest of the chain against the longer
+             * match.  (Whenever this happens, the final word is the same: a candidate is only ever dropped for not being
+             * longer than a nearer one that has already been measured.) */
+            if (live) {
+                const uint32_t r = __ldcg(c.R + p);
+                if ((r >> 16) > b1) {
+                    b1 = r >> 16;
+                    uint32_t maxl = c.n - p;
+                    if (maxl > 258u) maxl = 258u;
+                    if (b1 >= maxl) live = false;
+                    else tail = bg_ld32(c.dataw, p + b1 - 3u);
+                }
+            }
         }
     }
 }
@@ -605,8 +632,10 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
     c.litflag = smem + SM_LITFLAG;
     c.scal = (uint32_t *)(smem + SM_SCAL);
     const uint32_t crank = SPLIT ? cluster_rank() : 0u, csize = SPLIT ? cluster_size() : 1u;
-    c.R = SPLIT ? a.scratch : a.scratch + (size_t)blockIdx.x * BGZF_SCRATCH_WORDS;
-    c.cand = SPLIT ? a.cand : (a.cand ? a.cand + (size_t)blockIdx.x * (4u * BG_MAX_BLOCK) : nullptr);
+    const uint32_t unit = SPLIT ? blockIdx.x / csize : blockIdx.x;       /* SPLIT: cluster k of the grid takes block k */
+    uint32_t *const unit_scratch = a.scratch + (size_t)unit * (SPLIT ? BGZF_SCRATCH_WORDS + BGZF_SPLIT_EXTRA_WORDS : BGZF_SCRATCH_WORDS);
+    c.R = unit_scratch;
+    c.cand = a.cand ? a.cand + (size_t)unit * (4u * BG_MAX_BLOCK) : nullptr;
     c.crcpow = a.crcpow;
     c.prm = a.prm;
     c.perm = (const uint16_t *)(smem + SM_REGB + BG_B_PERM);
@@ -619,7 +648,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
     __syncthreads();
     uint32_t parity = 0;
 
-    for (uint32_t b = SPLIT ? 0u : blockIdx.x; b < a.nblocks; b += SPLIT ? a.nblocks : gridDim.x) {
+    for (uint32_t b = unit; b < a.nblocks; b += SPLIT ? a.nblocks : gridDim.x) {
         const uint8_t *src;
         uint32_t n;
         if (a.in_off) {
@@ -665,7 +694,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         uint4 *hi = (uint4 *)(c.R + BG_MAX_BLOCK + 32);       /* build commands live behind the match scratch */
         if (SPLIT) {
             /* every CTA has the same hashes; each finds the peers of its share of the tiles, the links travel through L2 */
-            uint4 *xprev = (uint4 *)(a.scratch + BGZF_SCRATCH_WORDS);
+            uint4 *xprev = (uint4 *)(unit_scratch + BGZF_SCRATCH_WORDS);
             build_peers_phase(c, hi, t & 31u, t >> 5, BG_THREADS / 32u, crank, csize, xprev, nullptr);
             cluster_sync();
             import_peer_tiles(c, xprev, t, crank, csize);
@@ -878,6 +907,28 @@ bgzf_gather_kernel(const uint8_t *slots, const uint32_t *len, const uint64_t *of
     if (t < n - done) dst[done + t] = ((const uint8_t *)src)[done + t];
 }
 
+/* ---- the hook combiner's way back: member b of a batch goes from its device slot to the caller's own pinned host buffer
+ * (16-byte header: the member size, 0 = did not fit; then the member).  Zero-copy stores over PCIe, 16 bytes per thread:
+ * only the member's bytes travel, and no copy call is needed per member. ---- */
+__global__ void __launch_bounds__(256)
+bgzf_deliver_kernel(const uint8_t *slots, const uint32_t *len, const uint64_t *out_off, uint8_t *host_out, uint32_t n)
+{
+    const uint32_t b = blockIdx.x, t = threadIdx.x;
+    if (b >= n) return;
+    const uint32_t nbytes = len[b];
+    const uint4 *src = (const uint4 *)(slots + (size_t)b * BG_SLOT_BYTES);
+    uint4 *dst = (uint4 *)(host_out + out_off[b]);
+    for (uint32_t i = t; i < (nbytes + 15u) / 16u; i += blockDim.x) dst[1u + i] = src[i];
+    if (t == 0) dst[0] = make_uint4(nbytes, 0u, 0u, 0u);
+}
+
+extern "C" cudaError_t bgzf_launch_deliver(const uint8_t *slots, const uint32_t *len, const uint64_t *out_off, uint8_t *host_out, uint32_t n,
+                                           cudaStream_t stream)
+{
+    bgzf_deliver_kernel<<<n, 256, 0, stream>>>(slots, len, out_off, host_out, n);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid, cudaStream_t stream)
 {
     /* (per device, once: the hook launches this kernel from many threads at a high rate) */
@@ -893,8 +944,8 @@ extern "C" cudaError_t bgzf_launch_compress(const BgzfCompressArgs *a, int grid,
     return cudaGetLastError();
 }
 
-/* one block (a->nblocks == 1) on a cluster of `csize` CTAs; a->scratch holds BGZF_SCRATCH_WORDS +
- * BGZF_SPLIT_EXTRA_WORDS words */
+/* a->nblocks blocks, each on its own cluster of `csize` CTAs; a->scratch holds BGZF_SCRATCH_WORDS +
+ * BGZF_SPLIT_EXTRA_WORDS words per block (a->cand, if any, 4 * 65536 words per block) */
 extern "C" cudaError_t bgzf_launch_compress_split(const BgzfCompressArgs *a, int csize, cudaStream_t stream)
 {
     static std::atomic<unsigned long long> configured{0};
@@ -907,7 +958,7 @@ extern "C" cudaError_t bgzf_launch_compress_split(const BgzfCompressArgs *a, int
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)csize);
+    cfg.gridDim = dim3((unsigned)csize * a->nblocks);
     cfg.blockDim = dim3(BG_THREADS);
     cfg.dynamicSmemBytes = SM_TOTAL;
     cfg.stream = stream;

@@ -72,6 +72,8 @@ cudaError_t bgzf_launch_scan(const uint32_t *len, uint64_t *off, uint32_t nmax, 
                              const uint64_t *base_dev, uint64_t *total_out, cudaStream_t stream);
 cudaError_t bgzf_launch_compact(const uint8_t *slots, const uint32_t *len, uint64_t *off, uint32_t nblocks, uint8_t *out,
                                 uint64_t *total, int append_eof, cudaStream_t stream);
+cudaError_t bgzf_launch_deliver(const uint8_t *slots, const uint32_t *len, const uint64_t *out_off, uint8_t *host_out, uint32_t n,
+                                cudaStream_t stream);
 size_t bgzf_index_tiles(uint64_t in_bytes);
 #define BGZF_INDEX_LAUNCHES 8
 cudaError_t bgzf_launch_index(const uint8_t *in, uint64_t in_bytes, const BgzfIndexWork *w, cudaStream_t stream);

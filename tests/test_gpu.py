@@ -415,6 +415,15 @@ def test_hook_from_many_threads(codec, tmp_path):
         tail = [l for l in r.stderr.decode().splitlines() if l.startswith("RC ")][-1].split()[1:]
         assert tail == ["1", "30", "-1", "0", "28"]           # does-not-fit -> 1 (*dlen untouched); cap < 26 -> -1; slen 0 -> EOF block
         assert "libdeflate_deflate 1" in r.stderr.decode()     # the reference's stderr line for the does-not-fit case
+    # the combiner path (what >36 concurrent callers get: payloads pooled into batches by one dispatcher thread): same bytes, same codes
+    for method, level in (("libdeflate6", 6), ("libdeflate10", 10)):
+        env = dict(os.environ, BGZF_METHOD=method, B200BGZF_HOOK_BATCH="1")
+        r = subprocess.run(["python", "-c", HOOK_DRIVER, b200bgzf.HOOK_PATH, os.path.join(H.ROOT, "tests"), os.path.join(H.ROOT, "7bgzf_b200")],
+                           capture_output=True, env=env)
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout + H.EOF_BLOCK == codec.compress(data, level)
+        tail = [l for l in r.stderr.decode().splitlines() if l.startswith("RC ")][-1].split()[1:]
+        assert tail == ["1", "30", "-1", "0", "28"]
     env = dict(os.environ, BGZF_METHOD="libdeflate13")
     r = subprocess.run(["python", "-c", HOOK_DRIVER, b200bgzf.HOOK_PATH, os.path.join(H.ROOT, "tests"), os.path.join(H.ROOT, "7bgzf_b200")],
                        capture_output=True, env=env)
