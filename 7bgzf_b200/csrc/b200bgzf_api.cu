@@ -260,8 +260,12 @@ int lane_reserve(b200bgzf_ctx *ctx, Lane &l, uint32_t blocks, size_t in_bytes, s
 /* one batch: compress kernel into slots, then scan + gather into `d_out` continuing at *d_total */
 int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint64_t in_bytes, uint32_t block_size,
                           const uint64_t *d_inoff, const uint32_t *d_inlen, uint32_t nblocks, int level, uint8_t *d_out,
-                          int append_eof, cudaStream_t stream)
+                          int append_eof, cudaStream_t stream, bool fused = false)
 {
+    /* fused: the compress kernel's last CTA compacts the batch itself (l.d_total[2] is its arrival counter, zeroed with
+     * l.d_total by the caller).  The pipelined host path uses it: a separate scan + gather launch per 32 MiB batch has to
+     * find free SMs among the resident 1024-thread compress CTAs of the neighbouring batches, and every SM it touches
+     * keeps a compress CTA waiting (measured: 41.3 -> 36.8 ms per GiB end to end without those launches). */
     if (nblocks) {
         BgzfCompressArgs a;
         memset(&a, 0, sizeof a);
@@ -284,12 +288,20 @@ int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint6
         a.crcpow = ctx->d_crcpow;
         a.err_flag = (uint32_t *)(l.d_total + 1);
         a.prof = ctx->prof_on ? ctx->d_prof : nullptr;
+        if (fused) {
+            a.gather_out = d_out;
+            a.gather_off = l.d_off;
+            a.gather_total = l.d_total;
+            a.done_count = (uint32_t *)(l.d_total + 2);
+        }
         const int grid = (int)std::min<uint32_t>(nblocks, (uint32_t)l.scratch_ctas);
         CK(bgzf_launch_compress(&a, grid, stream));
         ctx->launches += 1;
     }
-    CK(bgzf_launch_compact(l.d_slots, l.d_len, l.d_off, nblocks, d_out, l.d_total, append_eof, stream));
-    ctx->launches += 2;
+    if (!fused || nblocks == 0) {
+        CK(bgzf_launch_compact(l.d_slots, l.d_len, l.d_off, nblocks, d_out, l.d_total, append_eof, stream));
+        ctx->launches += 2;
+    }
     return 0;
 }
 
@@ -457,9 +469,12 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     /* batches rotate through the lanes (H2D, kernels, D2H on the lane's stream).  Measured: 400-512 blocks per batch is
      * best; multiples of the SM count are 5 % WORSE — when every CTA of a launch finishes at the same moment nothing of the
      * next launch overlaps with the hand-over, while uneven block counts let its CTAs trickle in */
-    const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), kHostBatchBlocks);
+    static const uint32_t host_batch = [] { const char *e = getenv("B200BGZF_HOST_BATCH"); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : kHostBatchBlocks; }();
+    static const uint32_t first_batch = [] { const char *e = getenv("B200BGZF_FIRST_BATCH"); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : 0u; }();
+    const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), host_batch);
     const size_t batch_in = (size_t)batch * block_size, batch_out = b200bgzf_compress_bound(batch_in, block_size);
-    uint32_t cur = batch;
+    static const int nlanes = [] { const char *e = getenv("B200BGZF_LANES"); return e && atoi(e) > 0 ? std::min(atoi(e), kLanes) : kLanes; }();
+    uint32_t cur = first_batch ? std::min(first_batch, batch) : batch;
     size_t host_off = 0;
     bool nofit = false;
     int r;
@@ -476,7 +491,7 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     };
     uint64_t done = 0, i = 0;
     while (done < nb_total) {
-        Lane &l = ctx->lanes[i % kLanes];
+        Lane &l = ctx->lanes[i % nlanes];
         if (l.pending && (r = complete(l))) return r;
         if ((r = lane_reserve(ctx, l, batch, batch_in, batch_out))) return r;
         const uint32_t nb = (uint32_t)std::min<uint64_t>(cur, nb_total - done);
@@ -485,7 +500,7 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
         const size_t bytes = (size_t)std::min<uint64_t>((uint64_t)nb * block_size, in_bytes - off);
         CK(cudaMemcpyAsync(l.d_in, (const uint8_t *)in + off, bytes, cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
-        if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream))) return r;
+        if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true))) return r;
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
         if (member_off) {
             CK(grow(&l.h_meta, &l.meta_cap, (size_t)batch, true));
@@ -498,8 +513,8 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
         i++;
     }
     /* drain in submission order */
-    for (uint64_t k = 0; k < (uint64_t)kLanes; k++) {
-        Lane &l = ctx->lanes[(i + k) % kLanes];
+    for (uint64_t k = 0; k < (uint64_t)nlanes; k++) {
+        Lane &l = ctx->lanes[(i + k) % nlanes];
         if (l.pending && (r = complete(l))) return r;
     }
     for (auto &l : ctx->lanes)

@@ -593,6 +593,46 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t *v, uint3
     return total;
 }
 
+/* one member, slot -> its place in the stream, by `nthr` threads (thread `t` of them); the destination may start at any byte */
+__device__ __forceinline__ void gather_member(const uint32_t *src, uint32_t n, uint8_t *dst, uint32_t t, uint32_t nthr)
+{
+    const uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);   /* bytes until dst is word aligned */
+    if (n <= head + 4) {
+        for (uint32_t i = t; i < n; i += nthr) dst[i] = (uint8_t)(__ldcg(src + (i >> 2)) >> (8u * (i & 3u)));
+        return;
+    }
+    if (t < head) dst[t] = (uint8_t)(__ldcg(src) >> (8u * t));
+    const uint32_t words = (n - head) >> 2;
+    uint32_t *dw = (uint32_t *)(dst + head);
+    const uint32_t sh = head * 8u;
+    for (uint32_t i = t; i < words; i += nthr)
+        dw[i] = __funnelshift_r(__ldcg(src + i), __ldcg(src + i + 1), sh);   /* src word i+1 stays inside the 64 KiB slot + pad */
+    const uint32_t done = head + words * 4u;
+    if (t < n - done) dst[done + t] = (uint8_t)(__ldcg(src + ((done + t) >> 2)) >> (8u * ((done + t) & 3u)));
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t *v, uint32_t *scratch, uint32_t t);
+
+/* the last CTA of a launch: member sizes -> offsets (tiles of 1024, running carry), then every member to its place */
+__device__ __forceinline__ void fused_compaction(const BgzfCompressArgs &a, uint32_t *v, uint32_t *scratch, uint32_t t)
+{
+    uint64_t carry = *a.gather_total;
+    for (uint32_t start = 0; start < a.nblocks; start += 1024u) {
+        const uint32_t i = start + t;
+        v[t] = i < a.nblocks ? __ldcg(a.out_len + i) : 0u;
+        __syncthreads();
+        const uint32_t total = block_exclusive_scan_1024(v, scratch, t);
+        if (i < a.nblocks) a.gather_off[i] = carry + v[t];
+        carry += total;
+        __syncthreads();
+    }
+    if (t == 0) *a.gather_total = carry;
+    __syncthreads();
+    const uint32_t grp = t >> 8, gt = t & 255u;
+    for (uint32_t b = grp; b < a.nblocks; b += BG_THREADS / 256u)
+        gather_member((const uint32_t *)(a.slots + (size_t)b * BG_SLOT_BYTES), __ldcg(a.out_len + b), a.gather_out + a.gather_off[b], gt, 256u);
+}
+
 #define PROF_MARK(i)                                                        \
     do {                                                                    \
         if (prof && t == 0) {                                               \
@@ -834,6 +874,17 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         fence_proxy_async();   /* our generic-proxy accesses to the payload area precede the next TMA write */
         __syncthreads();       /* everyone is done with the payload and the tables before the next block lands */
         PROF_MARK(9);
+    }
+    if (!SPLIT && a.gather_out) {
+        /* whoever finishes last compacts the batch (threadFenceReduction pattern: every CTA's members are out before it counts itself) */
+        __threadfence();
+        __syncthreads();
+        if (t == 0) scan_scratch[35] = atomicAdd(a.done_count, 1u) == gridDim.x - 1u ? 1u : 0u;
+        __syncthreads();
+        if (scan_scratch[35]) {
+            __threadfence();
+            fused_compaction(a, (uint32_t *)(smem + SM_REGB), scan_scratch, t);
+        }
     }
 }
 

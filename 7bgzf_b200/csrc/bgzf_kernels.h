@@ -28,6 +28,12 @@ struct BgzfCompressArgs {
     const uint32_t *crctab;    /* device u32[256] */
     const uint32_t *crcpow;    /* device u32[1024] */
     unsigned long long *prof;  /* device u64[BGZF_PROF_SLOTS] cycle counters, or NULL */
+    /* fused compaction (host-buffer batches): the last CTA to finish scans the member sizes and gathers the slots into one
+     * stream itself, so that no small kernel has to find room among the resident compress CTAs */
+    uint8_t *gather_out;       /* device: the batch's contiguous stream, or NULL (compaction by bgzf_launch_compact) */
+    uint64_t *gather_off;      /* device u64[nblocks]: out: where every member starts in gather_out */
+    uint64_t *gather_total;    /* device: in: bytes already in gather_out; out: bytes after this batch */
+    uint32_t *done_count;      /* device: zero before the launch */
 };
 
 struct BgzfInflateArgs {
