@@ -97,13 +97,15 @@ struct BgParams {
 /* level 1..12 -> search effort; the classes follow libdeflate_alloc_compressor_ex (deflate_compress.c:3921-4007):
  * 1-4 greedy, 5-7 lazy, 8-9 lazy2, 10-12 near-optimal (lazy2 first, then min-cost-path passes over up to four
  * matches per position, the role of deflate_compress_near_optimal :3593-3850 / deflate_find_min_cost_path :3328-3400).  The numbers are this codec's own: on low-entropy text (FASTQ/SAM) an 8-byte
- * hash with a shallow chain reaches the reference's level-6 size (+1 %) at a fraction of the candidate visits. */
+ * hash with a shallow chain reaches the reference's level-6 size (+1 %) at a fraction of the candidate visits.  Levels 8 and 9
+ * walk 32 and 64 chain nodes (the reference: 300 and 600): +1.3 ... +2.0 % of the reference's size on FASTQ / SAM / BAM-like
+ * data at the same level, for twice the throughput of the 64 / 128 this codec used before (+0.6 ... +1.2 %). */
 BG_HD BgParams bg_level_params(int level)
 {
     BgParams p;
     if (level < 1) level = 1;
     if (level > 12) level = 12;
-    p.depth = level <= 4 ? level : level == 5 ? 6 : level == 6 ? 8 : level == 7 ? 16 : level == 8 ? 64 : level == 9 ? 128
+    p.depth = level <= 4 ? level : level == 5 ? 6 : level == 6 ? 8 : level == 7 ? 16 : level == 8 ? 32 : level == 9 ? 64
             : level == 10 ? 128 : level == 11 ? 256 : 512;
     p.nice = level <= 2 ? 32 : level == 3 ? 48 : level <= 5 ? 64 : level == 6 ? 65 : level == 7 ? 130 : 258;
     p.lazy = level <= 4 ? 0 : level <= 7 ? 1 : 2;
@@ -430,42 +432,6 @@ BG_HD bool bg_in_window(uint32_t p, uint32_t q) { return p - q - 1u < 32768u; }
  * ranges with match remainders were both built and measured this round; in lock-step they cost more than these
  * nested loops save: DESIGN.md section 3, branch exp/range-parse.) */
 
-/* near-optimal class: like the exact search, but remembers the last four improvements.  Because the chain runs
- * from the nearest candidate outwards, lengths and offsets both grow along that list: for any length the
- * cheapest offset is the entry with the smallest length that still covers it (what bt_matchfinder_get_matches
- * hands to the reference's optimiser, bt_matchfinder.h:140-340, capped at four entries). */
-BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
-{
-    const uint32_t n = c.n;
-    uint32_t m1 = 0, m2 = 0, m3 = 0, cur = 0;
-    uint32_t maxl = n - p;
-    if (maxl > 258) maxl = 258;
-    uint32_t q = maxl >= (uint32_t)BG_MIN_LOOKUP ? (uint32_t)c.prev[p] : (uint32_t)BG_NOPOS;
-    if (bg_in_window(p, q)) {
-        const uint32_t *dw = c.dataw;
-        uint32_t best = 3, ptail = bg_ld32(dw, p);
-        int depth = (int)c.scal[BG_S_DEPTH];
-        for (;;) {
-            if (bg_ld32(dw, q + best - 3) == ptail) {
-                const uint32_t l = bg_match_len(dw, p, q, best > 3 ? 0 : 4, maxl);
-                if (l > best) {
-                    best = l;
-                    m3 = m2; m2 = m1; m1 = cur;
-                    cur = (l << 16) | (p - q);
-                    if (l == maxl) break;
-                    ptail = bg_ld32(dw, p + best - 3);
-                }
-            }
-            if (--depth <= 0) break;
-            q = c.prev[q];
-            if (!bg_in_window(p, q)) break;
-        }
-    }
-    uint32_t *cd = c.cand + 4u * p;
-    cd[0] = cur; cd[1] = m1; cd[2] = m2; cd[3] = m3;          /* (candidates keep the plain len << 16 | offset form) */
-    return cur ? bg_mw(cur >> 16, cur & 0xffffu) : 0u;
-}
-
 /* ---- greedy / lazy classes (levels 1-9): the search in three passes ---------------------------------------------
  * The reference searches only where its parse stands (13-23 % of the positions at level 6); an
  * all-position search pays the full chain walk and the long extensions inside every match as well.  Here:
@@ -484,10 +450,11 @@ BG_HD uint32_t bg_search_one_multi(const BgCtx &c, uint32_t p)
  * Region B during the search (the hash heads are dead): */
 #define BG_B_TODO 0u          /* u32[2048]  pass 1: eligible bits; then the todo bits */
 #define BG_B_MARK 8192u       /* u32[2064]  landing positions of the greedy steps (dead once the todo bits are made) */
-#define BG_B_QUEUE 8192u      /* u32[32][160]  per warp: (p << 16 | q) candidates waiting for their extension */
-#define BG_B_GATHER 28672u    /* u16[32][64]   per warp: todo positions waiting for a full batch */
-#define BG_QUEUE_WORDS 160u
-#define BG_SCAN_CHUNK 4u      /* chain steps between two looks at the queue: 31 + 32 * 4 entries fit */
+#define BG_B_QUEUE 8192u      /* u32[32][96]   per warp: (p << 16 | q) candidates waiting for their extension */
+#define BG_B_RINGR 20480u     /* u32[32][64]   per warp: the nearest-match words of the todo positions in the ring (fetched ahead, cp.async) */
+#define BG_B_RING 28672u      /* u16[32][64]   per warp: ring of todo positions waiting for a free lane */
+#define BG_QUEUE_WORDS 96u
+#define BG_SCAN_CHUNK 2u      /* chain steps between two looks at the queue and at the lanes that ran out: 31 + 32 * 2 entries fit */
 
 BG_HD bool bg_match_ok(uint32_t r, uint32_t minlen);
 
@@ -512,6 +479,23 @@ BG_HD uint32_t bg_nearest(const BgCtx &c, uint32_t p, bool *deep, uint32_t *targ
     return r;
 }
 
+/* ---- near-optimal class (levels 10-12): the same passes, over EVERY position that has a second candidate, and besides the
+ * longest match (R[p], which seeds the first parse) the longest match of each of four offset ranges is kept (cand[4p + bin]:
+ * match words merged with atomicMax like R[p]) — the candidates the min-cost-path passes choose from.  For a length l the
+ * cheapest offset is that of the nearest range holding a match of at least l bytes; a longer, nearer match makes a farther,
+ * shorter one irrelevant, so it does not matter whether such a dominated candidate was measured at all (the kernel stops
+ * testing against the nearest match once longer ones are known: same decisions, fewer extensions).  This is the role of
+ * bt_matchfinder_get_matches (bt_matchfinder.h:140-340: all matches of strictly increasing length and offset), capped at
+ * one match per range. */
+BG_HD uint32_t bg_off_bin(uint32_t off) { return off <= 32u ? 0u : off <= 512u ? 1u : off <= 8192u ? 2u : 3u; }
+
+BG_HD void bg_cand_init(const BgCtx &c, uint32_t p, uint32_t r)
+{
+    uint32_t *cd = c.cand + 4u * p;
+    const uint32_t k = r ? bg_off_bin(bg_mw_off(r)) : 4u;
+    cd[0] = k == 0 ? r : 0u; cd[1] = k == 1 ? r : 0u; cd[2] = k == 2 ? r : 0u; cd[3] = k == 3 ? r : 0u;
+}
+
 BG_HD void bg_phase_search_clear(const BgCtx &c, uint32_t t, uint32_t T)
 {
     uint32_t *w = (uint32_t *)(c.regb + BG_B_TODO);
@@ -527,6 +511,7 @@ BG_HD void bg_phase_search1(const BgCtx &c, uint32_t t, uint32_t T)
         bool deep;
         uint32_t target;
         c.R[p] = bg_nearest(c, p, &deep, &target);
+        if (c.prm.opt_passes > 0) bg_cand_init(c, p, c.R[p]);
         if (deep) bg_or32(&elig[p >> 5], 1u << (p & 31u));
         bg_or32(&mark[target >> 5], 1u << (target & 31u));
     }
@@ -543,6 +528,7 @@ BG_HD void bg_phase_search_todo(const BgCtx &c, uint32_t t, uint32_t T, uint32_t
         uint32_t w = m;
         if (c.prm.lazy >= 1) w |= (m << 1) | (pm >> 31);
         if (c.prm.lazy >= 2) w |= (m << 2) | (pm >> 30);
+        if (c.prm.opt_passes > 0) w = 0xffffffffu;                  /* near-optimal class: the optimiser may stand anywhere */
         w &= todo[i];
         if (i % parts != own) w = 0;
         todo[i] = w;
@@ -579,17 +565,13 @@ BG_HD void bg_phase_search2(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t *todo = (const uint32_t *)(c.regb + BG_B_TODO);
     for (uint32_t p = t; p < c.n; p += T) {
         if (!((todo[p >> 5] >> (p & 31u)) & 1u)) continue;
-#define BG_PUSH_SEQ(q) do { const uint32_t v_ = bg_deep_extend(c, p, (q)); if (v_ > c.R[p]) c.R[p] = v_; } while (0)
+#define BG_PUSH_SEQ(q) do { const uint32_t v_ = bg_deep_extend(c, p, (q)); if (v_ > c.R[p]) c.R[p] = v_; \
+                            if (v_ && c.prm.opt_passes > 0) { uint32_t *cd_ = c.cand + 4u * p + bg_off_bin(bg_mw_off(v_)); if (v_ > *cd_) *cd_ = v_; } } while (0)
         /* (the tail bytes compared are those of the NEAREST match for every candidate: R[p] is read once, before the walk) */
         BG_DEEP_SCAN(c, p, BG_PUSH_SEQ);
     }
 }
 
-BG_HD void bg_phase_search(const BgCtx &c, uint32_t t, uint32_t T)
-{
-    for (uint32_t p = t; p < c.n; p += T)
-        c.R[p] = bg_search_one_multi(c, p);
-}
 
 /* ---- near-optimal class: minimum-cost path ------------------------------------------------------------------ */
 #define BG_DP_OVERLAP 512u        /* a segment's backward pass starts this far past its end, from cost 0 */
@@ -623,12 +605,16 @@ BG_HD uint32_t bg_dp_choose(const BgCtx &c, uint32_t p, uint32_t e, const uint32
     const uint8_t *rb = c.regb;
     uint32_t best = bg_dp_pack(rb[BG_B_LITCOST + bg_ld8(c.dataw, p)] + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
     const uint32_t *cd = c.cand + 4u * p;
-    uint32_t L[4], O[4];
-    for (int k = 0; k < 4; k++) { L[k] = cd[k] >> 16; O[k] = cd[k] & 0xffffu; }
+    uint32_t L[4], O[4], longest = 0;
+    for (int k = 0; k < 4; k++) {
+        L[k] = cd[k] >> 16;
+        O[k] = cd[k] ? bg_mw_off(cd[k]) : 0u;
+        if (L[k] > longest) longest = L[k];
+    }
     uint32_t maxl = e - p;
-    if (L[0] < maxl) maxl = L[0];
+    if (longest < maxl) maxl = longest;
     for (uint32_t l = 3; l <= maxl; l++) {
-        const uint32_t k = l <= L[3] ? 3 : l <= L[2] ? 2 : l <= L[1] ? 1 : 0;
+        const uint32_t k = l <= L[0] ? 0 : l <= L[1] ? 1 : l <= L[2] ? 2 : 3;      /* the nearest range that has a match this long */
         uint32_t nb, ex;
         const uint32_t cost = rb[BG_B_LENCOST + l] + rb[BG_B_OFFCOST + bg_off_slot(O[k], &nb, &ex)] + ring[(p + l) & (BG_DP_RING - 1)];
         const uint32_t v = bg_dp_pack(cost, l, k);
@@ -644,7 +630,7 @@ BG_HD void bg_dp_commit(const BgCtx &c, uint32_t p, uint32_t choice)
         c.stepcode[p] = 0;
     } else {
         c.stepcode[p] = (uint8_t)(l <= 256 ? l - 2 : 255);
-        c.R[p] = bg_mw(l, c.cand[4u * p + k] & 0xffffu);
+        c.R[p] = bg_mw(l, bg_mw_off(c.cand[4u * p + k]));
     }
 }
 

@@ -250,6 +250,7 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
         }
         return;
     }
+    const bool opt = c.prm.opt_passes > 0;
     if (t == 0 && own == 0) atomicOr(&mark[0], 1u);
     for (uint32_t p0 = t - lane; p0 < n; p0 += BG_THREADS) {       /* (warp-uniform trip count) */
         const uint32_t word = p0 >> 5;
@@ -260,6 +261,16 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
         if (p < n) {
             r = bg_nearest(c, p, &deep, &target);
             c.R[p] = r;
+        }
+        if (opt) {
+            /* near-optimal class: every eligible position is searched (no landing marks); the nearest match opens its offset range */
+            if (p < n) {
+                const uint32_t k = r ? bg_off_bin(bg_mw_off(r)) : 4u;
+                ((uint4 *)c.cand)[p] = make_uint4(k == 0 ? r : 0u, k == 1 ? r : 0u, k == 2 ? r : 0u, k == 3 ? r : 0u);
+            }
+            const unsigned em = __ballot_sync(0xffffffffu, deep);
+            if (lane == 0) elig[word] = em;
+            continue;
         }
         const bool lit = p < n && target == p + 1;
         const unsigned lm = __ballot_sync(0xffffffffu, lit), em = __ballot_sync(0xffffffffu, deep);
@@ -274,14 +285,18 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
     }
 }
 
-/* pass 3: up to 32 queued candidates, one per lane: full extension, merged into the position's match word */
+/* pass 3: up to 32 queued candidates, one per lane: full extension, merged into the position's match word (near-optimal
+ * class: also into the word of the candidate's offset range) */
 __device__ __forceinline__ void drain_queue(const BgCtx &c, const uint32_t *queue, uint32_t from, uint32_t count, uint32_t lane)
 {
     if (lane < count) {
         const uint32_t e = queue[from + lane];
         const uint32_t p = e >> 16, q = e & 0xffffu;
         const uint32_t v = bg_deep_extend(c, p, q);
-        if (v) atomicMax(&c.R[p], v);
+        if (v) {
+            atomicMax(&c.R[p], v);
+            if (c.cand) atomicMax(&c.cand[4u * p + bg_off_bin(p - q)], v);
+        }
     }
 }
 
@@ -342,12 +357,12 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
     }
 }
 
-__device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
+__device__ __forceinline__ void search_deep_batches(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
     const uint32_t lane = t & 31u, warp = t >> 5;
     const uint32_t *todo = (const uint32_t *)(c.regb + BG_B_TODO);
     uint32_t *queue = (uint32_t *)(c.regb + BG_B_QUEUE) + warp * BG_QUEUE_WORDS;
-    volatile uint16_t *gather = (volatile uint16_t *)(c.regb + BG_B_GATHER) + warp * 64u;
+    volatile uint16_t *gather = (volatile uint16_t *)(c.regb + BG_B_RING) + warp * 64u;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t nwords = (c.n + 31u) >> 5;
     uint32_t fill = 0, cnt = 0;                                  /* todo positions waiting in gather[], candidates in queue[] (warp-uniform) */
@@ -374,19 +389,113 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
     drain_queue(c, queue, 0u, cnt, lane);
 }
 
-/* ---- near-optimal class: all-position search keeping four matches per position ---- */
-__device__ __forceinline__ void search_positions(const BgCtx &c, uint32_t t)
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src)
 {
-    for (uint32_t p = t; p < c.n; p += BG_THREADS)
-        c.R[p] = bg_search_one_multi(c, p);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-/* the same, for one CTA of a cluster that shares the search of ONE block: CTA `rank` of `parts` takes every
- * parts-th tile of 1024 positions and writes to the match scratch of the cluster's first CTA */
-__device__ __forceinline__ void search_positions_part(const BgCtx &c, uint32_t t, uint32_t rank, uint32_t parts)
+/* pass 2: the deep search of the todo positions.  Every lane walks the chain of ONE position; a lane whose chain has ended
+ * takes the next todo position of its warp at once (chains are anything from 1 to `depth` nodes long: a warp that walked 32
+ * positions side by side would idle most of its lanes most of the time).  The warp's todo positions wait in a small ring
+ * that is topped up from the todo bitmap, and the match word of the nearest candidate — which says what a deeper candidate
+ * has to beat — is fetched into the ring with cp.async when the position enters it, a turn or more before a lane needs it.
+ * Candidates that agree with the position on the 4 bytes ending just past the match to beat are placed on the warp's queue
+ * by one ballot per chain step; the queue is drained whenever it holds a full batch of 32 (pass 3). */
+__device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
-    for (uint32_t p = rank * BG_THREADS + t; p < c.n; p += parts * BG_THREADS)
-        c.R[p] = bg_search_one_multi(c, p);
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    const uint32_t *todo = (const uint32_t *)(c.regb + BG_B_TODO);
+    uint32_t *queue = (uint32_t *)(c.regb + BG_B_QUEUE) + warp * BG_QUEUE_WORDS;
+    volatile uint16_t *ring = (volatile uint16_t *)(c.regb + BG_B_RING) + warp * 64u;
+    volatile uint32_t *ringr = (volatile uint32_t *)(c.regb + BG_B_RINGR) + warp * 64u;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t nwords = (c.n + 31u) >> 5;
+    const int depth0 = (int)c.scal[BG_S_DEPTH] - 1;
+    /* warp w takes every 32nd of this CTA's words (32 positions each): records alternate between cheap (sequence) and
+     * deep (quality) stretches, so the work spreads evenly */
+    uint32_t word = own + parts * warp;
+    const uint32_t wstep = parts * (BG_THREADS / 32u);
+    uint32_t head = 0, tail = 0, cnt = 0;                          /* ring [head, tail), queue entries: warp-uniform */
+    uint32_t p = 0, q = BG_NOPOS, b1 = 3, tailw = 0;
+    int depth = 0;
+    bool live = false;
+    for (;;) {
+        /* top the ring up to 32 or more waiting positions */
+        while (tail - head < 32u && word < nwords) {
+            const uint32_t w = todo[word];
+            if (w) {
+                if ((w >> lane) & 1u) {
+                    const uint32_t slot = (tail + __popc(w & lt)) & 63u, pos = word * 32u + lane;
+                    ring[slot] = (uint16_t)pos;
+                    cp_async4((void *)(ringr + slot), c.R + pos);
+                }
+                tail += __popc(w);
+            }
+            word += wstep;
+        }
+        /* lanes without a chain take the oldest waiting positions */
+        const unsigned need = __ballot_sync(0xffffffffu, !live);
+        if (need && head != tail) {
+            cp_async_wait_all();
+            __syncwarp();
+            const uint32_t avail = tail - head, rank = __popc(need & lt);
+            if (!live && rank < avail) {
+                const uint32_t slot = (head + rank) & 63u;
+                p = ring[slot];
+                const uint32_t r1 = ringr[slot];
+                b1 = r1 ? r1 >> 16 : 3u;
+                tailw = bg_ld32(c.dataw, p + b1 - 3u);
+                q = c.prev[c.prev[p]];
+                depth = depth0;
+                live = depth > 0 && bg_in_window(p, q);
+            }
+            head += min(avail, (uint32_t)__popc(need));
+            __syncwarp();
+            if (head != tail || word < nwords) continue;           /* (more may be waiting: fill and hand out again before walking) */
+        }
+        if (!__any_sync(0xffffffffu, live)) break;
+#pragma unroll
+        for (uint32_t k = 0; k < BG_SCAN_CHUNK; k++) {
+            bool pass = false;
+            const uint32_t qc = q;
+            if (live) {
+                const uint32_t qn = c.prev[q];
+                pass = bg_ld32(c.dataw, q + b1 - 3u) == tailw;
+                depth--;
+                q = qn;
+                live = depth > 0 && bg_in_window(p, q);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                if (pass) queue[cnt + __popc(m & lt)] = (p << 16) | qc;
+                cnt += __popc(m);
+            }
+        }
+        if (cnt >= 32u) {
+            __syncwarp();
+            do {
+                cnt -= 32u;
+                drain_queue(c, queue, cnt, 32u, lane);
+            } while (cnt >= 32u);
+            __syncwarp();
+            /* some of this position's candidates may have been measured by now: test the rest of the chain against the longer
+             * match.  (Whenever this happens, the final words are the same where it matters: a candidate is only ever dropped
+             * for not being longer than a nearer one that has already been measured.) */
+            if (live) {
+                const uint32_t r = __ldcg(c.R + p);
+                if ((r >> 16) > b1) {
+                    b1 = r >> 16;
+                    uint32_t maxl = c.n - p;
+                    if (maxl > 258u) maxl = 258u;
+                    if (b1 >= maxl) live = false;
+                    else tailw = bg_ld32(c.dataw, p + b1 - 3u);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    drain_queue(c, queue, 0u, cnt, lane);
 }
 
 __device__ __forceinline__ uint32_t cluster_rank()
@@ -432,18 +541,23 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
         const bool more = top >= a + 32u;
         if (more) next = top - 32u >= lane && top - 32u - lane >= a ? __ldcg(cand4 + (top - 32u - lane)) : zero4;
         {
-            uint32_t oc = 0, litc = 0;
+            /* staged per position: M0..M3 = running maxima of the four ranges' lengths from the nearest range outwards (range k
+             * serves the lengths in (M[k-1], M[k]]), the four offset costs, the literal cost */
+            uint32_t oc = 0, litc = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
             if (top >= lane && q >= a) {
                 const uint32_t cd[4] = { mine.x, mine.y, mine.z, mine.w };
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const uint32_t off = cd[k] & 0xffffu;
                     uint32_t nbx, exx;
-                    if (off) oc |= (uint32_t)rb[BG_B_OFFCOST + bg_off_slot(off, &nbx, &exx)] << (8 * k);
+                    if (cd[k]) oc |= (uint32_t)rb[BG_B_OFFCOST + bg_off_slot(bg_mw_off(cd[k]), &nbx, &exx)] << (8 * k);
                 }
+                m0 = mine.x >> 16;
+                m1 = max(m0, mine.y >> 16);
+                m2 = max(m1, mine.z >> 16);
+                m3 = max(m2, mine.w >> 16);
                 litc = rb[BG_B_LITCOST + bg_ld8(c.dataw, q)];
             }
-            stage[lane] = make_uint4((mine.x >> 16) | (mine.y & 0xffff0000u), (mine.z >> 16) | (mine.w & 0xffff0000u), oc, litc);
+            stage[lane] = make_uint4(m0 | (m1 << 16), m2 | (m3 << 16), oc, litc);
         }
         __syncwarp();
         const uint32_t steps = top - a + 1 < 32u ? top - a + 1 : 32u;
@@ -451,9 +565,9 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
         for (uint32_t j = 0; j < steps; j++) {
             const uint32_t p = top - j;
             const uint4 st = stage[j];
-            const uint32_t L0 = st.x & 0xffffu, L1 = st.x >> 16, L2 = st.y & 0xffffu, L3 = st.y >> 16;
+            const uint32_t M0 = st.x & 0xffffu, M1 = st.x >> 16, M2 = st.y & 0xffffu, M3 = st.y >> 16;
             uint32_t maxl = e - p;
-            if (L0 < maxl) maxl = L0;
+            if (M3 < maxl) maxl = M3;
             uint32_t best = 0xffffffffu;
             if (lane == 0) best = bg_dp_pack(st.w + ring[(p + 1) & (BG_DP_RING - 1)], 1, 0);
             /* (most matches are shorter than 35: one length per lane; the loop proper is kept rolled so that the common
@@ -462,7 +576,7 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
             if (l <= maxl) {
 #pragma unroll 1
                 do {
-                    const uint32_t k = (l <= L3 ? 1u : 0u) + (l <= L2 ? 1u : 0u) + (l <= L1 ? 1u : 0u);
+                    const uint32_t k = (l > M0 ? 1u : 0u) + (l > M1 ? 1u : 0u) + (l > M2 ? 1u : 0u);
                     const uint32_t oc = (st.z >> (8 * k)) & 0xffu;
                     const uint32_t v = bg_dp_pack(rb[BG_B_LENCOST + l] + oc + ring[(p + l) & (BG_DP_RING - 1)], l, k);
                     best = v < best ? v : best;
@@ -481,7 +595,7 @@ __device__ __forceinline__ void dp_segment_warp(const BgCtx &c, uint32_t w, uint
             if (l == 1) {
                 c.stepcode[q] = 0;
             } else {
-                const uint32_t off = (k == 0 ? mine.x : k == 1 ? mine.y : k == 2 ? mine.z : mine.w) & 0xffffu;
+                const uint32_t off = bg_mw_off(k == 0 ? mine.x : k == 1 ? mine.y : k == 2 ? mine.z : mine.w);
                 c.stepcode[q] = (uint8_t)(l <= 256 ? l - 2 : 255);
                 c.R[q] = bg_mw(l, off);
             }
@@ -752,10 +866,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         }
         __syncthreads();
         PROF_MARK(10);
-        if (c.prm.opt_passes > 0) {
-            if (SPLIT) search_positions_part(c, t, crank, csize);
-            else search_positions(c, t);
-        } else {
+        {
             bg_phase_search_clear(c, t, T);
             if (SPLIT) cluster_sync();                           /* every CTA's bitmap is clear before anyone's marks arrive */
             else __syncthreads();
@@ -766,7 +877,9 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
             if (c.scal[BG_S_DEPTH] > 1) {                        /* (uniform for the CTA) */
                 bg_phase_search_todo(c, t, T, crank, csize);
                 __syncthreads();
-                search_deep(c, t, crank, csize);
+                /* shallow chains (levels 2-7): 32 positions side by side; deep ones: lanes refill themselves */
+                if (c.scal[BG_S_DEPTH] <= 24u) search_deep_batches(c, t, crank, csize);
+                else search_deep(c, t, crank, csize);
             }
         }
         if (SPLIT) {

@@ -79,15 +79,11 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     run(bg_phase_settle, c, order, k++);
     run(bg_phase_hash, c, order, k++);
     bg_build_sequential(c);
-    if (c.prm.opt_passes > 0) {
-        run(bg_phase_search, c, order, k++);
-    } else {
-        run(bg_phase_search_clear, c, order, k++);
-        run(bg_phase_search1, c, order, k++);
-        if (c.scal[BG_S_DEPTH] > 1) {
-            run([](const BgCtx &cc, uint32_t t, uint32_t T) { bg_phase_search_todo(cc, t, T, 0u, 1u); }, c, order, k++);
-            run(bg_phase_search2, c, order, k++);
-        }
+    run(bg_phase_search_clear, c, order, k++);
+    run(bg_phase_search1, c, order, k++);
+    if (c.scal[BG_S_DEPTH] > 1) {
+        run([](const BgCtx &cc, uint32_t t, uint32_t T) { bg_phase_search_todo(cc, t, T, 0u, 1u); }, c, order, k++);
+        run(bg_phase_search2, c, order, k++);
     }
     for (int pass = 0; pass <= c.prm.opt_passes; pass++) {
         if (pass == 0) {
