@@ -450,11 +450,13 @@ BG_HD bool bg_in_window(uint32_t p, uint32_t q) { return p - q - 1u < 32768u; }
  * Region B during the search (the hash heads are dead): */
 #define BG_B_TODO 0u          /* u32[2048]  pass 1: eligible bits; then the todo bits */
 #define BG_B_MARK 8192u       /* u32[2064]  landing positions of the greedy steps (dead once the todo bits are made) */
-#define BG_B_QUEUE 8192u      /* u32[32][96]   per warp: (p << 16 | q) candidates waiting for their extension */
-#define BG_B_RINGR 20480u     /* u32[32][64]   per warp: the nearest-match words of the todo positions in the ring (fetched ahead, cp.async) */
+#define BG_B_QUEUE 8192u      /* u32[32][160] (shallow chains) or u32[32][96] (deep): per warp, (p << 16 | q) candidates waiting for their extension */
+#define BG_B_RINGR 20480u     /* u32[32][64]   deep chains, per warp: the nearest-match words of the todo positions in the ring (fetched ahead, cp.async) */
 #define BG_B_RING 28672u      /* u16[32][64]   per warp: ring of todo positions waiting for a free lane */
-#define BG_QUEUE_WORDS 96u
-#define BG_SCAN_CHUNK 2u      /* chain steps between two looks at the queue and at the lanes that ran out: 31 + 32 * 2 entries fit */
+#define BG_QUEUE_WORDS 96u    /* deep chains: a look at the queue every 2 chain steps: 31 + 32 * 2 entries fit */
+#define BG_SCAN_CHUNK 2u
+#define BG_QUEUE_WORDS_SHALLOW 160u   /* shallow chains (32 positions side by side): every 4 steps, 31 + 32 * 4 */
+#define BG_SCAN_CHUNK_SHALLOW 4u
 
 BG_HD bool bg_match_ok(uint32_t r, uint32_t minlen);
 

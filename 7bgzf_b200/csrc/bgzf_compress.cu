@@ -317,7 +317,7 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
     bool live = active && depth > 0 && bg_in_window(p, q);
     while (__any_sync(0xffffffffu, live)) {
 #pragma unroll
-        for (uint32_t k = 0; k < BG_SCAN_CHUNK; k++) {
+        for (uint32_t k = 0; k < BG_SCAN_CHUNK_SHALLOW; k++) {
             bool pass = false;
             const uint32_t qc = q;
             if (live) {
@@ -361,7 +361,7 @@ __device__ __forceinline__ void search_deep_batches(const BgCtx &c, uint32_t t, 
 {
     const uint32_t lane = t & 31u, warp = t >> 5;
     const uint32_t *todo = (const uint32_t *)(c.regb + BG_B_TODO);
-    uint32_t *queue = (uint32_t *)(c.regb + BG_B_QUEUE) + warp * BG_QUEUE_WORDS;
+    uint32_t *queue = (uint32_t *)(c.regb + BG_B_QUEUE) + warp * BG_QUEUE_WORDS_SHALLOW;
     volatile uint16_t *gather = (volatile uint16_t *)(c.regb + BG_B_RING) + warp * 64u;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t nwords = (c.n + 31u) >> 5;
