@@ -15,6 +15,7 @@ BLOCK_SIZE = 0xFF00
 MAX_BLOCK_SIZE = 0x10000
 APPEND_EOF = 1
 VERIFY = 2
+FRAME_MIGZ = 4
 E_NOFIT, E_ARG, E_CUDA, E_FORMAT, E_NOSPACE, E_CRC = 1, -1, -2, -3, -4, -5
 EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
@@ -124,11 +125,11 @@ class Codec:
         return self.lib.b200bgzf_compress_bound(n, block_size)
 
     # ---- host buffers ----
-    def compress(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
+    def compress(self, data, level=6, block_size=BLOCK_SIZE, eof=True, flags=0):
         out = bytearray(self.bound(len(data), block_size))
         n = ctypes.c_size_t()
         self._check(self.lib.b200bgzf_compress_host(self.h, _addr(data) if len(data) else None, len(data), block_size, level,
-                                                    _addr(out), len(out), ctypes.byref(n), APPEND_EOF if eof else 0))
+                                                    _addr(out), len(out), ctypes.byref(n), (APPEND_EOF if eof else 0) | flags))
         return bytes(out[: n.value])
 
     def compress_indexed(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
@@ -220,15 +221,15 @@ class MultiCodec:
         if rc != 0:
             raise B200BgzfError(rc, self.lib.b200bgzf_strerror(rc).decode())
 
-    def compress_into(self, src_addr, nbytes, dst_addr, dst_cap, level=6, block_size=BLOCK_SIZE, eof=True):
+    def compress_into(self, src_addr, nbytes, dst_addr, dst_cap, level=6, block_size=BLOCK_SIZE, eof=True, flags=0):
         n = ctypes.c_size_t()
         self._check(self.lib.b200bgzf_multi_compress_host(self.h, src_addr, nbytes, block_size, level, dst_addr, dst_cap, ctypes.byref(n),
-                                                          APPEND_EOF if eof else 0))
+                                                          (APPEND_EOF if eof else 0) | flags))
         return n.value
 
-    def compress(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
+    def compress(self, data, level=6, block_size=BLOCK_SIZE, eof=True, flags=0):
         out = bytearray(self.bound(len(data), block_size))
-        n = self.compress_into(_addr(data) if len(data) else None, len(data), _addr(out), len(out), level, block_size, eof)
+        n = self.compress_into(_addr(data) if len(data) else None, len(data), _addr(out), len(out), level, block_size, eof, flags)
         return bytes(out[:n])
 
     def inflate_into(self, src_addr, nbytes, dst_addr, dst_cap, flags=0):

@@ -260,7 +260,7 @@ int lane_reserve(b200bgzf_ctx *ctx, Lane &l, uint32_t blocks, size_t in_bytes, s
 /* one batch: compress kernel into slots, then scan + gather into `d_out` continuing at *d_total */
 int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint64_t in_bytes, uint32_t block_size,
                           const uint64_t *d_inoff, const uint32_t *d_inlen, uint32_t nblocks, int level, uint8_t *d_out,
-                          int append_eof, cudaStream_t stream, bool fused = false)
+                          int append_eof, cudaStream_t stream, bool fused = false, uint32_t hdr_bytes = 18)
 {
     /* fused: the compress kernel's last CTA compacts the batch itself (l.d_total[2] is its arrival counter, zeroed with
      * l.d_total by the caller).  The pipelined host path uses it: a separate scan + gather launch per 32 MiB batch has to
@@ -275,6 +275,7 @@ int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint6
         a.in_bytes = in_bytes;
         a.block_size = block_size;
         a.nblocks = nblocks;
+        a.hdr_bytes = hdr_bytes;
         a.prm = bg_level_params(level);
         a.slots = l.d_slots;
         a.out_len = l.d_len;
@@ -341,7 +342,7 @@ extern "C" size_t b200bgzf_compress_bound(size_t in_bytes, uint32_t block_size)
 {
     if (block_size == 0 || block_size > B200BGZF_MAX_BLOCK_SIZE) return 0;
     const size_t nb = (in_bytes + block_size - 1) / block_size;
-    return in_bytes + nb * 36 + B200BGZF_EOF_BYTES;   /* 18 + 8 framing + up to two stored-block headers */
+    return in_bytes + nb * 38 + B200BGZF_EOF_BYTES;   /* 18 (BGZF) or 20 (MiGz) + 8 framing + up to two stored-block headers */
 }
 
 extern "C" int b200bgzf_create(b200bgzf_ctx **out, int device)
@@ -437,14 +438,15 @@ extern "C" int b200bgzf_compress_device(b200bgzf_ctx *ctx, const void *d_in, siz
     if (r) return r;
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : l.stream;
     CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), stream));
-    const int eof = (flags & B200BGZF_APPEND_EOF) ? 1 : 0;
+    const uint32_t hdr = (flags & B200BGZF_FRAME_MIGZ) ? 20u : 18u;
+    const int eof = (flags & B200BGZF_APPEND_EOF) && hdr == 18u ? 1 : 0;
     uint64_t done = 0;
     do {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, nb_total - done);
         const uint64_t off = done * block_size;
         const bool last = done + nb >= nb_total;
         r = launch_compress_batch(ctx, l, (const uint8_t *)d_in + off, in_bytes - off, block_size, nullptr, nullptr, nb, level,
-                                  (uint8_t *)d_out, eof && last, stream);
+                                  (uint8_t *)d_out, eof && last, stream, false, hdr);
         if (r) return r;
         done += nb;
     } while (done < nb_total);
@@ -500,7 +502,8 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
         const size_t bytes = (size_t)std::min<uint64_t>((uint64_t)nb * block_size, in_bytes - off);
         CK(cudaMemcpyAsync(l.d_in, (const uint8_t *)in + off, bytes, cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
-        if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true))) return r;
+        if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true,
+                                       (flags & B200BGZF_FRAME_MIGZ) ? 20u : 18u))) return r;
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
         if (member_off) {
             CK(grow(&l.h_meta, &l.meta_cap, (size_t)batch, true));
@@ -519,7 +522,7 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     }
     for (auto &l : ctx->lanes)
         if (l.stream) CK(cudaStreamSynchronize(l.stream));
-    if (flags & B200BGZF_APPEND_EOF) {
+    if ((flags & B200BGZF_APPEND_EOF) && !(flags & B200BGZF_FRAME_MIGZ)) {
         static const uint8_t eof[28] = { 0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0,
                                          0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         memcpy((uint8_t *)out + host_off, eof, sizeof eof);

@@ -133,6 +133,7 @@ struct BgCtx {
     const uint16_t *perm;   /* smem u16[BG_MAX_CHUNKS] or NULL: which chunk thread i walks in the token passes (tally, sizes, emit).
                                Any permutation gives the same bytes; the kernel groups chunks of similar make-up into one warp. */
     uint32_t n;         /* payload bytes */
+    uint32_t hdr;       /* member header bytes: 18 BGZF ("BC" subfield, BSIZE), 20 MiGz ("MZ" subfield, u32 compressed size: applet/7migz.c:224-228) */
     BgParams prm;
 };
 
@@ -1429,7 +1430,7 @@ BG_HD void bg_phase_decide_b(const BgCtx &c, uint32_t t, uint32_t T)
         c.scal[BG_S_HDRBITS] = hdrbits;
         c.scal[BG_S_TOKBITS] = tokbits;   /* includes the end-of-block symbol */
         c.scal[BG_S_PAYLOAD] = payload;
-        c.scal[BG_S_STATUS] = (18u + payload + 8u > BG_SLOT_BYTES) ? 1u : 0u;
+        c.scal[BG_S_STATUS] = (c.hdr + payload + 8u > BG_SLOT_BYTES) ? 1u : 0u;
     }
 }
 
@@ -1586,7 +1587,7 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
 /* phase 16: zero the output words this block will OR into */
 BG_HD void bg_phase_zero_out(const BgCtx &c, uint32_t t, uint32_t T)
 {
-    uint32_t bytes = 18 + c.scal[BG_S_PAYLOAD] + 8;
+    uint32_t bytes = c.hdr + c.scal[BG_S_PAYLOAD] + 8;
     if (bytes > BG_SLOT_BYTES) bytes = BG_SLOT_BYTES;
     uint32_t words = (bytes + 3) >> 2;
     for (uint32_t i = t; i < words; i += T)
@@ -1630,20 +1631,27 @@ BG_HD void bg_w_flush(BgWriter &w)
         bg_or32(&w.out[w.word], (uint32_t)w.acc);
 }
 
-/* BGZF framing: 18-byte header with BSIZE, then CRC32 + ISIZE after the payload (bgzf_compress.c:191-196) */
+/* framing: the member header, then CRC32 + ISIZE after the payload.  BGZF (bgzf_compress.c:191-196): 18 bytes, subfield
+ * "BC" with BSIZE = member size - 1.  MiGz (applet/7migz.c:224-233): 20 bytes, subfield "MZ" with the DEFLATE size as u32. */
 BG_HD void bg_emit_frame(const BgCtx &c)
 {
     const uint32_t payload = c.scal[BG_S_PAYLOAD];
-    const uint32_t total = 18 + payload + 8;
+    const uint32_t total = c.hdr + payload + 8;
     BgWriter w;
     bg_w_init(w, c.out, 0);
     bg_w_put(w, 0x04088b1fu, 32);          /* 1f 8b 08 04 */
     bg_w_put(w, 0u, 32);                   /* MTIME */
-    bg_w_put(w, 0x0006ff00u, 32);          /* XFL 00, OS ff, XLEN 0006 */
-    bg_w_put(w, 0x00024342u, 32);          /* 'B' 'C' SLEN 0002 */
-    bg_w_put(w, (total - 1) & 0xffffu, 16);
+    if (c.hdr == 18u) {
+        bg_w_put(w, 0x0006ff00u, 32);      /* XFL 00, OS ff, XLEN 0006 */
+        bg_w_put(w, 0x00024342u, 32);      /* 'B' 'C' SLEN 0002 */
+        bg_w_put(w, (total - 1) & 0xffffu, 16);
+    } else {
+        bg_w_put(w, 0x0008ff00u, 32);      /* XFL 00, OS ff, XLEN 0008 */
+        bg_w_put(w, 0x00045a4du, 32);      /* 'M' 'Z' SLEN 0004 */
+        bg_w_put(w, payload, 32);
+    }
     bg_w_flush(w);
-    bg_w_init(w, c.out, (18 + payload) * 8);
+    bg_w_init(w, c.out, (c.hdr + payload) * 8);
     bg_w_put(w, c.scal[BG_S_CRC], 32);
     bg_w_put(w, c.n, 32);
     bg_w_flush(w);
@@ -1657,7 +1665,7 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t n = c.n;
     uint8_t *rb = c.regb;
     const uint32_t btype = c.scal[BG_S_BTYPE];
-    const uint32_t base = 18 * 8;
+    const uint32_t base = c.hdr * 8;
     if (btype == 0) {
         /* stored: [01|00] LEN NLEN raw..., at most two stored blocks (n <= 65536) */
         const uint32_t first = n > 65535u ? 65535u : n;
@@ -1676,17 +1684,19 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
                 bg_w_flush(w);
             }
         }
-        /* raw bytes: payload byte i lands at slot byte 23+i (+5 more after the first 65535).
+        /* raw bytes: payload byte i lands at slot byte hdr+5+i (+5 more after the first 65535).
          * Output words whose four source bytes all lie in the first stored block are plain stores
          * of an unaligned read; the few bytes at either edge are OR-ed in one by one. */
-        const uint32_t wend = (first + 23u) >> 2;              /* first word that is not "full" */
-        for (uint32_t wd = 6 + t; wd < wend; wd += T)
-            c.out[wd] = bg_ld32(c.dataw, 4 * wd - 23);
-        const uint32_t s1 = wend > 6 ? 4 * wend - 23 : 1;      /* first source byte past the full words */
-        if (t < 16) {
-            uint32_t src = t == 0 ? 0 : s1 + (t - 1);
+        const uint32_t r0 = c.hdr + 5u;                        /* slot byte of payload byte 0 */
+        const uint32_t w0 = (r0 + 3u) >> 2, hb = 4u * w0 - r0;  /* first full word; payload bytes before it */
+        const uint32_t wend = (first + r0) >> 2;               /* first word that is not "full" */
+        for (uint32_t wd = w0 + t; wd < wend; wd += T)
+            c.out[wd] = bg_ld32(c.dataw, 4 * wd - r0);
+        const uint32_t s1 = wend > w0 ? 4 * wend - r0 : hb;    /* first source byte past the full words */
+        if (t < hb + 15u) {
+            uint32_t src = t < hb ? t : s1 + (t - hb);
             if (src < n) {
-                uint32_t dst = 23 + src + (src >= 65535u ? 5 : 0);
+                uint32_t dst = r0 + src + (src >= 65535u ? 5 : 0);
                 bg_or32(&c.out[dst >> 2], bg_ld8(c.dataw, src) << (8 * (dst & 3)));
             }
         }

@@ -792,6 +792,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
     c.cand = a.cand ? a.cand + (size_t)unit * (4u * BG_MAX_BLOCK) : nullptr;
     c.crcpow = a.crcpow;
     c.prm = a.prm;
+    c.hdr = a.hdr_bytes ? a.hdr_bytes : 18u;
     c.perm = (const uint16_t *)(smem + SM_REGB + BG_B_PERM);
 
     if (t < 256) c.crctab[t] = a.crctab[t];
@@ -980,7 +981,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         bg_phase_emit(c, t, T);
         if (t == 0) {
             const uint32_t st = c.scal[BG_S_STATUS];
-            a.out_len[b] = st ? 0u : 18u + c.scal[BG_S_PAYLOAD] + 8u;
+            a.out_len[b] = st ? 0u : c.hdr + c.scal[BG_S_PAYLOAD] + 8u;
             a.status[b] = st;
             if (st) atomicOr(a.err_flag, 1u);
         }

@@ -556,6 +556,7 @@ bgzf_verify_kernel(BgzfInflateArgs a)
     c.scal = (uint32_t *)(vs + BG_DATA_BYTES + 1024u + 256u);
     c.crcpow = a.crcpow;
     c.n = isize;
+    c.hdr = 18;
     /* stage: bytes up to the first 16-byte boundary of the source, 16-byte loads for the body, bytes for the rest */
     const uint32_t head = isize < 16 ? isize : (uint32_t)((16u - ((uintptr_t)out & 15u)) & 15u);
     const uint32_t body = (isize - head) & ~15u;

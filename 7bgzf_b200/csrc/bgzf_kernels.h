@@ -18,6 +18,7 @@ struct BgzfCompressArgs {
     uint64_t in_bytes;         /* fixed-size mode: total bytes */
     uint32_t block_size;       /* fixed-size mode: payload bytes per block (<= 65536) */
     uint32_t nblocks;
+    uint32_t hdr_bytes;        /* 0 or 18: BGZF members; 20: MiGz members (same DEFLATE data, other gzip subfield) */
     BgParams prm;              /* search effort, from bg_level_params(level) on the host */
     uint8_t *slots;            /* device: nblocks * 65536 (+16) bytes */
     uint32_t *out_len;         /* device: member size per block (0 on failure) */

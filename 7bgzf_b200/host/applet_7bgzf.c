@@ -310,6 +310,7 @@ static size_t walk_member_offsets(const unsigned char *buf, size_t len, uint64_t
 /* The reader starts on stdin BEFORE the GPU context exists: creating a CUDA context takes 0.3 - 2 s, during which the first
  * slots fill.  Slots are plain page-aligned memory: pinning 400 MB costs 0.3 s, and the pipeline is bound by file I/O
  * (2 - 8 GB/s), not by the 10 GB/s at which the driver stages pageable buffers. */
+static unsigned g_frame_flags;          /* B200BGZF_FRAME_MIGZ when run as `7migz` */
 static int run_pipeline(int ndevices, int decompress, int level, uint32_t block, const char *gzi_path)
 {
     b200bgzf_ctx *ctx = NULL;
@@ -375,7 +376,7 @@ static int run_pipeline(int ndevices, int decompress, int level, uint32_t block,
                 units += (long)sl->members;
             } else {
                 uint32_t used_block = block;
-                const unsigned fl = sl->last ? B200BGZF_APPEND_EOF : 0;
+                const unsigned fl = (sl->last ? B200BGZF_APPEND_EOF : 0) | g_frame_flags;
                 r = multi ? b200bgzf_multi_compress_host(multi, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len, fl)
                           : b200bgzf_compress_host_index(ctx, sl->in, sl->in_len, block, level, sl->out, ps.out_cap, &sl->out_len, fl, gzi.slot_off, gzi.slot_cap);
                 if (r == B200BGZF_E_NOFIT && block > B200BGZF_BLOCK_SIZE) {
@@ -393,7 +394,7 @@ static int run_pipeline(int ndevices, int decompress, int level, uint32_t block,
                 units += (long)((sl->in_len + block - 1) / block);
                 if (!r && gzi.slot_off && gzi_add_slot(&gzi, sl->in_len, sl->out_len, used_block, sl->last)) { fprintf(stderr, "out of memory\n"); ret = 1; }
             }
-        } else if (!decompress && sl->last) {
+        } else if (!decompress && sl->last && !g_frame_flags) {
             /* empty tail slot: still owe the EOF marker (7bgzf.c:283-289) */
             size_t n = 0;
             b200bgzf_compress_host(multi ? b200bgzf_multi_ctx(multi, 0) : ctx, NULL, 0, block, level, sl->out, ps.out_cap, &n, B200BGZF_APPEND_EOF);
@@ -428,11 +429,16 @@ static int run_pipeline(int ndevices, int decompress, int level, uint32_t block,
 int main(int argc, char **argv)
 {
     int levels[NFLAGS];
-    int decompress = 0, nthreads = 1, bad = 0, ndevices = 1;
+    int decompress = 0, nthreads = 1, bad = 0, ndevices = 1, migz = 0, bsize = 63;
     const char *gzi_path = NULL;
     memset(levels, 0, sizeof levels);
-    /* allow `cielbox 7bgzf ...` style invocation */
-    if (argc > 1 && !strcmp(argv[1], "7bgzf")) { argv++; argc--; }
+    /* allow `cielbox 7bgzf ...` style invocation; as `7migz` (applet/7migz.c) the same pipeline writes MiGz members:
+     * -b N = payload KiB per member, at most 63 here (one member = one 64 KiB GPU slot; the reference's default is 512) */
+    if (argc > 1 && (!strcmp(argv[1], "7bgzf") || !strcmp(argv[1], "7migz"))) { argv++; argc--; }
+    {
+        const char *base = strrchr(argv[0], '/');
+        migz = !strcmp(base ? base + 1 : argv[0], "7migz");
+    }
 
     static const struct option longopts[] = {
         { "stdout", no_argument, 0, 'c' },       { "zlib", optional_argument, 0, 'z' },
@@ -443,16 +449,17 @@ int main(int argc, char **argv)
         { "zopfli", required_argument, 0, 'Z' }, { "store", optional_argument, 0, 'T' },
         { "threads", required_argument, 0, '@' }, { "decompress", no_argument, 0, 'd' },
         { "help", no_argument, 0, 'h' },         { "gzi", required_argument, 0, 1000 },
-        { "devices", required_argument, 0, 1001 },
+        { "devices", required_argument, 0, 1001 },  { "bsize", required_argument, 0, 'b' },
         { 0, 0, 0, 0 },
     };
     int opt;
-    while ((opt = getopt_long(argc, argv, "cz::m::s::l::S::n::C::i::K::Z:T::@:dh", longopts, NULL)) != -1) {
+    while ((opt = getopt_long(argc, argv, "cz::m::s::l::S::n::C::i::K::Z:T::@:dhb:", longopts, NULL)) != -1) {
         if (opt == 'c') continue;
         if (opt == 'd') { decompress = 1; continue; }
         if (opt == '@') { nthreads = atoi(optarg); continue; }
         if (opt == 1000) { gzi_path = optarg; continue; }
         if (opt == 1001) { ndevices = atoi(optarg); if (ndevices < 1 || ndevices > 64) bad = 1; continue; }
+        if (opt == 'b') { bsize = atoi(optarg); continue; }
         if (opt == 'h' || opt == '?') { bad = 1; continue; }
         for (size_t k = 0; k < NFLAGS; k++)
             if (k_flags[k].short_opt == opt)
@@ -487,7 +494,12 @@ int main(int argc, char **argv)
         if (level > 12) level = 12;
         /* block size rule of the reference (7bgzf.c:141-147): 0x10000 with one thread, 0xff00 with -@N; the thread count has
          * no other meaning here (the GPU works on all blocks of a slot at once) */
-        ret = run_pipeline(ndevices, 0, level, nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE, gzi_path);
+        if (migz && (bsize < 1 || bsize > 63)) {
+            fprintf(stderr, "7migz: -b %d: members of more than 63 KiB of payload do not fit the GPU codec's 64 KiB slots\n", bsize);
+            return 1;
+        }
+        if (migz) g_frame_flags = B200BGZF_FRAME_MIGZ;
+        ret = run_pipeline(ndevices, 0, level, migz ? (uint32_t)bsize * 1024u : nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE, gzi_path);
     }
     gettimeofday(&t1, NULL);
     fprintf(stderr, "ellapsed time: %.6f sec\n", (t1.tv_sec + t1.tv_usec * 0.000001) - (t0.tv_sec + t0.tv_usec * 0.000001));

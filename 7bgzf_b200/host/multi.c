@@ -80,7 +80,7 @@ static void *shard_main(void *arg)
     if (j->inflate)
         j->rc = b200bgzf_inflate_host(j->ctx, j->in, j->in_bytes, j->out, j->out_cap, &j->out_bytes, j->flags);
     else
-        j->rc = b200bgzf_compress_host(j->ctx, j->in, j->in_bytes, j->block_size, j->level, j->out, j->out_cap, &j->out_bytes, 0);
+        j->rc = b200bgzf_compress_host(j->ctx, j->in, j->in_bytes, j->block_size, j->level, j->out, j->out_cap, &j->out_bytes, j->flags);
     return NULL;
 }
 
@@ -117,14 +117,15 @@ int b200bgzf_multi_compress_host(b200bgzf_multi *m, const void *in, size_t in_by
         b200bgzf_shard_blocks(nb, g, n, &b0, &b1);
         const size_t byte0 = (size_t)b0 * block_size, byte1 = (size_t)b1 * block_size < in_bytes ? (size_t)b1 * block_size : in_bytes;
         /* where this shard may write: behind the worst case of everything before it */
-        const size_t off = byte0 + (size_t)b0 * 36u + (size_t)g * B200BGZF_EOF_BYTES;
+        const size_t off = byte0 + (size_t)b0 * 38u + (size_t)g * B200BGZF_EOF_BYTES;
         jobs[g].ctx = m->ctx[g];
         jobs[g].in = (const unsigned char *)in + byte0;
         jobs[g].in_bytes = byte1 - byte0;
         jobs[g].out = (unsigned char *)out + off;
-        jobs[g].out_cap = (byte1 - byte0) + (size_t)(b1 - b0) * 36u + B200BGZF_EOF_BYTES;
+        jobs[g].out_cap = (byte1 - byte0) + (size_t)(b1 - b0) * 38u + B200BGZF_EOF_BYTES;
         jobs[g].block_size = block_size;
         jobs[g].level = level;
+        jobs[g].flags = flags & ~B200BGZF_APPEND_EOF;
     }
     const int rc = run_jobs(jobs, n);
     if (rc < 0) return rc;
@@ -134,7 +135,7 @@ int b200bgzf_multi_compress_host(b200bgzf_multi *m, const void *in, size_t in_by
         memmove((unsigned char *)out + pos, jobs[g].out, jobs[g].out_bytes);
         pos += jobs[g].out_bytes;
     }
-    if (flags & B200BGZF_APPEND_EOF) {
+    if ((flags & B200BGZF_APPEND_EOF) && !(flags & B200BGZF_FRAME_MIGZ)) {
         static const unsigned char eof[28] = { 0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0,
                                                0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         memcpy((unsigned char *)out + pos, eof, sizeof eof);

@@ -14,7 +14,7 @@ CU_SRCS   := $(CSRC)/bgzf_compress.cu $(CSRC)/bgzf_inflate.cu $(CSRC)/b200bgzf_a
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.h) include/b200bgzf.h
 
-all: $(PKG)/lib7bgzf_b200.so $(PKG)/7bgzf.so $(PKG)/7bgzf
+all: $(PKG)/lib7bgzf_b200.so $(PKG)/7bgzf.so $(PKG)/7bgzf $(PKG)/7migz
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -36,6 +36,10 @@ $(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/hook.o
 $(PKG)/7bgzf: $(OBJ)/applet_7bgzf.o $(PKG)/lib7bgzf_b200.so
 	$(CC) -o $@ $(OBJ)/applet_7bgzf.o -L$(PKG) -l7bgzf_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
 
+# the same applet under its MiGz name (applet/7migz.c: the reference is a multi-call binary too)
+$(PKG)/7migz: $(PKG)/7bgzf
+	ln -sf 7bgzf $@
+
 # ---- test / bench infrastructure (never linked into the product) ----
 testlibs: build/libdatagen.so build/libemul.so build/datagen build/hook_mt oracle/liboracle.so
 
@@ -54,6 +58,6 @@ oracle/liboracle.so: $(wildcard oracle/*.c)
 	$(CC) -O2 -fPIC -shared -pthread -o $@ $(wildcard oracle/*.c) -ldl
 
 clean:
-	rm -rf build $(PKG)/*.so $(PKG)/7bgzf oracle/liboracle.so
+	rm -rf build $(PKG)/*.so $(PKG)/7bgzf $(PKG)/7migz oracle/liboracle.so
 
 .PHONY: all testlibs clean

@@ -33,6 +33,9 @@ extern "C" {
 
 #define B200BGZF_APPEND_EOF 1u  /* compress: finish the stream with the 28-byte EOF member (applet/7bgzf.c:283-289) */
 #define B200BGZF_VERIFY 2u      /* inflate: check CRC32 and ISIZE of every member (the reference does not: 7bgzf.c:350-354) */
+#define B200BGZF_FRAME_MIGZ 4u  /* compress: MiGz members instead of BGZF ones — the same DEFLATE data behind the gzip subfield "MZ" with the
+                                   compressed size as u32 (applet/7migz.c:133-243).  No EOF marker exists in that
+                                   container (B200BGZF_APPEND_EOF is ignored); block_size <= 64512 keeps every member inside its slot. */
 
 typedef struct b200bgzf_ctx b200bgzf_ctx;
 

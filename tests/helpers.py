@@ -49,6 +49,8 @@ def acgt(n):
 def _emul():
     lib = ctypes.CDLL(os.path.join(ROOT, "build", "libemul.so"))
     lib.bgemul_compress_block.argtypes = [u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_uint32)]
+    lib.bgemul_set_header_bytes.argtypes = [ctypes.c_uint32]
+    lib.bgemul_set_header_bytes.restype = None
     return lib
 
 

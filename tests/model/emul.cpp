@@ -43,6 +43,10 @@ void run(phase_fn f, const BgCtx &c, int order, uint32_t seed)
 }
 }  // namespace
 
+static uint32_t g_emul_hdr = 18;
+/* member framing of the following bgemul_compress_block calls: 18 = BGZF (default), 20 = MiGz */
+extern "C" void bgemul_set_header_bytes(uint32_t hdr) { g_emul_hdr = hdr == 20 ? 20 : 18; }
+
 extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, int order, uint8_t *dst, uint32_t *dlen)
 {
     static Emu *e = new Emu();
@@ -71,6 +75,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     c.crcpow = e->crcpow.data();
     c.perm = nullptr;
     c.n = n;
+    c.hdr = g_emul_hdr;
     c.prm = bg_level_params(level);
     uint32_t k = 0;
     run(bg_phase_init, c, order, k++);
@@ -156,7 +161,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     if (c.scal[BG_S_STATUS]) return 1;
     run(bg_phase_zero_out, c, order, k++);
     run(bg_phase_emit, c, order, k++);
-    uint32_t total = 18 + c.scal[BG_S_PAYLOAD] + 8;
+    uint32_t total = c.hdr + c.scal[BG_S_PAYLOAD] + 8;
     memcpy(dst, e->out.data(), total);
     *dlen = total;
     return 0;

@@ -102,3 +102,21 @@ def test_size_on_bam_like_binary_records(level):
     assert len(mine) - 28 <= 1.03 * sum(ref_sizes), (len(mine), sum(ref_sizes))
     rc, out, _ = H.Ref(level).inflate_stream(mine)
     assert rc == 0 and out == data
+
+
+def test_migz_framing_decodes_through_the_reference_7migz():
+    """MiGz members (20-byte header, subfield "MZ" + u32 DEFLATE size: applet/7migz.c:224-233) from the block encoder, coded
+    and stored blocks alike: gzip and the reference's own `7migz -d` give the input back"""
+    import gzip, os, subprocess
+    d = H.synth("sam", 150000) + H.lcg_noise(70000) + b"x"
+    H._emul().bgemul_set_header_bytes(20)
+    try:
+        mz = H.emul_stream(d, 6, block=64512, eof=False)
+    finally:
+        H._emul().bgemul_set_header_bytes(18)
+    bz = H.emul_stream(d, 6, block=64512, eof=False)
+    assert gzip.decompress(mz) == d and len(mz) == len(bz) + 2 * 4 and mz[:16] == bytes.fromhex("1f8b08040000000000ff08004d5a0400")
+    box = os.path.join(H.ROOT, "oracle", "_ref", "cielbox_ref")
+    if os.path.exists(box):
+        r = subprocess.run([box, "7migz", "-d"], input=mz, capture_output=True)
+        assert r.returncode == 0 and r.stdout == d

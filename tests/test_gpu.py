@@ -309,6 +309,55 @@ def test_multi_context_sharding_gives_the_single_gpu_stream(codec):
             m.close()
 
 
+def test_migz_members_on_the_same_kernel(codec):
+    """SURVEY 8(f) rank 3, compress side: MiGz framing (gzip subfield "MZ" + u32 DEFLATE size, applet/7migz.c:224-233) around
+    the same per-block DEFLATE data.  Decodes through the reference's own 7migz -d, gzip, and our inflate; the DEFLATE
+    bytes of every member equal those of the BGZF member of the same payload."""
+    data = H.synth("sam", 9 * 64512 + 777) + H.lcg_noise(3000) + bytes(5000)
+    for level, blk in ((6, 64512), (1, 50000), (12, 64512)):
+        mz = codec.compress(data, level, block_size=blk, flags=b200bgzf.FRAME_MIGZ)
+        bz = codec.compress(data, level, block_size=blk, eof=False)
+        assert H.gunzip(mz) == data and codec.inflate(mz) == data and codec.inflate(mz, flags=b200bgzf.VERIFY) == data
+        off_m = off_b = 0
+        nm = 0
+        while off_m < len(mz):
+            assert mz[off_m : off_m + 16] == bytes.fromhex("1f8b08040000000000ff08004d5a0400")
+            csize = struct.unpack_from("<I", mz, off_m + 16)[0]
+            bsize = struct.unpack_from("<H", bz, off_b + 16)[0] + 1
+            assert mz[off_m + 20 : off_m + 20 + csize + 8] == bz[off_b + 18 : off_b + bsize]      # same DEFLATE data, CRC32 and ISIZE
+            off_m += 20 + csize + 8
+            off_b += bsize
+            nm += 1
+        assert off_m == len(mz) and off_b == len(bz) and nm == (len(data) + blk - 1) // blk
+        if level == 6:
+            H._emul().bgemul_set_header_bytes(20)
+            try:
+                assert mz == H.emul_stream(data, level, block=blk, eof=False)
+            finally:
+                H._emul().bgemul_set_header_bytes(18)
+    ref_box = os.path.join(H.ROOT, "oracle", "_ref", "cielbox_ref")
+    mz = codec.compress(data, 6, block_size=64512, flags=b200bgzf.FRAME_MIGZ)
+    if os.path.exists(ref_box):
+        r = subprocess.run([ref_box, "7migz", "-d"], input=mz, capture_output=True)
+        assert r.returncode == 0 and r.stdout == data
+    # the applet under its MiGz name: same stream; a member size the slots cannot hold is refused
+    a = subprocess.run([b200bgzf.APPLET_PATH, "7migz", "-c", "-l6", "-b", "63"], input=data, capture_output=True)
+    assert a.returncode == 0 and a.stdout == mz
+    d = subprocess.run([b200bgzf.APPLET_PATH, "7migz", "-d"], input=a.stdout, capture_output=True)
+    assert d.returncode == 0 and d.stdout == data
+    assert subprocess.run([b200bgzf.APPLET_PATH, "7migz", "-c", "-l6", "-b", "512"], input=data, capture_output=True).returncode != 0
+    if os.path.exists(ref_box):
+        # ... and our inflate takes what the reference's 7migz writes (64 KiB members here; its default 512 KiB members too)
+        for b in ("63", "512"):
+            rr = subprocess.run([ref_box, "7migz", "-c", "-l6", "-b", b], input=data, capture_output=True)
+            assert rr.returncode == 0 and codec.inflate(rr.stdout) == data
+    m = b200bgzf.MultiCodec([0, 0, 0])
+    try:
+        assert m.compress(data, 6, block_size=64512, flags=b200bgzf.FRAME_MIGZ) == mz
+    finally:
+        m.close()
+
+
 def test_verify_flag_checks_crc32_of_every_member(codec):
     """B200BGZF_VERIFY: CRC32 of the inflated payload against the trailer (the reference's decompress loop does not
     check it, applet/7bgzf.c:350-354): a flipped trailer byte is caught with the flag and ignored without."""
