@@ -48,7 +48,7 @@
 #define BG_MAX_TOKEN 258u
 #define BG_SLOT_BYTES 65536u  /* one output slot = the largest legal BGZF member */
 #define BG_CRC_WORDS 17u      /* CRC slice per thread, in 32-bit words (odd => conflict-free smem striding) */
-#define BG_MIN_LOOKUP 4       /* shortest match the chain search can return */
+#define BG_MIN_LOOKUP 3       /* shortest match the chain search can return (3 only where the hash window is 3 bytes: see bg_phase_settle) */
 
 /* ---- region B overlay (32 KiB): the hash heads during the build, then everything Huffman ---- */
 #define BG_B_LFREQ 0        /* u32[288] */
@@ -362,12 +362,19 @@ BG_HD void bg_phase_settle(const BgCtx &c, uint32_t t, uint32_t T)
     c.scal[BG_S_DEPTH] = c.scal[BG_S_NUSED] >= 80 && c.prm.opt_passes == 0 ? (uint32_t)c.prm.depth + ((uint32_t)c.prm.depth + 1) / 2 : (uint32_t)c.prm.depth;
     /* hash width follows the literal census alone (not the depth cap): cheap literals => only long matches pay */
     c.scal[BG_S_HBYTES] = bg_min_match_len(c.scal[BG_S_NUSED], 1000, n) >= 5 ? (uint32_t)c.prm.hlong : 4u;
+    /* Binary-looking blocks (3-byte matches pay: 80+ distinct byte values) at levels 6 and up hash THREE bytes, so that the
+     * chains also hold the 3-byte matches the reference finds with its hash3 table (hc_matchfinder.h:112-131,222-227).  Chain
+     * nodes that share only those 3 bytes with the position do not count against the depth (BG_DEEP_SCAN): the walk still
+     * reaches every node a 4-byte window would have chained.  Measured at level 6: an ELF binary -3.0 % (it was 4 % behind
+     * the reference), BAM-like records +-0.0 %; shallower walks (levels 2-5) lose on BAM-like data (+0.7 % at level 3): not done there. */
+    if (c.scal[BG_S_MINLEN] == 3 && c.prm.depth >= 8) c.scal[BG_S_HBYTES] = 3;
 }
 
 /* phase 4: hash every position that has a full hash window into prev[] */
 BG_HD uint32_t bg_hash(const uint32_t *dataw, uint32_t p, uint32_t hbytes)
 {
     uint32_t v = bg_ld32(dataw, p);
+    if (hbytes == 3) v &= 0xffffffu;
     uint32_t h = v * 0x1E35A7BDu;
     if (hbytes == 5)
         h ^= bg_ld8(dataw, p + 4) * 0x9E3779B1u;
@@ -474,9 +481,15 @@ BG_HD uint32_t bg_nearest(const BgCtx &c, uint32_t p, bool *deep, uint32_t *targ
     if (!bg_in_window(p, q)) return 0;
     const uint32_t *dw = c.dataw;
     uint32_t len = 3;
-    if (bg_ld32(dw, q) == bg_ld32(dw, p)) len = bg_match_len(dw, p, q, 4, maxl);
+    const bool h3 = c.scal[BG_S_HBYTES] == 3;
+    if (h3) {
+        len = 2;
+        if (((bg_ld32(dw, q) ^ bg_ld32(dw, p)) & 0xffffffu) == 0) len = bg_match_len(dw, p, q, 0, maxl);
+    } else if (bg_ld32(dw, q) == bg_ld32(dw, p)) {
+        len = bg_match_len(dw, p, q, 4, maxl);
+    }
     *deep = c.scal[BG_S_DEPTH] > 1 && len < (uint32_t)c.prm.nice && len < maxl && bg_in_window(p, c.prev[q]);
-    if (len <= 3) return 0;
+    if (len <= (h3 ? 2u : 3u)) return 0;
     const uint32_t r = bg_mw(len, p - q);
     if (bg_match_ok(r, c.scal[BG_S_MINLEN])) *target = p + len;
     return r;
@@ -538,18 +551,28 @@ BG_HD void bg_phase_search_todo(const BgCtx &c, uint32_t t, uint32_t T, uint32_t
     }
 }
 
+/* which of the 4 bytes ending just past the match to beat a candidate must share: all of them; with a 3-byte hash window
+ * and nothing to beat yet (no nearest match), the first three — a 3-byte match is a match there */
+BG_HD uint32_t bg_tail_mask(const BgCtx &c, uint32_t r1) { return c.scal[BG_S_HBYTES] == 3 && !r1 ? 0xffffffu : 0xffffffffu; }
+
 /* pass 2 for one position: chain candidates beyond the nearest that may beat it.  Calls push(q) for each. */
 #define BG_DEEP_SCAN(c, p, PUSH)                                                                     \
     do {                                                                                             \
         const uint32_t r1_ = (c).R[p];                                                               \
         const uint32_t b1_ = r1_ ? r1_ >> 16 : 3u;                                                   \
-        const uint32_t tail_ = bg_ld32((c).dataw, (p) + b1_ - 3u);                                   \
+        const uint32_t tmask_ = bg_tail_mask(c, r1_);                                                \
+        const uint32_t tail_ = bg_ld32((c).dataw, (p) + b1_ - 3u) & tmask_;                          \
         uint32_t q_ = (c).prev[(c).prev[p]];                                                         \
-        int depth_ = (int)(c).scal[BG_S_DEPTH] - 1;                                                  \
-        while (depth_ > 0 && bg_in_window(p, q_)) {                                                  \
-            if (bg_ld32((c).dataw, q_ + b1_ - 3u) == tail_) { PUSH(q_); }                            \
+        int depth_ = (int)(c).scal[BG_S_DEPTH] - 1, cap_ = 4 * depth_;                               \
+        const bool h3_ = (c).scal[BG_S_HBYTES] == 3;                                                 \
+        const uint32_t f4_ = bg_ld32((c).dataw, (p));                                                \
+        while (depth_ > 0 && cap_ > 0 && bg_in_window(p, q_)) {                                      \
+            if ((bg_ld32((c).dataw, q_ + b1_ - 3u) & tmask_) == tail_) { PUSH(q_); }                 \
+            /* 3-byte hash window: a node that shares only 3 bytes with p is looked at for free (up to 4x the depth in   \
+             * all), so that the nodes a 4-byte window would have chained are still all visited */                    \
+            if (!h3_ || bg_ld32((c).dataw, q_) == f4_) depth_--;                                     \
+            cap_--;                                                                                  \
             q_ = (c).prev[q_];                                                                       \
-            depth_--;                                                                                \
         }                                                                                            \
     } while (0)
 
@@ -559,7 +582,7 @@ BG_HD uint32_t bg_deep_extend(const BgCtx &c, uint32_t p, uint32_t q)
     uint32_t maxl = c.n - p;
     if (maxl > 258) maxl = 258;
     const uint32_t l = bg_match_len(c.dataw, p, q, 0, maxl);
-    return l >= 4 ? bg_mw(l, p - q) : 0u;
+    return l >= (c.scal[BG_S_HBYTES] == 3 ? 3u : 4u) ? bg_mw(l, p - q) : 0u;
 }
 
 /* sequential twin of the kernel's passes 2 and 3 */

@@ -308,13 +308,18 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
     uint32_t q = BG_NOPOS, b1 = 3, tail = 0;
     int depth = (int)c.scal[BG_S_DEPTH] - 1;
     const unsigned lt = (1u << lane) - 1u;
+    uint32_t tmask = 0xffffffffu;
     if (active) {
         const uint32_t r1 = __ldcg(c.R + p);
         b1 = r1 ? r1 >> 16 : 3u;
-        tail = bg_ld32(c.dataw, p + b1 - 3u);
+        tmask = bg_tail_mask(c, r1);
+        tail = bg_ld32(c.dataw, p + b1 - 3u) & tmask;
         q = c.prev[c.prev[p]];
     }
     bool live = active && depth > 0 && bg_in_window(p, q);
+    const bool h3 = c.scal[BG_S_HBYTES] == 3;                     /* (uniform) 3-byte hash window: see BG_DEEP_SCAN */
+    const uint32_t f4 = active ? bg_ld32(c.dataw, p) : 0u;
+    int cap = 4 * depth;
     while (__any_sync(0xffffffffu, live)) {
 #pragma unroll
         for (uint32_t k = 0; k < BG_SCAN_CHUNK_SHALLOW; k++) {
@@ -322,10 +327,11 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
             const uint32_t qc = q;
             if (live) {
                 const uint32_t qn = c.prev[q];
-                pass = bg_ld32(c.dataw, q + b1 - 3u) == tail;
-                depth--;
+                pass = (bg_ld32(c.dataw, q + b1 - 3u) & tmask) == tail;
+                if (!h3 || bg_ld32(c.dataw, q) == f4) depth--;
+                cap--;
                 q = qn;
-                live = depth > 0 && bg_in_window(p, q);
+                live = depth > 0 && cap > 0 && bg_in_window(p, q);
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
@@ -347,6 +353,7 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
                 const uint32_t r = __ldcg(c.R + p);
                 if ((r >> 16) > b1) {
                     b1 = r >> 16;
+                    tmask = 0xffffffffu;
                     uint32_t maxl = c.n - p;
                     if (maxl > 258u) maxl = 258u;
                     if (b1 >= maxl) live = false;
@@ -417,8 +424,9 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
     uint32_t word = own + parts * warp;
     const uint32_t wstep = parts * (BG_THREADS / 32u);
     uint32_t head = 0, tail = 0, cnt = 0;                          /* ring [head, tail), queue entries: warp-uniform */
-    uint32_t p = 0, q = BG_NOPOS, b1 = 3, tailw = 0;
-    int depth = 0;
+    uint32_t p = 0, q = BG_NOPOS, b1 = 3, tailw = 0, tmask = 0xffffffffu, f4 = 0;
+    int depth = 0, cap = 0;
+    const bool h3 = c.scal[BG_S_HBYTES] == 3;                     /* (uniform) 3-byte hash window: see BG_DEEP_SCAN */
     bool live = false;
     for (;;) {
         /* top the ring up to 32 or more waiting positions */
@@ -445,9 +453,12 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
                 p = ring[slot];
                 const uint32_t r1 = ringr[slot];
                 b1 = r1 ? r1 >> 16 : 3u;
-                tailw = bg_ld32(c.dataw, p + b1 - 3u);
+                tmask = bg_tail_mask(c, r1);
+                tailw = bg_ld32(c.dataw, p + b1 - 3u) & tmask;
+                f4 = bg_ld32(c.dataw, p);
                 q = c.prev[c.prev[p]];
                 depth = depth0;
+                cap = 4 * depth0;
                 live = depth > 0 && bg_in_window(p, q);
             }
             head += min(avail, (uint32_t)__popc(need));
@@ -461,10 +472,11 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
             const uint32_t qc = q;
             if (live) {
                 const uint32_t qn = c.prev[q];
-                pass = bg_ld32(c.dataw, q + b1 - 3u) == tailw;
-                depth--;
+                pass = (bg_ld32(c.dataw, q + b1 - 3u) & tmask) == tailw;
+                if (!h3 || bg_ld32(c.dataw, q) == f4) depth--;
+                cap--;
                 q = qn;
-                live = depth > 0 && bg_in_window(p, q);
+                live = depth > 0 && cap > 0 && bg_in_window(p, q);
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
@@ -486,6 +498,7 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
                 const uint32_t r = __ldcg(c.R + p);
                 if ((r >> 16) > b1) {
                     b1 = r >> 16;
+                    tmask = 0xffffffffu;
                     uint32_t maxl = c.n - p;
                     if (maxl > 258u) maxl = 258u;
                     if (b1 >= maxl) live = false;

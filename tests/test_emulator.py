@@ -120,3 +120,18 @@ def test_migz_framing_decodes_through_the_reference_7migz():
     if os.path.exists(box):
         r = subprocess.run([box, "7migz", "-d"], input=mz, capture_output=True)
         assert r.returncode == 0 and r.stdout == d
+
+
+@pytest.mark.parametrize("level", [6, 7, 8, 9])
+def test_size_on_an_executable_with_the_three_byte_hash_window(level):
+    """Off the benchmark corpora: an ELF binary (the reference's own multi-call binary, built by oracle/Makefile.ref).  Levels 6
+    and up hash three bytes on binary-looking blocks and stay within 3 % of the reference at the same level (levels 2-5 keep
+    the 4-byte window — BAM-like records would pay for the longer chains there — and are 4 % behind on such data: DESIGN.md)"""
+    import os
+    path = os.path.join(H.ROOT, "oracle", "_ref", "cielbox_ref")
+    if not (H.have_ref() and os.path.exists(path)):
+        pytest.skip("oracle/_ref not built")
+    d = open(path, "rb").read()
+    mine = len(H.emul_stream(d, level)) - 28
+    _, ref_sizes, _ = H.Ref(level).compress_stream(d, keep=False, threads=os.cpu_count() or 1)
+    assert mine <= 1.03 * sum(ref_sizes), (mine, sum(ref_sizes))

@@ -309,6 +309,22 @@ def test_multi_context_sharding_gives_the_single_gpu_stream(codec):
             m.close()
 
 
+@pytest.mark.parametrize("level", [1, 6, 7, 9, 11])
+def test_binary_corpus_three_byte_hash_window(codec, level):
+    """an ELF binary (oracle/_ref/cielbox_ref): bytes of the CPU run of the same algorithm, decodes through the reference decoder,
+    and — at the levels that hash three bytes on binary-looking blocks (6+) and at level 1 — within 3 % of the reference's size"""
+    path = os.path.join(H.ROOT, "oracle", "_ref", "cielbox_ref")
+    if not (H.have_ref() and os.path.exists(path)):
+        pytest.skip("oracle/_ref not built")
+    d = open(path, "rb").read()
+    got = codec.compress(d, level)
+    assert got == H.emul_stream(d, level)
+    rc, out, _ = H.Ref(6).inflate_stream(got)
+    assert rc == 0 and out == d and codec.inflate(got, flags=b200bgzf.VERIFY) == d
+    _, ref_sizes, _ = H.Ref(level).compress_stream(d, keep=False, threads=os.cpu_count() or 1)
+    assert len(got) - 28 <= 1.03 * sum(ref_sizes), (len(got), sum(ref_sizes))
+
+
 def test_migz_members_on_the_same_kernel(codec):
     """SURVEY 8(f) rank 3, compress side: MiGz framing (gzip subfield "MZ" + u32 DEFLATE size, applet/7migz.c:224-233) around
     the same per-block DEFLATE data.  Decodes through the reference's own 7migz -d, gzip, and our inflate; the DEFLATE

@@ -1,14 +1,16 @@
 #!/bin/bash
-# One GPU-box call that produces every measured artefact of a round under gpurun_out/ (then summarise here: tools/launch_summary.py, tools/ncu_summary.py, tools/sass_summary.py).
-#   gpurun --timeout 1500 -- 'bash tools/capture_round.sh r01'
-R=${1:-r01}; O=gpurun_out; mkdir -p $O
+# One GPU-box call that produces every measured artefact of a round under gpurun_out/ (then summarise here:
+# tools/launch_summary.py, tools/ncu_summary.py, tools/ncu_funcs.py, tools/sass_summary.py, tools/traffic_from_ncu.py).
+#   gpurun --timeout 1800 -- 'bash tools/capture_round.sh r02'
+R=${1:-r02}; O=gpurun_out; mkdir -p $O
 python bench.py --steps 5 --warmup 3 > $O/bench_$R.json 2> $O/bench_$R.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_${R}_reference.json 2>> $O/bench_$R.err
+python bench.py --level 12 --mib 1024 --steps 1 --warmup 3 > $O/bench_${R}_L12.json 2>> $O/bench_$R.err
+python bench.py --workload config5 > $O/bench_${R}_config5.json 2>> $O/bench_$R.err
 python tools/level_sweep.py 256 > $O/levels_$R.jsonl 2>> $O/bench_$R.err
+(for l in 1 6 9 12; do python tools/phase_profile.py $l $([ $l = 12 ] && echo 16 || echo 64) fastq; done; python tools/phase_profile.py 6 64 sam) > $O/phases_$R.txt 2>&1
 python tools/pcie_probe.py > $O/pcie_$R.txt 2>&1
 python tools/e2e_probe.py 1024 >> $O/pcie_$R.txt 2>&1
-./build/datagen sam 268435456 2 > /tmp/sam256.bin
-( export BGZF_METHOD=libdeflate6; for t in 1 4 8 16 64; do ./build/hook_mt 7bgzf_b200/7bgzf.so $t /tmp/sam256.bin 4; done; echo one SM per call; for t in 1 16; do B200BGZF_SPLIT=1 ./build/hook_mt 7bgzf_b200/7bgzf.so $t /tmp/sam256.bin 4; done; echo reference; for t in 1 16; do ./build/hook_mt oracle/_ref/7bgzf_ref.so $t /tmp/sam256.bin; done ) > $O/hook_$R.txt 2>&1
 bash tools/applet_compare.sh 1024 > $O/applet_$R.txt 2>&1
 # launch list of the bench command (shares per kernel; times under ncu are cold-cache and serialised)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$R.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_bench_$R.log 2>&1
