@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib7bgzf_b200.so")
+LIB_PATH = os.environ.get("B200BGZF_LIB_PATH") or os.path.join(_HERE, "lib7bgzf_b200.so")   # (the checked build: make checked)
 HOOK_PATH = os.path.join(_HERE, "7bgzf.so")
 APPLET_PATH = os.path.join(_HERE, "7bgzf")
 

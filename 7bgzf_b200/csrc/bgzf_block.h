@@ -28,12 +28,23 @@
 #define BGZF_BLOCK_H
 
 #include <stdint.h>
+#include <stdio.h>
 
 #if defined(__CUDACC__)
 #define BG_HD __host__ __device__ __forceinline__
 #else
 #define BG_HD static inline
 #endif
+/* Bounds asserts of the checked build (`make checked`: -DBG_CHECK, build/checked/lib7bgzf_b200.so).  compute-sanitizer is not
+ * available on the GPU pool, so the indices this round's code computes (bitmaps, queues, rings, scratch words, chunk order,
+ * compaction offsets) are asserted in a separate build that the GPU tests can be pointed at (B200BGZF_LIB_PATH).  A failed
+ * assert traps: the launch fails and the test with it. */
+#if defined(BG_CHECK) && defined(__CUDA_ARCH__)
+#define BG_ASSERT(cond) do { if (!(cond)) { printf("BG_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define BG_ASSERT(cond) do { } while (0)
+#endif
+
 
 #define BG_MAX_BLOCK 65536u   /* largest payload a block may carry (applet -@1 uses 0x10000, htslib 0xff00) */
 #define BG_DATA_BYTES (BG_MAX_BLOCK + 32u)
@@ -1765,12 +1776,14 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
     }
     for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
         const uint32_t ch = c.perm ? c.perm[i] : i;
+        BG_ASSERT(ch < BG_MAX_CHUNKS);
         if (ch * BG_CHUNK >= n) continue;
         uint32_t p = entry[ch];
         if (p == BG_NOPOS) continue;
         p += ch * BG_CHUNK;
         uint32_t end = ch * BG_CHUNK + BG_CHUNK;
         if (end > n) end = n;
+        BG_ASSERT(p < end && (base + hdrbits + cbits[ch]) / 8u < BG_SLOT_BYTES);
         BgWriter w;
         bg_w_init(w, c.out, base + hdrbits + cbits[ch]);
         while (p < end) {

@@ -219,6 +219,7 @@ __device__ __forceinline__ void mark_remote(uint32_t *local_word, uint32_t owner
 template <bool SPLIT>
 __device__ __forceinline__ void mark_bits(uint32_t *mark, uint32_t word, uint32_t bits, uint32_t own, uint32_t parts)
 {
+    BG_ASSERT(word < 2064u);
     if (!SPLIT) {
         atomicOr(&mark[word], bits);
         return;
@@ -254,6 +255,7 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
     if (t == 0 && own == 0) atomicOr(&mark[0], 1u);
     for (uint32_t p0 = t - lane; p0 < n; p0 += BG_THREADS) {       /* (warp-uniform trip count) */
         const uint32_t word = p0 >> 5;
+        BG_ASSERT(word < 2048u);
         if (SPLIT && word % parts != own) continue;
         const uint32_t p = p0 + lane;
         bool deep = false;
@@ -292,6 +294,7 @@ __device__ __forceinline__ void drain_queue(const BgCtx &c, const uint32_t *queu
     if (lane < count) {
         const uint32_t e = queue[from + lane];
         const uint32_t p = e >> 16, q = e & 0xffffu;
+        BG_ASSERT(p < c.n && q < p && p - q <= 32768u);
         const uint32_t v = bg_deep_extend(c, p, q);
         if (v) {
             atomicMax(&c.R[p], v);
@@ -335,6 +338,7 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
+                BG_ASSERT(cnt + __popc(m) <= BG_QUEUE_WORDS_SHALLOW);
                 if (pass) queue[cnt + __popc(m & lt)] = (p << 16) | qc;
                 cnt += __popc(m);
             }
@@ -378,6 +382,7 @@ __device__ __forceinline__ void search_deep_batches(const BgCtx &c, uint32_t t, 
     for (uint32_t i = own + parts * warp; i < nwords; i += parts * (BG_THREADS / 32u)) {
         const uint32_t w = todo[i];
         if (w == 0) continue;
+        BG_ASSERT(fill + __popc(w) <= 64u);
         if ((w >> lane) & 1u) gather[fill + __popc(w & lt)] = (uint16_t)(i * 32u + lane);
         fill += __popc(w);
         __syncwarp();
@@ -433,8 +438,10 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
         while (tail - head < 32u && word < nwords) {
             const uint32_t w = todo[word];
             if (w) {
+                BG_ASSERT(tail - head + __popc(w) <= 64u);
                 if ((w >> lane) & 1u) {
                     const uint32_t slot = (tail + __popc(w & lt)) & 63u, pos = word * 32u + lane;
+                    BG_ASSERT(pos < c.n);
                     ring[slot] = (uint16_t)pos;
                     cp_async4((void *)(ringr + slot), c.R + pos);
                 }
@@ -480,6 +487,7 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
+                BG_ASSERT(cnt + __popc(m) <= BG_QUEUE_WORDS);
                 if (pass) queue[cnt + __popc(m & lt)] = (p << 16) | qc;
                 cnt += __popc(m);
             }
@@ -672,6 +680,7 @@ __device__ __forceinline__ void chunk_order_scan(const BgCtx &c, uint32_t t)
 __device__ __forceinline__ void chunk_order_place(const BgCtx &c, uint32_t t, uint32_t cls, uint32_t rank)
 {
     const uint32_t *cnt = (const uint32_t *)(c.regb + BG_B_CLASSCNT);
+    BG_ASSERT(cls < 8u && cnt[cls * 32u + (t >> 5)] + rank < BG_MAX_CHUNKS);
     ((uint16_t *)(c.regb + BG_B_PERM))[cnt[cls * 32u + (t >> 5)] + rank] = (uint16_t)t;
 }
 
@@ -756,8 +765,10 @@ __device__ __forceinline__ void fused_compaction(const BgzfCompressArgs &a, uint
     if (t == 0) *a.gather_total = carry;
     __syncthreads();
     const uint32_t grp = t >> 8, gt = t & 255u;
-    for (uint32_t b = grp; b < a.nblocks; b += BG_THREADS / 256u)
+    for (uint32_t b = grp; b < a.nblocks; b += BG_THREADS / 256u) {
+        BG_ASSERT(__ldcg(a.out_len + b) <= BG_SLOT_BYTES && a.gather_off[b] + __ldcg(a.out_len + b) <= carry);
         gather_member((const uint32_t *)(a.slots + (size_t)b * BG_SLOT_BYTES), __ldcg(a.out_len + b), a.gather_out + a.gather_off[b], gt, 256u);
+    }
 }
 
 #define PROF_MARK(i)                                                        \

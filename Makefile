@@ -40,6 +40,13 @@ $(PKG)/7bgzf: $(OBJ)/applet_7bgzf.o $(PKG)/lib7bgzf_b200.so
 $(PKG)/7migz: $(PKG)/7bgzf
 	ln -sf 7bgzf $@
 
+# the same library with the bounds asserts compiled in (BG_ASSERT, csrc/bgzf_block.h): point the GPU tests at it with
+#   B200BGZF_LIB_PATH=build/checked/lib7bgzf_b200.so python -m pytest tests -m gpu
+checked: build/checked/lib7bgzf_b200.so
+build/checked/lib7bgzf_b200.so: $(CU_SRCS) $(HDRS) $(OBJ)/method.o $(OBJ)/multi.o
+	@mkdir -p build/checked
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DBG_CHECK -shared -o $@ $(CU_SRCS) $(OBJ)/method.o $(OBJ)/multi.o -Xlinker --version-script=$(HOST)/exports.map -lpthread
+
 # ---- test / bench infrastructure (never linked into the product) ----
 testlibs: build/libdatagen.so build/libemul.so build/datagen build/hook_mt oracle/liboracle.so
 
@@ -60,4 +67,4 @@ oracle/liboracle.so: $(wildcard oracle/*.c)
 clean:
 	rm -rf build $(PKG)/*.so $(PKG)/7bgzf $(PKG)/7migz oracle/liboracle.so
 
-.PHONY: all testlibs clean
+.PHONY: all testlibs clean checked

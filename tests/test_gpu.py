@@ -644,3 +644,21 @@ def test_full_size_near_optimal_256mib_through_reference_decoder(codec):
     _, ref_sizes, _ = H.Ref(12).compress_stream(ctypes.string_at(host.data_ptr(), sample), keep=False, threads=os.cpu_count() or 1)
     ours = sum(m[1] for m in H.members(ctypes.string_at(out.data_ptr(), clen))[: sample // H.BLOCK])
     assert ours <= 1.03 * sum(ref_sizes), (ours, sum(ref_sizes))
+
+
+def test_checked_build_bounds_asserts_stay_silent():
+    """compute-sanitizer is not available on the GPU pool; instead the indices the kernels compute (search bitmaps, candidate
+    queues, position rings, scratch words, chunk order, compaction offsets) are asserted in a separate build (`make checked`,
+    -DBG_CHECK).  The parity tests that exercise those paths are run once more against that library: an assert that fires
+    traps, the launch fails, and so does the test."""
+    import sys
+    lib = os.path.join(H.ROOT, "build", "checked", "lib7bgzf_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("build/checked missing: make checked")
+    env = dict(os.environ, B200BGZF_LIB_PATH=lib)
+    sel = "edge_inputs or whole_stream or binary_corpus or near_optimal_block or migz or multi_context or odd_block_sizes or bam_like or device_index"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(H.ROOT, "tests", "test_gpu.py"), "-q", "-x", "-m", "gpu", "-k", sel,
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=H.ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "BG_ASSERT failed" not in r.stdout + r.stderr
+    assert " passed" in r.stdout
