@@ -1,0 +1,50 @@
+"""Differential fuzz of the compress kernel against the CPU run of the same block algorithm (tests/model/emul.cpp):
+random mixtures of text, runs, periodic data, noise and synthetic records, random block sizes and levels.
+  python tools/compress_fuzz.py [cases] [seed]     (GPU box; prints one summary line)"""
+import os, random, sys
+root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, os.path.join(root, "tests")); sys.path.insert(0, os.path.join(root, "7bgzf_b200"))
+import helpers as H, b200bgzf
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
+fq, sam, bam = H.synth("fastq", 1 << 20), H.synth("sam", 1 << 20), H.bamlike(1 << 19)
+elf = open(os.path.join(root, "oracle", "_ref", "cielbox_ref"), "rb").read() if os.path.exists(os.path.join(root, "oracle", "_ref", "cielbox_ref")) else bam
+
+
+def piece():
+    k = rnd.randrange(9)
+    n = rnd.choice([1, 3, 17, 100, 1000, 5000, 20000, 70000])
+    if k == 0: return bytes(rnd.randrange(256) for _ in range(min(n, 4000)))
+    if k == 1: return bytes([rnd.randrange(256)]) * n
+    if k == 2:
+        p = bytes(rnd.randrange(256) for _ in range(rnd.choice([2, 3, 4, 5, 7, 8, 31, 32, 33, 255, 258, 259])))
+        return (p * (n // len(p) + 1))[:n]
+    src = (fq, sam, bam, elf)[rnd.randrange(4)]
+    o = rnd.randrange(max(1, len(src) - n))
+    if k == 3:
+        b = bytearray(src[o : o + n])
+        for _ in range(max(1, n // 50)): b[rnd.randrange(len(b))] = rnd.randrange(256)
+        return bytes(b)
+    if k == 4: return bytes(rnd.choice(b"ACGT") for _ in range(min(n, 30000)))
+    return src[o : o + n]
+
+
+c = b200bgzf.Codec(0)
+bad = 0
+total = 0
+for i in range(cases):
+    data = b"".join(piece() for _ in range(rnd.randrange(1, 8)))[: 400000]
+    level = rnd.choice([1, 2, 3, 4, 5, 6, 6, 6, 7, 8, 9, 10, 12]) if len(data) < 150000 else rnd.choice([1, 3, 6, 6, 7, 9])
+    bs = rnd.choice([0xFF00, 0xFF00, 0x10000 - 64, 4099, 32768, 65535, 1000, 257])
+    if len(data) // bs > 400: bs = 0xFF00
+    got = c.compress(data, level, block_size=bs)
+    want = H.emul_stream(data, level, block=bs)
+    total += len(data)
+    if got != want:
+        bad += 1
+        print(f"case {i}: level {level} block {bs} len {len(data)}: GPU stream differs from the emulator's")
+    if H.gunzip(got) != data or c.inflate(got) != data:
+        bad += 1
+        print(f"case {i}: level {level} block {bs} len {len(data)}: round trip failed")
+print(f"{cases} cases, {total >> 20} MiB: {bad} mismatches")
+sys.exit(1 if bad else 0)
