@@ -385,7 +385,7 @@ BG_HD void bg_phase_settle(const BgCtx &c, uint32_t t, uint32_t T)
 BG_HD uint32_t bg_hash(const uint32_t *dataw, uint32_t p, uint32_t hbytes)
 {
     uint32_t v = bg_ld32(dataw, p);
-    if (hbytes == 3) v &= 0xffffffu;
+    if (hbytes == 3) v &= 0xffffffu;        /* (callers in a loop pass a loop-invariant hbytes: the test is hoisted or predicated) */
     uint32_t h = v * 0x1E35A7BDu;
     if (hbytes == 5)
         h ^= bg_ld8(dataw, p + 4) * 0x9E3779B1u;
@@ -481,7 +481,22 @@ BG_HD bool bg_match_ok(uint32_t r, uint32_t minlen);
 
 /* pass 1 for one position: match word of the nearest candidate (0: none of length >= 4); *deep: a deep search may
  * improve on it; *target: where a greedy step from p lands */
-BG_HD uint32_t bg_nearest(const BgCtx &c, uint32_t p, bool *deep, uint32_t *target)
+struct BgSearchPrm {      /* the block's search scalars, read once per phase (not once per position) */
+    uint32_t depth, nice, minlen;
+    bool h3;              /* 3-byte hash window (binary-looking block, level 6 and up) */
+};
+BG_HD BgSearchPrm bg_search_prm(const BgCtx &c)
+{
+    BgSearchPrm s;
+    s.depth = c.scal[BG_S_DEPTH];
+    s.nice = (uint32_t)c.prm.nice;
+    s.minlen = c.scal[BG_S_MINLEN];
+    s.h3 = c.scal[BG_S_HBYTES] == 3;
+    return s;
+}
+
+template <bool H3>
+BG_HD uint32_t bg_nearest_t(const BgCtx &c, const BgSearchPrm &sp, uint32_t p, bool *deep, uint32_t *target)
 {
     uint32_t maxl = c.n - p;
     if (maxl > 258) maxl = 258;
@@ -492,18 +507,21 @@ BG_HD uint32_t bg_nearest(const BgCtx &c, uint32_t p, bool *deep, uint32_t *targ
     if (!bg_in_window(p, q)) return 0;
     const uint32_t *dw = c.dataw;
     uint32_t len = 3;
-    const bool h3 = c.scal[BG_S_HBYTES] == 3;
-    if (h3) {
+    if (H3) {
         len = 2;
         if (((bg_ld32(dw, q) ^ bg_ld32(dw, p)) & 0xffffffu) == 0) len = bg_match_len(dw, p, q, 0, maxl);
     } else if (bg_ld32(dw, q) == bg_ld32(dw, p)) {
         len = bg_match_len(dw, p, q, 4, maxl);
     }
-    *deep = c.scal[BG_S_DEPTH] > 1 && len < (uint32_t)c.prm.nice && len < maxl && bg_in_window(p, c.prev[q]);
-    if (len <= (h3 ? 2u : 3u)) return 0;
+    *deep = sp.depth > 1 && len < sp.nice && len < maxl && bg_in_window(p, c.prev[q]);
+    if (len <= (H3 ? 2u : 3u)) return 0;
     const uint32_t r = bg_mw(len, p - q);
-    if (bg_match_ok(r, c.scal[BG_S_MINLEN])) *target = p + len;
+    if (bg_match_ok(r, sp.minlen)) *target = p + len;
     return r;
+}
+BG_HD uint32_t bg_nearest(const BgCtx &c, const BgSearchPrm &sp, uint32_t p, bool *deep, uint32_t *target)
+{
+    return sp.h3 ? bg_nearest_t<true>(c, sp, p, deep, target) : bg_nearest_t<false>(c, sp, p, deep, target);
 }
 
 /* ---- near-optimal class (levels 10-12): the same passes, over EVERY position that has a second candidate, and besides the
@@ -534,10 +552,11 @@ BG_HD void bg_phase_search1(const BgCtx &c, uint32_t t, uint32_t T)
 {
     uint32_t *elig = (uint32_t *)(c.regb + BG_B_TODO), *mark = (uint32_t *)(c.regb + BG_B_MARK);
     if (t == 0) bg_or32(&mark[0], 1u);
+    const BgSearchPrm sp = bg_search_prm(c);
     for (uint32_t p = t; p < c.n; p += T) {
         bool deep;
         uint32_t target;
-        c.R[p] = bg_nearest(c, p, &deep, &target);
+        c.R[p] = bg_nearest(c, sp, p, &deep, &target);
         if (c.prm.opt_passes > 0) bg_cand_init(c, p, c.R[p]);
         if (deep) bg_or32(&elig[p >> 5], 1u << (p & 31u));
         bg_or32(&mark[target >> 5], 1u << (target & 31u));
@@ -564,18 +583,18 @@ BG_HD void bg_phase_search_todo(const BgCtx &c, uint32_t t, uint32_t T, uint32_t
 
 /* which of the 4 bytes ending just past the match to beat a candidate must share: all of them; with a 3-byte hash window
  * and nothing to beat yet (no nearest match), the first three — a 3-byte match is a match there */
-BG_HD uint32_t bg_tail_mask(const BgCtx &c, uint32_t r1) { return c.scal[BG_S_HBYTES] == 3 && !r1 ? 0xffffffu : 0xffffffffu; }
+BG_HD uint32_t bg_tail_mask(bool h3, uint32_t r1) { return h3 && !r1 ? 0xffffffu : 0xffffffffu; }
 
 /* pass 2 for one position: chain candidates beyond the nearest that may beat it.  Calls push(q) for each. */
 #define BG_DEEP_SCAN(c, p, PUSH)                                                                     \
     do {                                                                                             \
         const uint32_t r1_ = (c).R[p];                                                               \
         const uint32_t b1_ = r1_ ? r1_ >> 16 : 3u;                                                   \
-        const uint32_t tmask_ = bg_tail_mask(c, r1_);                                                \
+        const bool h3_ = (c).scal[BG_S_HBYTES] == 3;                                                 \
+        const uint32_t tmask_ = bg_tail_mask(h3_, r1_);                                              \
         const uint32_t tail_ = bg_ld32((c).dataw, (p) + b1_ - 3u) & tmask_;                          \
         uint32_t q_ = (c).prev[(c).prev[p]];                                                         \
         int depth_ = (int)(c).scal[BG_S_DEPTH] - 1, cap_ = 4 * depth_;                               \
-        const bool h3_ = (c).scal[BG_S_HBYTES] == 3;                                                 \
         const uint32_t f4_ = bg_ld32((c).dataw, (p));                                                \
         while (depth_ > 0 && cap_ > 0 && bg_in_window(p, q_)) {                                      \
             if ((bg_ld32((c).dataw, q_ + b1_ - 3u) & tmask_) == tail_) { PUSH(q_); }                 \
@@ -588,12 +607,12 @@ BG_HD uint32_t bg_tail_mask(const BgCtx &c, uint32_t r1) { return c.scal[BG_S_HB
     } while (0)
 
 /* pass 3 for one queued candidate: its full length, merged into R[p] (the kernel: atomicMax) */
-BG_HD uint32_t bg_deep_extend(const BgCtx &c, uint32_t p, uint32_t q)
+BG_HD uint32_t bg_deep_extend(const BgCtx &c, bool h3, uint32_t p, uint32_t q)
 {
     uint32_t maxl = c.n - p;
     if (maxl > 258) maxl = 258;
     const uint32_t l = bg_match_len(c.dataw, p, q, 0, maxl);
-    return l >= (c.scal[BG_S_HBYTES] == 3 ? 3u : 4u) ? bg_mw(l, p - q) : 0u;
+    return l >= (h3 ? 3u : 4u) ? bg_mw(l, p - q) : 0u;
 }
 
 /* sequential twin of the kernel's passes 2 and 3 */
@@ -602,7 +621,7 @@ BG_HD void bg_phase_search2(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t *todo = (const uint32_t *)(c.regb + BG_B_TODO);
     for (uint32_t p = t; p < c.n; p += T) {
         if (!((todo[p >> 5] >> (p & 31u)) & 1u)) continue;
-#define BG_PUSH_SEQ(q) do { const uint32_t v_ = bg_deep_extend(c, p, (q)); if (v_ > c.R[p]) c.R[p] = v_; \
+#define BG_PUSH_SEQ(q) do { const uint32_t v_ = bg_deep_extend(c, c.scal[BG_S_HBYTES] == 3, p, (q)); if (v_ > c.R[p]) c.R[p] = v_; \
                             if (v_ && c.prm.opt_passes > 0) { uint32_t *cd_ = c.cand + 4u * p + bg_off_bin(bg_mw_off(v_)); if (v_ > *cd_) *cd_ = v_; } } while (0)
         /* (the tail bytes compared are those of the NEAREST match for every candidate: R[p] is read once, before the walk) */
         BG_DEEP_SCAN(c, p, BG_PUSH_SEQ);
@@ -1787,29 +1806,37 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
         BgWriter w;
         bg_w_init(w, c.out, base + hdrbits + cbits[ch]);
         while (p < end) {
+            /* every turn ends in the same two puts (the second one may be empty): the three kinds of token differ only in how
+             * the two (value, bits) pairs are made, so the lanes of a warp are together again for the packing */
+            uint32_t v1, n1, v2 = 0, n2 = 0;
+            const uint32_t sc = c.stepcode[p];
             if ((p & 3u) == 0 && p + 4 <= end && *(const uint32_t *)(c.stepcode + p) == 0) {
                 /* four literals in a row: two puts of two code words each (<= 30 bits) */
                 const uint32_t d = c.dataw[p >> 2];
                 const uint32_t e0 = littab[d & 0xffu], e1 = littab[(d >> 8) & 0xffu], e2 = littab[(d >> 16) & 0xffu], e3 = littab[d >> 24];
                 const uint32_t l0 = e0 >> 24, l2 = e2 >> 24;
-                bg_w_put(w, (e0 & 0xffffffu) | ((e1 & 0xffffffu) << l0), l0 + (e1 >> 24));
-                bg_w_put(w, (e2 & 0xffffffu) | ((e3 & 0xffffffu) << l2), l2 + (e3 >> 24));
+                v1 = (e0 & 0xffffffu) | ((e1 & 0xffffffu) << l0);
+                n1 = l0 + (e1 >> 24);
+                v2 = (e2 & 0xffffffu) | ((e3 & 0xffffffu) << l2);
+                n2 = l2 + (e3 >> 24);
                 p += 4;
-                continue;
-            }
-            uint32_t sc = c.stepcode[p];
-            if (sc == 0) {
+            } else if (sc == 0) {
                 const uint32_t e = littab[bg_ld8(c.dataw, p)];
-                bg_w_put(w, e & 0xffffffu, e >> 24);
+                v1 = e & 0xffffffu;
+                n1 = e >> 24;
                 p++;
             } else {
                 uint32_t len = sc == 255 ? (c.R[p] >> 16) : sc + 2, nb, ex;
                 const uint32_t el = lentab[len];
-                bg_w_put(w, el & 0xffffffu, el >> 24);
+                v1 = el & 0xffffffu;
+                n1 = el >> 24;
                 const uint32_t eo = offtab[bg_off_slot((uint32_t)c.offarr[p >> 1] + 1, &nb, &ex)];
-                bg_w_put(w, (eo & 0xffffffu) | (ex << (eo >> 24)), (eo >> 24) + nb);
+                v2 = (eo & 0xffffffu) | (ex << (eo >> 24));
+                n2 = (eo >> 24) + nb;
                 p += len;
             }
+            bg_w_put(w, v1, n1);
+            bg_w_put(w, v2, n2);
         }
         bg_w_flush(w);
     }

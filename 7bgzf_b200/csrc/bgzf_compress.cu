@@ -237,17 +237,18 @@ __device__ __forceinline__ void mark_bits(uint32_t *mark, uint32_t word, uint32_
 /* pass 1: nearest-candidate match of every position; landing marks and eligibility bits with one ballot per 32 positions.
  * SPLIT: a cluster shares ONE block; CTA `own` of `parts` takes every parts-th group of 32 positions, and a landing
  * mark goes to the bitmap of the CTA that owns the landing position's group (it alone reads that word afterwards). */
-template <bool SPLIT>
-__device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
+template <bool SPLIT, bool H3>
+__device__ __forceinline__ void search_nearest_t(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
     const uint32_t n = c.n, lane = t & 31u;
     uint32_t *elig = (uint32_t *)(c.regb + BG_B_TODO), *mark = (uint32_t *)(c.regb + BG_B_MARK);
-    if (c.scal[BG_S_DEPTH] <= 1) {                                  /* depth 1 (level 1): the nearest candidate is the whole search */
+    const BgSearchPrm sp = bg_search_prm(c);
+    if (sp.depth <= 1) {                                            /* depth 1 (level 1): the nearest candidate is the whole search */
         for (uint32_t p = t; p < n; p += BG_THREADS) {
             if (SPLIT && (p >> 5) % parts != own) continue;
             bool deep;
             uint32_t target;
-            c.R[p] = bg_nearest(c, p, &deep, &target);
+            c.R[p] = bg_nearest_t<H3>(c, sp, p, &deep, &target);
         }
         return;
     }
@@ -261,7 +262,7 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
         bool deep = false;
         uint32_t target = p + 1, r = 0;
         if (p < n) {
-            r = bg_nearest(c, p, &deep, &target);
+            r = bg_nearest_t<H3>(c, sp, p, &deep, &target);
             c.R[p] = r;
         }
         if (opt) {
@@ -287,15 +288,23 @@ __device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint3
     }
 }
 
+template <bool SPLIT>
+__device__ __forceinline__ void search_nearest(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
+{
+    if (c.scal[BG_S_HBYTES] == 3) search_nearest_t<SPLIT, true>(c, t, own, parts);      /* (uniform for the CTA) */
+    else search_nearest_t<SPLIT, false>(c, t, own, parts);
+}
+
 /* pass 3: up to 32 queued candidates, one per lane: full extension, merged into the position's match word (near-optimal
  * class: also into the word of the candidate's offset range) */
+template <bool H3>
 __device__ __forceinline__ void drain_queue(const BgCtx &c, const uint32_t *queue, uint32_t from, uint32_t count, uint32_t lane)
 {
     if (lane < count) {
         const uint32_t e = queue[from + lane];
         const uint32_t p = e >> 16, q = e & 0xffffu;
         BG_ASSERT(p < c.n && q < p && p - q <= 32768u);
-        const uint32_t v = bg_deep_extend(c, p, q);
+        const uint32_t v = bg_deep_extend(c, H3, p, q);
         if (v) {
             atomicMax(&c.R[p], v);
             if (c.cand) atomicMax(&c.cand[4u * p + bg_off_bin(p - q)], v);
@@ -306,6 +315,7 @@ __device__ __forceinline__ void drain_queue(const BgCtx &c, const uint32_t *queu
 /* pass 2 for a batch of todo positions (one per lane): walk the chain beyond the nearest candidate; candidates that agree on
  * the 4 bytes ending just past the nearest match go to the warp's queue (one ballot per chain step places them), which is
  * drained whenever it holds a full batch.  cnt = entries waiting in the queue (warp-uniform, < 32 on entry and on exit). */
+template <bool H3>
 __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint32_t &cnt, uint32_t p, bool active, uint32_t lane)
 {
     uint32_t q = BG_NOPOS, b1 = 3, tail = 0;
@@ -315,13 +325,12 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
     if (active) {
         const uint32_t r1 = __ldcg(c.R + p);
         b1 = r1 ? r1 >> 16 : 3u;
-        tmask = bg_tail_mask(c, r1);
+        tmask = bg_tail_mask(H3, r1);
         tail = bg_ld32(c.dataw, p + b1 - 3u) & tmask;
         q = c.prev[c.prev[p]];
     }
     bool live = active && depth > 0 && bg_in_window(p, q);
-    const bool h3 = c.scal[BG_S_HBYTES] == 3;                     /* (uniform) 3-byte hash window: see BG_DEEP_SCAN */
-    const uint32_t f4 = active ? bg_ld32(c.dataw, p) : 0u;
+    const uint32_t f4 = H3 && active ? bg_ld32(c.dataw, p) : 0u;   /* 3-byte hash window: see BG_DEEP_SCAN */
     int cap = 4 * depth;
     while (__any_sync(0xffffffffu, live)) {
 #pragma unroll
@@ -331,10 +340,10 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
             if (live) {
                 const uint32_t qn = c.prev[q];
                 pass = (bg_ld32(c.dataw, q + b1 - 3u) & tmask) == tail;
-                if (!h3 || bg_ld32(c.dataw, q) == f4) depth--;
-                cap--;
+                if (!H3 || bg_ld32(c.dataw, q) == f4) depth--;
+                if (H3) cap--;
                 q = qn;
-                live = depth > 0 && cap > 0 && bg_in_window(p, q);
+                live = depth > 0 && (!H3 || cap > 0) && bg_in_window(p, q);
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
@@ -347,7 +356,7 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
             __syncwarp();
             do {
                 cnt -= 32u;
-                drain_queue(c, queue, cnt, 32u, lane);
+                drain_queue<H3>(c, queue, cnt, 32u, lane);
             } while (cnt >= 32u);
             __syncwarp();
             /* some of this position's candidates may have been measured by now: test the rest of the chain against the longer
@@ -368,6 +377,7 @@ __device__ __forceinline__ void deep_batch(const BgCtx &c, uint32_t *queue, uint
     }
 }
 
+template <bool H3>
 __device__ __forceinline__ void search_deep_batches(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
     const uint32_t lane = t & 31u, warp = t >> 5;
@@ -392,13 +402,13 @@ __device__ __forceinline__ void search_deep_batches(const BgCtx &c, uint32_t t, 
             __syncwarp();
             if (lane + 32u < fill) gather[lane] = (uint16_t)rest;
             fill -= 32u;
-            deep_batch(c, queue, cnt, p, true, lane);
+            deep_batch<H3>(c, queue, cnt, p, true, lane);
         }
     }
     __syncwarp();
-    if (fill) deep_batch(c, queue, cnt, lane < fill ? gather[lane] : 0u, lane < fill, lane);
+    if (fill) deep_batch<H3>(c, queue, cnt, lane < fill ? gather[lane] : 0u, lane < fill, lane);
     __syncwarp();
-    drain_queue(c, queue, 0u, cnt, lane);
+    drain_queue<H3>(c, queue, 0u, cnt, lane);
 }
 
 __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src)
@@ -414,6 +424,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
  * has to beat — is fetched into the ring with cp.async when the position enters it, a turn or more before a lane needs it.
  * Candidates that agree with the position on the 4 bytes ending just past the match to beat are placed on the warp's queue
  * by one ballot per chain step; the queue is drained whenever it holds a full batch of 32 (pass 3). */
+template <bool H3>
 __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t own, uint32_t parts)
 {
     const uint32_t lane = t & 31u, warp = t >> 5;
@@ -431,7 +442,6 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
     uint32_t head = 0, tail = 0, cnt = 0;                          /* ring [head, tail), queue entries: warp-uniform */
     uint32_t p = 0, q = BG_NOPOS, b1 = 3, tailw = 0, tmask = 0xffffffffu, f4 = 0;
     int depth = 0, cap = 0;
-    const bool h3 = c.scal[BG_S_HBYTES] == 3;                     /* (uniform) 3-byte hash window: see BG_DEEP_SCAN */
     bool live = false;
     for (;;) {
         /* top the ring up to 32 or more waiting positions */
@@ -460,9 +470,9 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
                 p = ring[slot];
                 const uint32_t r1 = ringr[slot];
                 b1 = r1 ? r1 >> 16 : 3u;
-                tmask = bg_tail_mask(c, r1);
+                tmask = bg_tail_mask(H3, r1);
                 tailw = bg_ld32(c.dataw, p + b1 - 3u) & tmask;
-                f4 = bg_ld32(c.dataw, p);
+                if (H3) f4 = bg_ld32(c.dataw, p);
                 q = c.prev[c.prev[p]];
                 depth = depth0;
                 cap = 4 * depth0;
@@ -480,10 +490,10 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
             if (live) {
                 const uint32_t qn = c.prev[q];
                 pass = (bg_ld32(c.dataw, q + b1 - 3u) & tmask) == tailw;
-                if (!h3 || bg_ld32(c.dataw, q) == f4) depth--;
-                cap--;
+                if (!H3 || bg_ld32(c.dataw, q) == f4) depth--;
+                if (H3) cap--;
                 q = qn;
-                live = depth > 0 && cap > 0 && bg_in_window(p, q);
+                live = depth > 0 && (!H3 || cap > 0) && bg_in_window(p, q);
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
@@ -496,7 +506,7 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
             __syncwarp();
             do {
                 cnt -= 32u;
-                drain_queue(c, queue, cnt, 32u, lane);
+                drain_queue<H3>(c, queue, cnt, 32u, lane);
             } while (cnt >= 32u);
             __syncwarp();
             /* some of this position's candidates may have been measured by now: test the rest of the chain against the longer
@@ -516,7 +526,7 @@ __device__ __forceinline__ void search_deep(const BgCtx &c, uint32_t t, uint32_t
         }
     }
     __syncwarp();
-    drain_queue(c, queue, 0u, cnt, lane);
+    drain_queue<H3>(c, queue, 0u, cnt, lane);
 }
 
 __device__ __forceinline__ uint32_t cluster_rank()
@@ -903,8 +913,14 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
                 bg_phase_search_todo(c, t, T, crank, csize);
                 __syncthreads();
                 /* shallow chains (levels 2-7): 32 positions side by side; deep ones: lanes refill themselves */
-                if (c.scal[BG_S_DEPTH] <= 24u) search_deep_batches(c, t, crank, csize);
-                else search_deep(c, t, crank, csize);
+                const bool h3 = c.scal[BG_S_HBYTES] == 3;        /* (uniform) the 3-byte-window variants carry the free-node rule */
+                if (c.scal[BG_S_DEPTH] <= 24u) {
+                    if (h3) search_deep_batches<true>(c, t, crank, csize);
+                    else search_deep_batches<false>(c, t, crank, csize);
+                } else {
+                    if (h3) search_deep<true>(c, t, crank, csize);
+                    else search_deep<false>(c, t, crank, csize);
+                }
             }
         }
         if (SPLIT) {
