@@ -26,7 +26,19 @@ EXPORTS = [
     "b200bgzf_host_alloc", "b200bgzf_host_free", "b200bgzf_member_header", "b200bgzf_compress_host_index", "b200bgzf_gzi_format",
     "b200bgzf_multi_create", "b200bgzf_multi_destroy", "b200bgzf_multi_count", "b200bgzf_multi_ctx", "b200bgzf_shard_blocks",
     "b200bgzf_multi_compress_bound", "b200bgzf_multi_compress_host", "b200bgzf_multi_inflate_host",
+    "b200bgzf_pieces_gap_bytes", "b200bgzf_compress_pieces_host", "b200bgzf_crc32_combine", "b200bgzf_container_plan",
+    "b200bgzf_container_head", "b200bgzf_container_bound", "b200bgzf_container_frame", "b200bgzf_container_compress_host",
+    "b200bgzf_inflate_units_host", "b200bgzf_container_units", "b200bgzf_units_free", "b200bgzf_container_inflate_host",
 ]
+CONTAINER_GZIP, CONTAINER_MIGZ, CONTAINER_GZINGA, CONTAINER_DICTZIP, CONTAINER_RAZF = 1, 2, 3, 4, 5
+
+
+class Unit(ctypes.Structure):
+    _fields_ = [("in_off", ctypes.c_uint64), ("in_len", ctypes.c_uint32), ("hdr_len", ctypes.c_uint32), ("out_len", ctypes.c_uint32), ("piece", ctypes.c_uint32)]
+
+
+class PieceSpec(ctypes.Structure):
+    _fields_ = [("member_blocks", ctypes.c_uint32), ("head_gap", ctypes.c_uint32), ("tail_gap", ctypes.c_uint32), ("no_final", ctypes.c_uint32)]
 
 
 class B200BgzfError(RuntimeError):
@@ -78,7 +90,63 @@ def load(path=LIB_PATH):
     lib.b200bgzf_multi_compress_bound.restype = sz
     lib.b200bgzf_multi_compress_host.argtypes = [vp, vp, sz, u32, i32, vp, sz, psz, ctypes.c_uint]
     lib.b200bgzf_multi_inflate_host.argtypes = [vp, vp, sz, vp, sz, psz, ctypes.c_uint]
+    pspec, pu64, pu32 = ctypes.POINTER(PieceSpec), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(u32)
+    lib.b200bgzf_pieces_gap_bytes.argtypes = [sz, u32, pspec]
+    lib.b200bgzf_pieces_gap_bytes.restype = sz
+    lib.b200bgzf_compress_pieces_host.argtypes = [vp, vp, sz, u32, i32, pspec, vp, sz, psz, pu64, pu32, sz]
+    lib.b200bgzf_crc32_combine.argtypes = [u32, u32, ctypes.c_uint64]
+    lib.b200bgzf_crc32_combine.restype = u32
+    lib.b200bgzf_container_plan.argtypes = [i32, u32, pu32, pspec]
+    lib.b200bgzf_container_head.argtypes = [i32, sz]
+    lib.b200bgzf_container_head.restype = sz
+    lib.b200bgzf_container_bound.argtypes = [i32, u32, sz]
+    lib.b200bgzf_container_bound.restype = sz
+    lib.b200bgzf_container_frame.argtypes = [i32, u32, vp, sz, sz, pu64, pu32, sz, sz]
+    lib.b200bgzf_container_frame.restype = sz
+    lib.b200bgzf_container_compress_host.argtypes = [vp, i32, u32, vp, sz, i32, vp, sz, psz]
+    punit = ctypes.POINTER(Unit)
+    lib.b200bgzf_inflate_units_host.argtypes = [vp, vp, sz, punit, sz, vp, sz, psz, ctypes.c_uint]
+    lib.b200bgzf_container_units.argtypes = [i32, vp, sz, ctypes.POINTER(punit), psz, psz]
+    lib.b200bgzf_units_free.argtypes = [punit]
+    lib.b200bgzf_units_free.restype = None
+    lib.b200bgzf_container_inflate_host.argtypes = [vp, i32, vp, sz, vp, sz, psz]
     return lib
+
+
+def container_units(kind, blob, lib=None):
+    """([(in_off, in_len, hdr_len, out_len, piece)], decoded size) — b200bgzf_container_units; raises on a malformed container"""
+    lib = lib or load()
+    u, n, total = ctypes.POINTER(Unit)(), ctypes.c_size_t(), ctypes.c_size_t()
+    rc = lib.b200bgzf_container_units(kind, _addr(blob), len(blob), ctypes.byref(u), ctypes.byref(n), ctypes.byref(total))
+    if rc != 0:
+        raise B200BgzfError(rc, "container units")
+    try:
+        return [(u[i].in_off, u[i].in_len, u[i].hdr_len, u[i].out_len, u[i].piece) for i in range(n.value)], total.value
+    finally:
+        lib.b200bgzf_units_free(u)
+
+
+def container_plan(kind, param=0, lib=None):
+    """(block size, PieceSpec) of a container — b200bgzf_container_plan"""
+    lib = lib or load()
+    bs, sp = ctypes.c_uint32(), PieceSpec()
+    rc = lib.b200bgzf_container_plan(kind, param, ctypes.byref(bs), ctypes.byref(sp))
+    if rc != 0:
+        raise B200BgzfError(rc, "container plan")
+    return bs.value, sp
+
+
+def container_frame(kind, param, stream, piece_off, piece_crc, in_bytes, lib=None):
+    """b200bgzf_container_frame around a piece stream (bytes): the finished container (one dictzip member)"""
+    lib = lib or load()
+    n = len(piece_off)
+    head = lib.b200bgzf_container_head(kind, n)
+    buf = bytearray(head + len(stream) + 64 + 40 * (n + 1))
+    buf[head : head + len(stream)] = stream
+    off = (ctypes.c_uint64 * max(n, 1))(*piece_off)
+    crc = (ctypes.c_uint32 * max(n, 1))(*piece_crc)
+    total = lib.b200bgzf_container_frame(kind, param, _addr(buf), len(buf), len(stream), off, crc, n, in_bytes)
+    return bytes(buf[:total])
 
 
 def _addr(buf):
@@ -130,6 +198,43 @@ class Codec:
         n = ctypes.c_size_t()
         self._check(self.lib.b200bgzf_compress_host(self.h, _addr(data) if len(data) else None, len(data), block_size, level,
                                                     _addr(out), len(out), ctypes.byref(n), (APPEND_EOF if eof else 0) | flags))
+        return bytes(out[: n.value])
+
+    def compress_pieces(self, data, spec, level=6, block_size=BLOCK_SIZE):
+        """(piece stream, piece offsets, piece CRCs) — b200bgzf_compress_pieces_host"""
+        nb = (len(data) + block_size - 1) // block_size
+        cap = self.bound(len(data), block_size) + self.lib.b200bgzf_pieces_gap_bytes(len(data), block_size, ctypes.byref(spec))
+        out = bytearray(cap)
+        off = (ctypes.c_uint64 * max(nb, 1))()
+        crc = (ctypes.c_uint32 * max(nb, 1))()
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_compress_pieces_host(self.h, _addr(data) if len(data) else None, len(data), block_size, level,
+                                                           ctypes.byref(spec), _addr(out), len(out), ctypes.byref(n), off, crc, max(nb, 1)))
+        return bytes(out[: n.value]), list(off[:nb]), list(crc[:nb])
+
+    def container(self, kind, data, level=6, param=0):
+        """a whole container (gzip / MiGz / GZinga / dictzip / RAZF) — b200bgzf_container_compress_host"""
+        out = bytearray(self.lib.b200bgzf_container_bound(kind, param, len(data)))
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_container_compress_host(self.h, kind, param, _addr(data) if len(data) else None, len(data), level,
+                                                              _addr(out), len(out), ctypes.byref(n)))
+        return bytes(out[: n.value])
+
+    def container_inflate(self, kind, blob):
+        """b200bgzf_container_inflate_host"""
+        if kind == CONTAINER_MIGZ:
+            return self.inflate(blob)
+        _, total = container_units(kind, blob, self.lib)
+        out = bytearray(max(total, 1))
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_container_inflate_host(self.h, kind, _addr(blob), len(blob), _addr(out), len(out), ctypes.byref(n)))
+        return bytes(out[: n.value])
+
+    def inflate_units(self, blob, units, out_bytes):
+        arr = (Unit * len(units))(*[Unit(*u) for u in units])
+        out = bytearray(max(out_bytes, 1))
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_inflate_units_host(self.h, _addr(blob), len(blob), arr, len(units), _addr(out), len(out), ctypes.byref(n), 0))
         return bytes(out[: n.value])
 
     def compress_indexed(self, data, level=6, block_size=BLOCK_SIZE, eof=True):

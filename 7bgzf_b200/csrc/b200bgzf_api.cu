@@ -258,9 +258,17 @@ int lane_reserve(b200bgzf_ctx *ctx, Lane &l, uint32_t blocks, size_t in_bytes, s
 }
 
 /* one batch: compress kernel into slots, then scan + gather into `d_out` continuing at *d_total */
+/* piece mode of a batch (BgzfCompressArgs.piece_mode ...): where the batch sits in the stream of pieces */
+struct PieceLaunch {
+    b200bgzf_piece_spec spec;
+    uint64_t base, total;
+    uint32_t *d_crc;
+};
+
 int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint64_t in_bytes, uint32_t block_size,
                           const uint64_t *d_inoff, const uint32_t *d_inlen, uint32_t nblocks, int level, uint8_t *d_out,
-                          int append_eof, cudaStream_t stream, bool fused = false, uint32_t hdr_bytes = 18)
+                          int append_eof, cudaStream_t stream, bool fused = false, uint32_t hdr_bytes = 18,
+                          const PieceLaunch *pl = nullptr)
 {
     /* fused: the compress kernel's last CTA compacts the batch itself (l.d_total[2] is its arrival counter, zeroed with
      * l.d_total by the caller).  The pipelined host path uses it: a separate scan + gather launch per 32 MiB batch has to
@@ -289,6 +297,16 @@ int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint6
         a.crcpow = ctx->d_crcpow;
         a.err_flag = (uint32_t *)(l.d_total + 1);
         a.prof = ctx->prof_on ? ctx->d_prof : nullptr;
+        if (pl) {
+            a.piece_mode = 1;
+            a.member_blocks = pl->spec.member_blocks;
+            a.head_gap = pl->spec.head_gap;
+            a.tail_gap = pl->spec.tail_gap;
+            a.no_final = pl->spec.no_final ? 1u : 0u;
+            a.piece_base = pl->base;
+            a.piece_total = pl->total;
+            a.crc_out = pl->d_crc;
+        }
         if (fused) {
             a.gather_out = d_out;
             a.gather_off = l.d_off;
@@ -456,13 +474,16 @@ extern "C" int b200bgzf_compress_device(b200bgzf_ctx *ctx, const void *d_in, siz
     return l.h_total[1] ? B200BGZF_E_NOFIT : B200BGZF_OK;
 }
 
-/* member_off (optional): where every member starts in `out` — the offsets the device scan computes anyway */
-extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
-                                            size_t out_cap, size_t *out_bytes, unsigned flags, uint64_t *member_off, size_t member_cap)
+namespace {
+/* the pipelined host-buffer path.  member_off (optional): where every member (piece) starts in `out` — the offsets the
+ * device scan computes anyway.  ps (optional): piece mode; piece_crc then receives the CRC-32 of every block's input. */
+int compress_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                       size_t out_cap, size_t *out_bytes, unsigned flags, uint64_t *member_off, size_t member_cap,
+                       const b200bgzf_piece_spec *ps, uint32_t *piece_crc)
 {
     if (!ctx || !out || !out_bytes || (!in && in_bytes) || block_size == 0 || block_size > B200BGZF_MAX_BLOCK_SIZE || !level_ok(level))
         return B200BGZF_E_ARG;
-    if (out_cap < b200bgzf_compress_bound(in_bytes, block_size)) return B200BGZF_E_NOSPACE;
+    if (out_cap < b200bgzf_compress_bound(in_bytes, block_size) + (ps ? b200bgzf_pieces_gap_bytes(in_bytes, block_size, ps) : 0)) return B200BGZF_E_NOSPACE;
     if (member_off && member_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
     DeviceGuard g(ctx->device);
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -474,7 +495,8 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     static const uint32_t host_batch = [] { const char *e = getenv("B200BGZF_HOST_BATCH"); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : kHostBatchBlocks; }();
     static const uint32_t first_batch = [] { const char *e = getenv("B200BGZF_FIRST_BATCH"); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : 0u; }();
     const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), host_batch);
-    const size_t batch_in = (size_t)batch * block_size, batch_out = b200bgzf_compress_bound(batch_in, block_size);
+    const size_t batch_in = (size_t)batch * block_size;
+    const size_t batch_out = b200bgzf_compress_bound(batch_in, block_size) + (ps ? (size_t)batch * (ps->head_gap + ps->tail_gap) : 0);
     static const int nlanes = [] { const char *e = getenv("B200BGZF_LANES"); return e && atoi(e) > 0 ? std::min(atoi(e), kLanes) : kLanes; }();
     uint32_t cur = first_batch ? std::min(first_batch, batch) : batch;
     size_t host_off = 0;
@@ -486,6 +508,7 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
         if (l.h_total[1]) nofit = true;
         if (member_off)
             for (uint32_t k = 0; k < l.pend_nb; k++) member_off[l.pend_first + k] = host_off + l.h_meta[k];
+        if (piece_crc) memcpy(piece_crc + l.pend_first, l.h_meta + batch, l.pend_nb * sizeof(uint32_t));
         CK(cudaMemcpyAsync((uint8_t *)out + host_off, l.d_out, total, cudaMemcpyDeviceToHost, l.stream));
         host_off += total;
         l.pending = false;
@@ -502,12 +525,21 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
         const size_t bytes = (size_t)std::min<uint64_t>((uint64_t)nb * block_size, in_bytes - off);
         CK(cudaMemcpyAsync(l.d_in, (const uint8_t *)in + off, bytes, cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
+        PieceLaunch pl;
+        if (ps) {
+            pl.spec = *ps;
+            pl.base = done;
+            pl.total = nb_total;
+            pl.d_crc = l.d_inlen;                               /* (unused by fixed-size batches) */
+        }
         if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true,
-                                       (flags & B200BGZF_FRAME_MIGZ) ? 20u : 18u))) return r;
+                                       (flags & B200BGZF_FRAME_MIGZ) ? 20u : 18u, ps ? &pl : nullptr))) return r;
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
-        if (member_off) {
-            CK(grow(&l.h_meta, &l.meta_cap, (size_t)batch, true));
-            CK(cudaMemcpyAsync(l.h_meta, l.d_off, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+        if (member_off || piece_crc) {
+            /* pinned: u64[batch] member offsets, then u32[batch] CRCs */
+            CK(grow(&l.h_meta, &l.meta_cap, (size_t)batch + ((size_t)batch + 1) / 2, true));
+            if (member_off) CK(cudaMemcpyAsync(l.h_meta, l.d_off, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
+            if (piece_crc) CK(cudaMemcpyAsync(l.h_meta + batch, l.d_inlen, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
             l.pend_first = done;
             l.pend_nb = nb;
         }
@@ -522,7 +554,7 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     }
     for (auto &l : ctx->lanes)
         if (l.stream) CK(cudaStreamSynchronize(l.stream));
-    if ((flags & B200BGZF_APPEND_EOF) && !(flags & B200BGZF_FRAME_MIGZ)) {
+    if ((flags & B200BGZF_APPEND_EOF) && !(flags & B200BGZF_FRAME_MIGZ) && !ps) {
         static const uint8_t eof[28] = { 0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0,
                                          0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         memcpy((uint8_t *)out + host_off, eof, sizeof eof);
@@ -530,6 +562,32 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
     }
     *out_bytes = host_off;
     return nofit ? B200BGZF_E_NOFIT : B200BGZF_OK;
+}
+}  // namespace
+
+extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
+                                            size_t out_cap, size_t *out_bytes, unsigned flags, uint64_t *member_off, size_t member_cap)
+{
+    return compress_host_impl(ctx, in, in_bytes, block_size, level, out, out_cap, out_bytes, flags, member_off, member_cap, nullptr, nullptr);
+}
+
+extern "C" size_t b200bgzf_pieces_gap_bytes(size_t in_bytes, uint32_t block_size, const b200bgzf_piece_spec *ps)
+{
+    if (!ps || !block_size || !ps->member_blocks) return 0;
+    const uint64_t nb = (in_bytes + block_size - 1) / block_size;
+    const uint64_t members = (nb + ps->member_blocks - 1) / ps->member_blocks;
+    return (size_t)(members * ((uint64_t)ps->head_gap + ps->tail_gap));
+}
+
+extern "C" int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level,
+                                             const b200bgzf_piece_spec *ps, void *out, size_t out_cap, size_t *out_bytes,
+                                             uint64_t *piece_off, uint32_t *piece_crc, size_t piece_cap)
+{
+    if (!ps || ps->member_blocks == 0 || ps->head_gap > B200BGZF_MAX_GAP || ps->tail_gap > B200BGZF_MAX_GAP) return B200BGZF_E_ARG;
+    /* a stored piece (5 bytes of block header) and both gaps must stay inside the 64 KiB slot */
+    if ((uint64_t)block_size + 5u + ps->head_gap + ps->tail_gap > B200BGZF_MAX_BLOCK_SIZE) return B200BGZF_E_ARG;
+    if (piece_crc && piece_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
+    return compress_host_impl(ctx, in, in_bytes, block_size, level, out, out_cap, out_bytes, 0, piece_off, piece_cap, ps, piece_crc);
 }
 
 extern "C" int b200bgzf_compress_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level, void *out,
@@ -1185,8 +1243,10 @@ extern "C" int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size
     return (ef & 1u) ? B200BGZF_E_FORMAT : (ef & 2u) ? B200BGZF_E_CRC : B200BGZF_OK;
 }
 
-extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
-                                     unsigned flags)
+namespace {
+/* units == nullptr: the members are found by walking their headers; else: the caller's list (members and raw pieces) */
+int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const b200bgzf_unit *units, size_t nunits, void *out,
+                      size_t out_cap, size_t *out_bytes, unsigned flags)
 {
     if (!ctx || !in || !out_bytes) return B200BGZF_E_ARG;
     const uint8_t *p = (const uint8_t *)in;
@@ -1219,16 +1279,36 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
             if (l.pending && (r = complete(l))) return r;
         return 0;
     };
-    while (off < in_bytes) {
+    size_t u = 0;                                       /* next unit of the caller's list */
+    while (units ? u < nunits : off < in_bytes) {
         Lane &l = ctx->lanes[i % nlanes];
         if (l.pending && (r = complete(l))) return r;
         if ((r = lane_reserve(ctx, l, (uint32_t)kBatchMax, 0, 0, false))) return r;
-        CK(grow(&l.h_meta, &l.meta_cap, 3 * kBatchMax, true));
-        uint32_t *h_hdr = (uint32_t *)(l.h_meta + 2 * kBatchMax), *h_msz = h_hdr + kBatchMax;
+        CK(grow(&l.h_meta, &l.meta_cap, 4 * kBatchMax, true));
+        uint32_t *h_hdr = (uint32_t *)(l.h_meta + 2 * kBatchMax), *h_msz = h_hdr + kBatchMax, *h_isz = h_msz + kBatchMax;
         /* walk the next `batch` members */
-        const size_t in0 = off, out0 = total;
+        size_t in0 = off;
+        const size_t out0 = total;
         size_t nb = 0;
-        while (nb < batch && off < in_bytes) {
+        if (units) {
+            in0 = off = (size_t)units[u].in_off;
+            while (nb < batch && u < nunits) {
+                const b200bgzf_unit &un = units[u];
+                /* ascending, inside the input, and a member has room for its trailer */
+                if (un.in_off < off || un.in_off + un.in_len > in_bytes || un.hdr_len > un.in_len || (!un.piece && un.in_len < un.hdr_len + 8u) ||
+                    un.in_len == 0 || un.hdr_len > 0xffffu) { drain(); return B200BGZF_E_FORMAT; }
+                l.h_meta[nb] = un.in_off - in0;
+                l.h_meta[kBatchMax + nb] = total - out0;
+                h_hdr[nb] = un.hdr_len;
+                h_msz[nb] = un.in_len;
+                h_isz[nb] = un.piece ? un.out_len : 0xffffffffu;
+                total += un.piece ? un.out_len : rd32(p + un.in_off + un.in_len - 4);
+                off = (size_t)(un.in_off + un.in_len);
+                nb++;
+                u++;
+            }
+        }
+        while (!units && nb < batch && off < in_bytes) {
             uint64_t sz = 0;
             const uint32_t hlen = member_parse(p + off, in_bytes - off, &sz);
             if (!hlen) { drain(); return B200BGZF_E_FORMAT; }
@@ -1249,9 +1329,11 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
         CK(cudaMemcpyAsync(l.d_outoff, l.h_meta + kBatchMax, nb * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemcpyAsync(l.d_inlen, h_hdr, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemcpyAsync(l.d_len, h_msz, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
+        if (units) CK(cudaMemcpyAsync(l.d_off, h_isz, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));   /* (d_off: unused by inflate batches) */
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
         BgzfInflateArgs a;
         memset(&a, 0, sizeof a);
+        a.unit_isize = units ? (const uint32_t *)l.d_off : nullptr;
         a.in = l.d_in;
         a.in_off = l.d_inoff;
         a.out_off = l.d_outoff;
@@ -1274,4 +1356,22 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
     }
     if ((r = drain())) return r;
     return bad ? B200BGZF_E_FORMAT : badcrc ? B200BGZF_E_CRC : B200BGZF_OK;
+}
+}  // namespace
+
+extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
+                                     unsigned flags)
+{
+    return inflate_host_impl(ctx, in, in_bytes, nullptr, 0, out, out_cap, out_bytes, flags);
+}
+
+extern "C" int b200bgzf_inflate_units_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const b200bgzf_unit *units, size_t nunits,
+                                           void *out, size_t out_cap, size_t *out_bytes, unsigned flags)
+{
+    if (!units && nunits) return B200BGZF_E_ARG;
+    if (nunits == 0) {
+        if (out_bytes) *out_bytes = 0;
+        return out_bytes ? B200BGZF_OK : B200BGZF_E_ARG;
+    }
+    return inflate_host_impl(ctx, in, in_bytes, units, nunits, out, out_cap, out_bytes, flags);
 }

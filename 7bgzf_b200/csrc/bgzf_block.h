@@ -144,9 +144,23 @@ struct BgCtx {
     const uint16_t *perm;   /* smem u16[BG_MAX_CHUNKS] or NULL: which chunk thread i walks in the token passes (tally, sizes, emit).
                                Any permutation gives the same bytes; the kernel groups chunks of similar make-up into one warp. */
     uint32_t n;         /* payload bytes */
-    uint32_t hdr;       /* member header bytes: 18 BGZF ("BC" subfield, BSIZE), 20 MiGz ("MZ" subfield, u32 compressed size: applet/7migz.c:224-228) */
+    /* framing of this block's slot, packed into one word (bg_frame): header bytes | trailer bytes << 8 | final << 16 | piece << 17.
+     * Members: hdr = 18 BGZF ("BC" subfield, BSIZE) or 20 MiGz ("MZ" subfield, u32 compressed size: applet/7migz.c:224-228),
+     * trl = 8 (CRC32, ISIZE), final = 1.
+     * Piece mode (the other block-gzip containers and whole-stream gzip: a member is made of several 64 KiB pieces): the slot
+     * holds `hdr` free bytes, the DEFLATE data of this block, `trl` free bytes; no gzip framing is written (the host fills the
+     * gaps of a member's first and last piece).  A piece that is not `final` carries BFINAL = 0 and ends with an empty stored
+     * block that pads to the byte ("full flush": what the reference makes of every dictzip / RAZF chunk by clearing the
+     * final bit and appending 00 00 ff ff, applet/7dictzip.c:92-126, 7razf_testdecode.c:1023), so pieces concatenate bytewise. */
+    uint32_t frame;
     BgParams prm;
 };
+
+BG_HD uint32_t bg_frame(uint32_t hdr, uint32_t trl, uint32_t final, uint32_t piece) { return hdr | (trl << 8) | (final << 16) | (piece << 17); }
+BG_HD uint32_t bg_f_hdr(const BgCtx &c) { return c.frame & 0xffu; }
+BG_HD uint32_t bg_f_trl(const BgCtx &c) { return (c.frame >> 8) & 0xffu; }
+BG_HD uint32_t bg_f_final(const BgCtx &c) { return (c.frame >> 16) & 1u; }
+BG_HD bool bg_f_piece(const BgCtx &c) { return (c.frame >> 17) & 1u; }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* small helpers                                                                                    */
@@ -1441,6 +1455,9 @@ BG_HD void bg_phase_hdr5(const BgCtx &c, uint32_t t, uint32_t T, uint32_t nitems
     c.scal[BG_S_NP] = np;
 }
 
+/* bytes of a coded block of `bits` bits; a non-final piece adds the empty stored block: 3 bits, padding, 00 00 ff ff */
+BG_HD uint32_t bg_coded_bytes(const BgCtx &c, uint32_t bits) { return bg_f_final(c) ? (bits + 7) >> 3 : ((bits + 3 + 7) >> 3) + 4; }
+
 /* block type from the exact costs: every thread evaluates the same few scalars */
 BG_HD uint32_t bg_block_type(const BgCtx &c, uint32_t *hdrbits, uint32_t *tokbits, uint32_t *payload)
 {
@@ -1455,10 +1472,10 @@ BG_HD uint32_t bg_block_type(const BgCtx &c, uint32_t *hdrbits, uint32_t *tokbit
         return 0;
     }
     if (sta_bits <= dyn_bits) {
-        *hdrbits = 3; *tokbits = sta_bits - 3; *payload = (sta_bits + 7) >> 3;
+        *hdrbits = 3; *tokbits = sta_bits - 3; *payload = bg_coded_bytes(c, sta_bits);
         return 1;
     }
-    *hdrbits = hdr; *tokbits = dyn_bits - hdr; *payload = (dyn_bits + 7) >> 3;
+    *hdrbits = hdr; *tokbits = dyn_bits - hdr; *payload = bg_coded_bytes(c, dyn_bits);
     return 2;
 }
 
@@ -1483,7 +1500,7 @@ BG_HD void bg_phase_decide_b(const BgCtx &c, uint32_t t, uint32_t T)
         c.scal[BG_S_HDRBITS] = hdrbits;
         c.scal[BG_S_TOKBITS] = tokbits;   /* includes the end-of-block symbol */
         c.scal[BG_S_PAYLOAD] = payload;
-        c.scal[BG_S_STATUS] = (c.hdr + payload + 8u > BG_SLOT_BYTES) ? 1u : 0u;
+        c.scal[BG_S_STATUS] = (bg_f_hdr(c) + payload + bg_f_trl(c) > BG_SLOT_BYTES) ? 1u : 0u;
     }
 }
 
@@ -1640,7 +1657,7 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
 /* phase 16: zero the output words this block will OR into */
 BG_HD void bg_phase_zero_out(const BgCtx &c, uint32_t t, uint32_t T)
 {
-    uint32_t bytes = c.hdr + c.scal[BG_S_PAYLOAD] + 8;
+    uint32_t bytes = bg_f_hdr(c) + c.scal[BG_S_PAYLOAD] + bg_f_trl(c);
     if (bytes > BG_SLOT_BYTES) bytes = BG_SLOT_BYTES;
     uint32_t words = (bytes + 3) >> 2;
     for (uint32_t i = t; i < words; i += T)
@@ -1688,13 +1705,14 @@ BG_HD void bg_w_flush(BgWriter &w)
  * "BC" with BSIZE = member size - 1.  MiGz (applet/7migz.c:224-233): 20 bytes, subfield "MZ" with the DEFLATE size as u32. */
 BG_HD void bg_emit_frame(const BgCtx &c)
 {
+    if (bg_f_piece(c)) return;                   /* the gaps stay zero: the host writes the container's framing */
     const uint32_t payload = c.scal[BG_S_PAYLOAD];
-    const uint32_t total = c.hdr + payload + 8;
+    const uint32_t total = bg_f_hdr(c) + payload + 8;
     BgWriter w;
     bg_w_init(w, c.out, 0);
     bg_w_put(w, 0x04088b1fu, 32);          /* 1f 8b 08 04 */
     bg_w_put(w, 0u, 32);                   /* MTIME */
-    if (c.hdr == 18u) {
+    if (bg_f_hdr(c) == 18u) {
         bg_w_put(w, 0x0006ff00u, 32);      /* XFL 00, OS ff, XLEN 0006 */
         bg_w_put(w, 0x00024342u, 32);      /* 'B' 'C' SLEN 0002 */
         bg_w_put(w, (total - 1) & 0xffffu, 16);
@@ -1704,7 +1722,7 @@ BG_HD void bg_emit_frame(const BgCtx &c)
         bg_w_put(w, payload, 32);
     }
     bg_w_flush(w);
-    bg_w_init(w, c.out, (c.hdr + payload) * 8);
+    bg_w_init(w, c.out, (bg_f_hdr(c) + payload) * 8);
     bg_w_put(w, c.scal[BG_S_CRC], 32);
     bg_w_put(w, c.n, 32);
     bg_w_flush(w);
@@ -1718,7 +1736,7 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t n = c.n;
     uint8_t *rb = c.regb;
     const uint32_t btype = c.scal[BG_S_BTYPE];
-    const uint32_t base = c.hdr * 8;
+    const uint32_t base = bg_f_hdr(c) * 8;
     if (btype == 0) {
         /* stored: [01|00] LEN NLEN raw..., at most two stored blocks (n <= 65536) */
         const uint32_t first = n > 65535u ? 65535u : n;
@@ -1726,13 +1744,13 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
             bg_emit_frame(c);
             BgWriter w;
             bg_w_init(w, c.out, base);
-            bg_w_put(w, n > 65535u ? 0u : 1u, 8);
+            bg_w_put(w, n > 65535u ? 0u : bg_f_final(c), 8);
             bg_w_put(w, first | ((~first & 0xffffu) << 16), 32);
             bg_w_flush(w);
             if (n > 65535u) {
                 uint32_t rest = n - 65535u;
                 bg_w_init(w, c.out, base + (5 + 65535u) * 8);
-                bg_w_put(w, 1u, 8);
+                bg_w_put(w, bg_f_final(c), 8);
                 bg_w_put(w, rest | ((~rest & 0xffffu) << 16), 32);
                 bg_w_flush(w);
             }
@@ -1740,7 +1758,7 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
         /* raw bytes: payload byte i lands at slot byte hdr+5+i (+5 more after the first 65535).
          * Output words whose four source bytes all lie in the first stored block are plain stores
          * of an unaligned read; the few bytes at either edge are OR-ed in one by one. */
-        const uint32_t r0 = c.hdr + 5u;                        /* slot byte of payload byte 0 */
+        const uint32_t r0 = bg_f_hdr(c) + 5u;                        /* slot byte of payload byte 0 */
         const uint32_t w0 = (r0 + 3u) >> 2, hb = 4u * w0 - r0;  /* first full word; payload bytes before it */
         const uint32_t wend = (first + r0) >> 2;               /* first word that is not "full" */
         for (uint32_t wd = w0 + t; wd < wend; wd += T)
@@ -1767,7 +1785,7 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
         bg_emit_frame(c);
         BgWriter w;
         bg_w_init(w, c.out, base);
-        bg_w_put(w, 1u | (btype << 1), 3);
+        bg_w_put(w, bg_f_final(c) | (btype << 1), 3);
         if (btype == 2) {
             const uint32_t nl = c.scal[BG_S_NL], nd = c.scal[BG_S_ND], np = c.scal[BG_S_NP];
             bg_w_put(w, (nl - 257) | ((nd - 1) << 5) | ((np - 4) << 10), 14);
@@ -1779,6 +1797,12 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
         bg_w_init(w, c.out, base + hdrbits + c.scal[BG_S_TOKBITS] - llen[256]);
         bg_w_put(w, lcode[256], llen[256]);
         bg_w_flush(w);
+        if (!bg_f_final(c)) {
+            /* empty stored block: its three header bits and the padding are zeros already; LEN 0000, NLEN ffff close the piece */
+            bg_w_init(w, c.out, (bg_f_hdr(c) + c.scal[BG_S_PAYLOAD] - 4u) * 8u);
+            bg_w_put(w, 0xffff0000u, 32);
+            bg_w_flush(w);
+        }
     }
     if (btype == 2) {
         /* the run-length items of the dynamic header, one thread each, at the bit offsets of phase 14f */

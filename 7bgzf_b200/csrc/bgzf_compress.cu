@@ -826,7 +826,7 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
     c.cand = a.cand ? a.cand + (size_t)unit * (4u * BG_MAX_BLOCK) : nullptr;
     c.crcpow = a.crcpow;
     c.prm = a.prm;
-    c.hdr = a.hdr_bytes ? a.hdr_bytes : 18u;
+    c.frame = bg_frame(a.hdr_bytes ? a.hdr_bytes : 18u, 8u, 1u, 0u);
     c.perm = (const uint16_t *)(smem + SM_REGB + BG_B_PERM);
 
     if (t < 256) c.crctab[t] = a.crctab[t];
@@ -851,6 +851,12 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         }
         c.n = n;
         c.out = (uint32_t *)(a.slots + (size_t)b * BG_SLOT_BYTES);
+        if (a.piece_mode) {
+            /* piece b of the call is piece gb of the stream: members are runs of member_blocks pieces (the last one may be short) */
+            const uint64_t gb = a.piece_base + b;
+            const bool first = gb % a.member_blocks == 0, last = (gb + 1) % a.member_blocks == 0 || gb + 1 == a.piece_total;
+            c.frame = bg_frame(first ? a.head_gap : 0u, last ? a.tail_gap : 0u, last && !a.no_final ? 1u : 0u, 1u);
+        }
 
         /* 1. stage the payload: TMA for the 16-byte-aligned bulk, plain loads for the ragged rest */
         const bool aligned = (((uintptr_t)src) & 15u) == 0;
@@ -1021,7 +1027,8 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
         bg_phase_emit(c, t, T);
         if (t == 0) {
             const uint32_t st = c.scal[BG_S_STATUS];
-            a.out_len[b] = st ? 0u : c.hdr + c.scal[BG_S_PAYLOAD] + 8u;
+            a.out_len[b] = st ? 0u : bg_f_hdr(c) + c.scal[BG_S_PAYLOAD] + bg_f_trl(c);
+            if (a.crc_out) a.crc_out[b] = c.scal[BG_S_CRC];
             a.status[b] = st;
             if (st) atomicOr(a.err_flag, 1u);
         }

@@ -377,12 +377,17 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
         hlen = 18;
         msize = ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
     }
-    if (msize < hlen + 8u) {
+    if (msize < hlen + 8u && !(a.unit_isize && a.unit_isize[m] != 0xffffffffu && msize >= hlen)) {
         if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
         return;
     }
-    const uint8_t *trailer = mem + msize - 8;
-    const uint32_t isize = (uint32_t)trailer[4] | ((uint32_t)trailer[5] << 8) | ((uint32_t)trailer[6] << 16) | ((uint32_t)trailer[7] << 24);
+    /* a piece (unit_isize given and not ~0): raw DEFLATE data without a trailer, e.g. one dictzip chunk or RAZF block; it is
+     * complete when it has produced its share of the output at a block boundary (its blocks are not final: the reference
+     * clears the bit and appends an empty stored block, applet/7dictzip.c:92-126) */
+    const bool piece = a.unit_isize && a.unit_isize[m] != 0xffffffffu;
+    const uint8_t *trailer = piece ? mem + msize : mem + msize - 8;
+    const uint32_t isize = piece ? a.unit_isize[m]
+                                 : (uint32_t)trailer[4] | ((uint32_t)trailer[5] << 8) | ((uint32_t)trailer[6] << 16) | ((uint32_t)trailer[7] << 24);
     uint8_t *out = a.out + a.out_off[m];
     if (!a.hdr_len && isize > 65536u) {                 /* (a BGZF payload is at most 64 KiB; other containers' members may be larger) */
         if (lane == 0) { a.status[m] = INF_E_HEADER; atomicOr(a.err_flag, 1u); }
@@ -401,7 +406,9 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
     o.lane = lane;
     const uint32_t end_apos = o.end;
     bool last = false;
-    while (!last && err == INF_OK) {
+    uint32_t nblk = 0;
+    while (!last && err == INF_OK && !(piece && nblk && o.apos == end_apos)) {
+        nblk++;
         last = br_take(r, 1);
         const uint32_t btype = br_take(r, 2);
         if (btype == 0) {
@@ -541,6 +548,7 @@ bgzf_verify_kernel(BgzfInflateArgs a)
     extern __shared__ __align__(16) uint8_t vs[];
     const uint32_t t = threadIdx.x, m = blockIdx.x;
     if (m >= a.nblocks || a.status[m] != INF_OK) return;          /* (uniform for the CTA) */
+    if (a.unit_isize && a.unit_isize[m] != 0xffffffffu) return;   /* a piece has no trailer of its own */
     const uint8_t *mem = a.in + a.in_off[m];
     const uint32_t msize = a.hdr_len ? a.msize[m] : ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
     const uint8_t *tr = mem + msize - 8;
@@ -556,7 +564,7 @@ bgzf_verify_kernel(BgzfInflateArgs a)
     c.scal = (uint32_t *)(vs + BG_DATA_BYTES + 1024u + 256u);
     c.crcpow = a.crcpow;
     c.n = isize;
-    c.hdr = 18;
+    c.frame = bg_frame(18u, 8u, 1u, 0u);
     /* stage: bytes up to the first 16-byte boundary of the source, 16-byte loads for the body, bytes for the rest */
     const uint32_t head = isize < 16 ? isize : (uint32_t)((16u - ((uintptr_t)out & 15u)) & 15u);
     const uint32_t body = (isize - head) & ~15u;

@@ -35,6 +35,15 @@ struct BgzfCompressArgs {
     uint64_t *gather_off;      /* device u64[nblocks]: out: where every member starts in gather_out */
     uint64_t *gather_total;    /* device: in: bytes already in gather_out; out: bytes after this batch */
     uint32_t *done_count;      /* device: zero before the launch */
+    /* piece mode (BgCtx.piece in bgzf_block.h): raw DEFLATE pieces for containers whose members span several blocks */
+    uint32_t piece_mode;       /* 0: BGZF / MiGz members */
+    uint32_t member_blocks;    /* pieces per member (>= 1); a member's last piece is the final DEFLATE block unless no_final */
+    uint64_t piece_base;       /* index, in the whole stream, of this call's first piece */
+    uint64_t piece_total;      /* pieces in the whole stream (its last piece ends a member whatever its index) */
+    uint32_t head_gap;         /* free bytes before a member's first piece */
+    uint32_t tail_gap;         /* free bytes after a member's last piece */
+    uint32_t no_final;         /* 1: no piece is final (dictzip closes the member with an empty block of its own) */
+    uint32_t *crc_out;         /* device u32[nblocks], optional: CRC-32 of every block's input */
 };
 
 struct BgzfInflateArgs {
@@ -44,6 +53,8 @@ struct BgzfInflateArgs {
     const uint32_t *hdr_len;   /* device, optional: offset of the DEFLATE data inside each member, as found by the host's header
                                   parser (any flavour of applet/7bgzf.c:81-131); NULL: strict BGZF headers, parsed by the kernel */
     const uint32_t *msize;     /* device, with hdr_len: whole member size */
+    const uint32_t *unit_isize; /* device, optional (with hdr_len): 0xffffffff = a member (ISIZE from its trailer); anything else = a raw
+                                  DEFLATE piece of msize bytes (hdr_len bytes skipped, no trailer) that yields this many bytes */
     uint32_t nblocks;
     uint8_t *out;              /* device */
     uint32_t *status;          /* device: 0 ok, else error code per member */

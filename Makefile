@@ -25,11 +25,11 @@ $(OBJ)/%.o: $(HOST)/%.c include/b200bgzf.h
 	$(CC) $(CFLAGS) -c $< -o $@
 
 # the codec library: kernels + C ABI (+ the BGZF_METHOD parser)
-$(PKG)/lib7bgzf_b200.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o
+$(PKG)/lib7bgzf_b200.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/containers.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(HOST)/exports.map -lpthread
 
 # the LD_PRELOAD object: the same plus htslib's bgzf_compress
-$(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/hook.o
+$(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/containers.o $(OBJ)/hook.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(HOST)/exports.map -lpthread
 
 # the applet
@@ -43,9 +43,9 @@ $(PKG)/7migz: $(PKG)/7bgzf
 # the same library with the bounds asserts compiled in (BG_ASSERT, csrc/bgzf_block.h): point the GPU tests at it with
 #   B200BGZF_LIB_PATH=build/checked/lib7bgzf_b200.so python -m pytest tests -m gpu
 checked: build/checked/lib7bgzf_b200.so
-build/checked/lib7bgzf_b200.so: $(CU_SRCS) $(HDRS) $(OBJ)/method.o $(OBJ)/multi.o
+build/checked/lib7bgzf_b200.so: $(CU_SRCS) $(HDRS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/containers.o
 	@mkdir -p build/checked
-	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DBG_CHECK -shared -o $@ $(CU_SRCS) $(OBJ)/method.o $(OBJ)/multi.o -Xlinker --version-script=$(HOST)/exports.map -lpthread
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DBG_CHECK -shared -o $@ $(CU_SRCS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/containers.o -Xlinker --version-script=$(HOST)/exports.map -lpthread
 
 # ---- test / bench infrastructure (never linked into the product) ----
 testlibs: build/libdatagen.so build/libemul.so build/datagen build/hook_mt oracle/liboracle.so

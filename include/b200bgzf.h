@@ -111,6 +111,24 @@ int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, vo
                           unsigned flags);
 
 /*
+ * Inflate a list of units found by the caller — what the readers of the indexed containers need (dictzip's chunk table,
+ * RAZF's block index, GZinga's member index: applet/7dictzip.c:320-400, 7razf.c:293-384, 7gzinga.c:218-307).  A unit is either
+ * a gzip member (piece = 0: hdr_len bytes of header, DEFLATE data, CRC32 + ISIZE; out_len is ignored, ISIZE counts) or a raw
+ * DEFLATE piece (piece = 1: in_len bytes after hdr_len skipped bytes, no trailer) that is complete once it has produced
+ * out_len bytes at a block boundary.  Units are listed in ascending input order; their outputs follow one another in `out`.
+ * One warp decodes one unit, as for BGZF members.  (B200BGZF_VERIFY checks the members only: pieces carry no CRC.)
+ */
+typedef struct b200bgzf_unit {
+    uint64_t in_off;
+    uint32_t in_len;
+    uint32_t hdr_len;
+    uint32_t out_len;
+    uint32_t piece;
+} b200bgzf_unit;
+int b200bgzf_inflate_units_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const b200bgzf_unit *units, size_t nunits,
+                                void *out, size_t out_cap, size_t *out_bytes, unsigned flags);
+
+/*
  * Several GPUs behind one call (the reference's fan-out over blocks: applet/7bgzf.c:159-227).  GPU g of G takes
  * the contiguous block range [B*g/G, B*(g+1)/G) of the input (b200bgzf_shard_blocks), runs its own pipelined host-buffer
  * call on its own context and host thread, and the shard outputs are joined at host-known offsets: no collective, and the
@@ -129,6 +147,72 @@ int b200bgzf_multi_compress_host(b200bgzf_multi *m, const void *in, size_t in_by
                                  size_t out_cap, size_t *out_bytes, unsigned flags);
 int b200bgzf_multi_inflate_host(b200bgzf_multi *m, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
                                 unsigned flags);
+
+/*
+ * SURVEY §8(f) ranks 3 and 4 — the other block-gzip containers and whole-stream gzip on the same kernel.
+ *
+ * Piece mode: block b of the input becomes a raw DEFLATE *piece* (no gzip framing).  Members are runs of
+ * spec->member_blocks pieces; a member's last piece is the final DEFLATE block, every other piece has BFINAL = 0 and ends
+ * with an empty stored block that pads to the byte — the "full flush" the reference applies to every dictzip / RAZF chunk
+ * (applet/7dictzip.c:92-126, applet/7razf.c:124-160) — so the pieces of a member concatenate bytewise into one DEFLATE
+ * stream, and each piece also decodes on its own.  head_gap / tail_gap zero bytes are left before a member's first and
+ * after its last piece for the container's header and trailer.  Returns the pieces (with their gaps) back to back in
+ * `out`, piece_off[b] = where piece b (or its head gap) starts, piece_crc[b] = CRC-32 of block b's input (combine them
+ * with b200bgzf_crc32_combine).  block_size + 5 + head_gap + tail_gap must not exceed 65536.
+ */
+#define B200BGZF_MAX_GAP 64u
+typedef struct b200bgzf_piece_spec {
+    uint32_t member_blocks;   /* pieces per member, >= 1 (0xffffffff: one member) */
+    uint32_t head_gap;        /* <= B200BGZF_MAX_GAP */
+    uint32_t tail_gap;        /* <= B200BGZF_MAX_GAP */
+    uint32_t no_final;        /* 1: no piece is final (dictzip closes its member with an empty block of its own) */
+} b200bgzf_piece_spec;
+size_t b200bgzf_pieces_gap_bytes(size_t in_bytes, uint32_t block_size, const b200bgzf_piece_spec *spec);
+int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level,
+                                  const b200bgzf_piece_spec *spec, void *out, size_t out_cap, size_t *out_bytes,
+                                  uint64_t *piece_off, uint32_t *piece_crc, size_t piece_cap);
+/* CRC-32 of A||B from CRC-32(A), CRC-32(B) and len(B) (zlib's crc32_combine, lib/zlib/crc32.c:1021-1026) */
+uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+
+/*
+ * The containers (host code in 7bgzf_b200/host/containers.c; `param` = 0 for the reference's default):
+ *   GZIP     one gzip member (applet/7gzip.c + zlibrawstdio_compress.h:259-300 hand the whole file to one
+ *            libdeflate_deflate call; here: independent 65280-byte pieces, as pigz -i does)
+ *   MIGZ     applet/7migz.c:133-243 — members of `param` KiB (default 512), subfield "MZ" = DEFLATE size
+ *   GZINGA   applet/7gzinga.c:78-216 — 100 KiB members with an empty comment, then an index member whose comment lists
+ *            "n:end-offset;" of every member
+ *   DICTZIP  applet/7dictzip.c:177-318 — chunks of `param` bytes (default 58315), subfield "RA" with every chunk's size,
+ *            members of at most 32762 chunks, each closed by an empty static block
+ *   RAZF     applet/7razf.c:160-290 — 32768-byte blocks, subfield "RAZF", block index (big endian) after the trailer;
+ *            inputs below 4 GiB
+ * b200bgzf_container_compress_host = plan + b200bgzf_compress_pieces_host + b200bgzf_container_frame.
+ */
+#define B200BGZF_CONTAINER_GZIP 1
+#define B200BGZF_CONTAINER_MIGZ 2
+#define B200BGZF_CONTAINER_GZINGA 3
+#define B200BGZF_CONTAINER_DICTZIP 4
+#define B200BGZF_CONTAINER_RAZF 5
+/* block size and piece layout of a container (dictzip: for a member of `npieces` chunks); 0 or B200BGZF_E_ARG */
+int b200bgzf_container_plan(int kind, uint32_t param, uint32_t *block_size, b200bgzf_piece_spec *spec);
+/* bytes of container header that precede the piece stream of a member and do not live in a gap (dictzip's chunk table) */
+size_t b200bgzf_container_head(int kind, size_t npieces);
+size_t b200bgzf_container_bound(int kind, uint32_t param, size_t in_bytes);
+/* Writes the framing around a piece stream: `member` is where the container (dictzip: this member) starts, the stream of
+ * `stream_bytes` bytes made with the plan above lies at member + b200bgzf_container_head().  No GPU involved.  Returns the
+ * size of the finished container (member), 0 if `cap` is too small or an argument is off. */
+size_t b200bgzf_container_frame(int kind, uint32_t param, void *member, size_t cap, size_t stream_bytes, const uint64_t *piece_off,
+                                const uint32_t *piece_crc, size_t npieces, size_t in_bytes);
+int b200bgzf_container_compress_host(b200bgzf_ctx *ctx, int kind, uint32_t param, const void *in, size_t in_bytes, int level,
+                                     void *out, size_t out_cap, size_t *out_bytes);
+
+/* The readers: the unit list of a dictzip / RAZF / GZinga file from its own index (a plain gzip member without an index is
+ * one unit: one warp decodes it), to be released with b200bgzf_units_free; out_bytes = the decoded size.  No GPU involved.
+ * b200bgzf_container_inflate_host = that list + b200bgzf_inflate_units_host (MiGz: b200bgzf_inflate_host, whose header
+ * walk knows the "MZ" subfield). */
+int b200bgzf_container_units(int kind, const void *in, size_t in_bytes, b200bgzf_unit **units, size_t *nunits, size_t *out_bytes);
+void b200bgzf_units_free(b200bgzf_unit *units);
+int b200bgzf_container_inflate_host(b200bgzf_ctx *ctx, int kind, const void *in, size_t in_bytes, void *out, size_t out_cap,
+                                    size_t *out_bytes);
 
 /* Page-locked host memory for the *_host entry points (pageable buffers work too, but are copied at a fraction of
  * the PCIe rate).  The applet reads stdin straight into such buffers. */

@@ -61,6 +61,21 @@ def emul_block(payload, level=6, order=0):
     return rc, dst.raw[: dl.value]
 
 
+def emul_piece(payload, level=6, head_gap=0, tail_gap=0, final=True, order=0):
+    """One block in piece mode (raw DEFLATE between `head_gap` and `tail_gap` free bytes): (slot bytes, CRC-32 of payload)."""
+    lib = _emul()
+    lib.bgemul_set_piece.argtypes = [ctypes.c_uint32] * 4
+    lib.bgemul_set_piece.restype = None
+    lib.bgemul_last_crc.restype = ctypes.c_uint32
+    lib.bgemul_set_piece(1, head_gap, tail_gap, 1 if final else 0)
+    try:
+        rc, m = emul_block(payload, level, order)
+        assert rc == 0, rc
+        return m, lib.bgemul_last_crc()
+    finally:
+        lib.bgemul_set_piece(0, 0, 0, 1)
+
+
 def emul_stream(data, level=6, block=BLOCK, order=0, eof=True):
     out = bytearray()
     for off in range(0, len(data), block):
@@ -226,3 +241,56 @@ def bamlike(n, seed=5):
         if len(out) >= n:
             break
     return bytes(out[:n])
+
+
+# ---- the other containers: pieces from the emulator + the library's framing (no GPU) ----
+REF_CIELBOX = os.path.join(ROOT, "oracle", "_ref", "cielbox_ref")
+DICTZIP_MAX_CHUNKS = 32762
+
+
+def codec_module():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "7bgzf_b200"))
+    import b200bgzf
+    return b200bgzf
+
+
+def emul_container(kind, data, level=6, param=0):
+    """The container b200bgzf_container_compress_host writes, with the emulator standing in for the kernel."""
+    B = codec_module()
+    lib = B.load()
+    bs, sp = B.container_plan(kind, param, lib)
+    blocks = [data[i : i + bs] for i in range(0, len(data), bs)]
+    per = DICTZIP_MAX_CHUNKS if kind == B.CONTAINER_DICTZIP else max(len(blocks), 1)
+    out, done = bytearray(), 0
+    while True:
+        part = blocks[done : done + per]
+        stream, offs, crcs = bytearray(), [], []
+        for i, b in enumerate(part):
+            first = i % sp.member_blocks == 0
+            last = (i + 1) % sp.member_blocks == 0 or i + 1 == len(part)
+            m, crc = emul_piece(b, level, sp.head_gap if first else 0, sp.tail_gap if last else 0, last and not sp.no_final)
+            offs.append(len(stream))
+            crcs.append(crc)
+            stream += m
+        out += B.container_frame(kind, param, bytes(stream), offs, crcs, sum(map(len, part)), lib)
+        done += len(part)
+        if done >= len(blocks):
+            return bytes(out)
+
+
+def ref_applet_decode(applet, blob):
+    """Decode `blob` with the reference's own applet (7gzip / 7migz read stdin; 7gzinga / 7dictzip / 7razf take a file)."""
+    import subprocess, tempfile
+    with tempfile.NamedTemporaryFile(delete=False) as f:
+        f.write(blob)
+        name = f.name
+    try:
+        if applet in ("7gzip", "7migz", "7bgzf"):
+            with open(name, "rb") as fin:
+                r = subprocess.run([REF_CIELBOX, applet, "-d"], stdin=fin, capture_output=True)
+        else:
+            r = subprocess.run([REF_CIELBOX, applet, "-cd", name], capture_output=True)
+        return r.returncode, r.stdout
+    finally:
+        os.unlink(name)

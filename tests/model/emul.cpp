@@ -46,6 +46,17 @@ void run(phase_fn f, const BgCtx &c, int order, uint32_t seed)
 static uint32_t g_emul_hdr = 18;
 /* member framing of the following bgemul_compress_block calls: 18 = BGZF (default), 20 = MiGz */
 extern "C" void bgemul_set_header_bytes(uint32_t hdr) { g_emul_hdr = hdr == 20 ? 20 : 18; }
+/* piece mode of the following calls (BgCtx.piece): head / tail gap bytes and whether the piece is the final DEFLATE block;
+ * enable = 0 returns to members */
+static uint32_t g_emul_piece = 0, g_emul_head = 0, g_emul_tail = 0, g_emul_final = 1, g_emul_crc = 0;
+extern "C" void bgemul_set_piece(uint32_t enable, uint32_t head_gap, uint32_t tail_gap, uint32_t final)
+{
+    g_emul_piece = enable ? 1 : 0;
+    g_emul_head = head_gap;
+    g_emul_tail = tail_gap;
+    g_emul_final = final ? 1 : 0;
+}
+extern "C" uint32_t bgemul_last_crc(void) { return g_emul_crc; }
 
 extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, int order, uint8_t *dst, uint32_t *dlen)
 {
@@ -75,7 +86,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     c.crcpow = e->crcpow.data();
     c.perm = nullptr;
     c.n = n;
-    c.hdr = g_emul_hdr;
+    c.frame = g_emul_piece ? bg_frame(g_emul_head, g_emul_tail, g_emul_final, 1u) : bg_frame(g_emul_hdr, 8u, 1u, 0u);
     c.prm = bg_level_params(level);
     uint32_t k = 0;
     run(bg_phase_init, c, order, k++);
@@ -161,7 +172,8 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     if (c.scal[BG_S_STATUS]) return 1;
     run(bg_phase_zero_out, c, order, k++);
     run(bg_phase_emit, c, order, k++);
-    uint32_t total = c.hdr + c.scal[BG_S_PAYLOAD] + 8;
+    uint32_t total = bg_f_hdr(c) + c.scal[BG_S_PAYLOAD] + bg_f_trl(c);
+    g_emul_crc = c.scal[BG_S_CRC];
     memcpy(dst, e->out.data(), total);
     *dlen = total;
     return 0;

@@ -1,0 +1,338 @@
+"""the other block-gzip containers (MiGz at any member size, GZinga, dictzip, RAZF) and
+whole-stream gzip, written around raw DEFLATE pieces.  CPU part: the emulator makes the pieces (the very code the kernel
+runs), the library's framing (7bgzf_b200/host/containers.c, no GPU involved) wraps them, and the reference's own decoders
+(`7gzip -d`, `7migz -d`, `7gzinga -cd`, `7dictzip -cd`, `7razf -cd` of the compiled reference) must give the input back.
+GPU part: the product's containers are byte-identical to the emulated ones."""
+import ctypes
+import gzip
+import os
+import struct
+import zlib
+
+import pytest
+
+import helpers as H
+
+B = H.codec_module()
+needs_ref = pytest.mark.skipif(not os.path.exists(H.REF_CIELBOX), reason="oracle/_ref not built")
+KINDS = {"gzip": B.CONTAINER_GZIP, "migz": B.CONTAINER_MIGZ, "gzinga": B.CONTAINER_GZINGA, "dictzip": B.CONTAINER_DICTZIP, "razf": B.CONTAINER_RAZF}
+APPLET = {"gzip": "7gzip", "migz": "7migz", "gzinga": "7gzinga", "dictzip": "7dictzip", "razf": "7razf"}
+INPUTS = {
+    "fastq": H.synth("fastq", 700001), "sam": H.synth("sam", 300000), "noise": H.lcg_noise(200000), "one": b"x",
+    "zeros": bytes(150000), "edge": H.synth("fastq", 2 * 51200),      # exactly one GZinga member, two pieces
+}
+
+
+def test_crc32_combine_matches_zlib():
+    lib = B.load()
+    a, b = H.lcg_noise(1000), H.synth("sam", 70001)
+    for x, y in ((a, b), (b, a), (a, b""), (b"", a), (b, b)):
+        assert lib.b200bgzf_crc32_combine(zlib.crc32(x), zlib.crc32(y), len(y)) == zlib.crc32(x + y)
+    assert lib.b200bgzf_crc32_combine(zlib.crc32(a), zlib.crc32(bytes(1 << 20)), 1 << 20) == zlib.crc32(a + bytes(1 << 20))
+    assert lib.b200bgzf_crc32_combine(0x12345678, 0x9abcdef0, 5 << 32) == H.oracle().oracle_crc32_combine(0x12345678, 0x9abcdef0, 5 << 32)
+
+
+def test_plans_keep_a_stored_piece_inside_its_slot():
+    lib = B.load()
+    for kind in KINDS.values():
+        for param in (0, 1, 63, 64, 100, 512, 1000, 4000):
+            if kind == B.CONTAINER_DICTZIP and param and param < 16:
+                continue
+            bs, sp = B.container_plan(kind, param if kind in (B.CONTAINER_MIGZ, B.CONTAINER_DICTZIP) else 0, lib)
+            assert 0 < bs <= 65280 and bs + 5 + sp.head_gap + sp.tail_gap <= 65536
+            if kind == B.CONTAINER_MIGZ:
+                assert bs * sp.member_blocks == (param or 512) * 1024
+    with pytest.raises(B.B200BgzfError):
+        B.container_plan(B.CONTAINER_DICTZIP, 65281, lib)
+    with pytest.raises(B.B200BgzfError):
+        B.container_plan(9, 0, lib)
+
+
+def test_non_final_pieces_end_on_a_byte_and_decode_alone():
+    data = H.synth("fastq", 4 * 32768 + 17)
+    whole = zlib.decompressobj(-15)
+    got = b""
+    blocks = [data[i : i + 32768] for i in range(0, len(data), 32768)]
+    for i, b in enumerate(blocks):
+        last = i + 1 == len(blocks)
+        m, crc = H.emul_piece(b, 6, final=last)
+        assert crc == zlib.crc32(b)
+        one = zlib.decompressobj(-15)
+        assert one.decompress(m) == b and one.eof == last
+        if not last:
+            assert m.endswith(b"\x00\x00\xff\xff")          # the empty stored block of a full flush
+        got += whole.decompress(m)
+    assert got == data and whole.eof
+
+
+@pytest.mark.parametrize("level", [1, 6, 12])
+@pytest.mark.parametrize("name", sorted(INPUTS))
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_emulated_containers_decode_with_zlib(kind, name, level):
+    if level != 6 and name not in ("fastq", "noise"):
+        pytest.skip("levels 1 and 12 on two corpora")
+    data = INPUTS[name]
+    blob = H.emul_container(KINDS[kind], data, level)
+    if kind == "razf":
+        assert zlib.decompressobj(31).decompress(blob) == data      # (the block index follows the member)
+    else:
+        assert gzip.decompress(blob) == data
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(INPUTS))
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_emulated_containers_decode_with_the_reference_applets(kind, name):
+    data = INPUTS[name]
+    blob = H.emul_container(KINDS[kind], data, 6)
+    if kind == "gzinga" and len(blob) < 32768:
+        pytest.skip("the reference's GZinga reader looks for the index in the last 32 KiB and fails on smaller files (applet/7gzinga.c:232-236)")
+    rc, out = H.ref_applet_decode(APPLET[kind], blob)
+    assert out == data, (rc, len(out))
+
+
+@needs_ref
+@pytest.mark.parametrize("kib", [16, 63, 64, 100, 512])
+def test_migz_members_of_any_size_through_the_reference_reader(kib):
+    data = H.synth("sam", 1200000)
+    blob = H.emul_container(B.CONTAINER_MIGZ, data, 6, kib)
+    # every member: subfield MZ carries the DEFLATE size, ISIZE the member's share of the input
+    off, total = 0, 0
+    while off < len(blob):
+        assert blob[off : off + 16] == bytes.fromhex("1f8b08040000000000ff08004d5a0400")
+        dsz = struct.unpack_from("<I", blob, off + 16)[0]
+        isize = struct.unpack_from("<I", blob, off + 20 + dsz + 4)[0]
+        assert isize == min(kib * 1024, len(data) - total)
+        total += isize
+        off += 20 + dsz + 8
+    assert off == len(blob) and total == len(data)
+    rc, out = H.ref_applet_decode("7migz", blob)
+    assert out == data, rc
+
+
+def test_container_layouts():
+    data = H.synth("fastq", 300000)
+    # GZinga: index member lists the end offset of every member
+    z = H.emul_container(B.CONTAINER_GZINGA, data, 6)
+    tail = z.rindex(bytes.fromhex("1f8b0810000000000 0ff".replace(" ", "")))
+    comment = z[tail + 10 : z.index(b"\x00", tail + 10)].decode()
+    ends = [int(e.split(":")[1]) for e in comment.split(";") if e]
+    assert len(ends) == 3 and ends[-1] == tail and all(z[e : e + 4] == b"\x1f\x8b\x08\x10" for e in ends)
+    assert z[tail:].endswith(b"\x00\x03\x00" + bytes(8))
+    # dictzip: the RA table holds every chunk's compressed size; chunks decode on their own
+    d = H.emul_container(B.CONTAINER_DICTZIP, data, 6)
+    xlen, ver, chlen, chcnt = struct.unpack_from("<H", d, 10)[0], *struct.unpack_from("<HHH", d, 16)
+    assert d[12:14] == b"RA" and ver == 1 and chlen == 58315 and chcnt == 6 and xlen == 10 + 2 * chcnt
+    sizes = struct.unpack_from("<%dH" % chcnt, d, 22)
+    pos = 22 + 2 * chcnt
+    for i, sz in enumerate(sizes):
+        assert zlib.decompressobj(-15).decompress(d[pos : pos + sz]) == data[i * chlen : (i + 1) * chlen]
+        pos += sz
+    assert d[pos : pos + 2] == b"\x03\x00" and struct.unpack_from("<II", d, pos + 2) == (zlib.crc32(data), len(data)) and pos + 10 == len(d)
+    # RAZF: big-endian index after the trailer
+    r = H.emul_container(B.CONTAINER_RAZF, data, 6)
+    fsize, index_at = struct.unpack_from(">QQ", r, len(r) - 16)
+    assert fsize == len(data) and r[:19] == bytes.fromhex("1f8b08040000000000030700") + b"RAZF\x01\x80\x00"
+    nblk, bin0 = struct.unpack_from(">IQ", r, index_at)
+    assert nblk == (len(data) + 32767) // 32768 - 1
+    cells = struct.unpack_from(">%dI" % nblk, r, index_at + 12)
+    for i, c in enumerate(cells):
+        blk = zlib.decompressobj(-15).decompress(r[bin0 + c :], 32768)
+        assert blk == data[(i + 1) * 32768 : (i + 2) * 32768]
+    assert struct.unpack_from("<II", r, index_at - 8) == (zlib.crc32(data), len(data))
+
+
+def test_dictzip_splits_into_members_of_32762_chunks():
+    # tiny chunks make the member limit reachable: 40000 chunks of 64 bytes -> two members
+    data = H.synth("sam", 40000 * 64)
+    d = H.emul_container(B.CONTAINER_DICTZIP, data, 6, 64)
+    assert gzip.decompress(d) == data
+    counts, pos = [], 0
+    while pos < len(d):
+        chcnt = struct.unpack_from("<H", d, pos + 20)[0]
+        counts.append(chcnt)
+        pos += 22 + 2 * chcnt + sum(struct.unpack_from("<%dH" % chcnt, d, pos + 22)) + 10
+    assert counts == [32762, 40000 - 32762] and pos == len(d)
+    if os.path.exists(H.REF_CIELBOX):
+        rc, out = H.ref_applet_decode("7dictzip", d)
+        assert out == data, rc
+
+
+def _ref_written(kind, data, tmp_path):
+    """the container as the reference's own writer makes it (libdeflate level 6)"""
+    import subprocess
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    if kind == "dictzip":
+        dst = tmp_path / "out.dz"
+        subprocess.run([H.REF_CIELBOX, "7dictzip", "-cl6", str(src), str(dst)], capture_output=True, check=True)
+        return dst.read_bytes()
+    if kind == "razf":
+        return subprocess.run([H.REF_CIELBOX, "7razf", "-cl6", str(src)], capture_output=True, check=True).stdout
+    with open(src, "rb") as f:
+        return subprocess.run([H.REF_CIELBOX, APPLET[kind], "-cl6"], stdin=f, capture_output=True, check=True).stdout
+
+
+def _check_units(kind, blob, data):
+    """every unit of the reader's list decodes (zlib) to its slice of the data"""
+    units, total = B.container_units(KINDS[kind], blob)
+    assert total == len(data)
+    pos = 0
+    for in_off, in_len, hdr_len, out_len, piece in units:
+        o = zlib.decompressobj(-15)
+        got = o.decompress(blob[in_off + hdr_len : in_off + in_len], out_len) if piece else o.decompress(blob[in_off + hdr_len : in_off + in_len - 8])
+        assert piece or o.eof
+        assert len(got) == out_len and got == data[pos : pos + out_len], (kind, in_off)
+        pos += out_len
+    assert pos == len(data)
+    return units
+
+
+@pytest.mark.parametrize("kind", ["dictzip", "gzinga", "gzip", "razf"])
+def test_readers_list_the_units_of_our_containers(kind):
+    for name in ("fastq", "noise", "one", "edge"):
+        _check_units(kind, H.emul_container(KINDS[kind], INPUTS[name], 6), INPUTS[name])
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["dictzip", "gzinga", "gzip", "razf"])
+def test_readers_list_the_units_of_reference_written_containers(kind, tmp_path):
+    data = INPUTS["fastq"]
+    units = _check_units(kind, _ref_written(kind, data, tmp_path), data)
+    assert len(units) == {"dictzip": 13, "gzinga": 7, "gzip": 1, "razf": 22}[kind]
+
+
+@pytest.mark.parametrize("kind", ["dictzip", "gzinga", "razf"])
+def test_readers_reject_damaged_indexes(kind):
+    blob = H.emul_container(KINDS[kind], INPUTS["sam"], 6)
+    for bad in (blob[:-1], blob[: len(blob) // 2], blob[1:], b"", b"\x1f\x8b" + bytes(40)):
+        with pytest.raises(B.B200BgzfError):
+            B.container_units(KINDS[kind], bad)
+    if kind == "dictzip":
+        dmg = bytearray(blob)
+        dmg[22] ^= 0x40                                  # a chunk size that no longer adds up to the trailer
+        with pytest.raises(B.B200BgzfError):
+            B.container_units(KINDS[kind], bytes(dmg))
+    if kind == "razf":
+        dmg = bytearray(blob)
+        dmg[-1] ^= 0x10                                  # index offset
+        with pytest.raises(B.B200BgzfError):
+            B.container_units(KINDS[kind], bytes(dmg))
+
+
+def test_empty_input():
+    assert gzip.decompress(H.emul_container(B.CONTAINER_GZIP, b"", 6)) == b""
+    assert gzip.decompress(H.emul_container(B.CONTAINER_GZINGA, b"", 6)) == b""
+    assert gzip.decompress(H.emul_container(B.CONTAINER_DICTZIP, b"", 6)) == b""
+    assert H.emul_container(B.CONTAINER_MIGZ, b"", 6) == b""           # (the reference writes nothing either)
+
+
+# ---------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def codec():
+    c = B.Codec(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, 6, 12])
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_gpu_containers_are_the_emulated_ones(codec, kind, level):
+    for name in ("fastq", "noise", "one", "edge"):
+        data = INPUTS[name]
+        assert codec.container(KINDS[kind], data, level) == H.emul_container(KINDS[kind], data, level), (kind, name, level)
+
+
+@pytest.mark.gpu
+def test_gpu_pieces_api(codec):
+    data = H.synth("sam", 5 * 65280 + 123)
+    spec = B.PieceSpec(3, 12, 8, 0)
+    stream, off, crc = codec.compress_pieces(data, spec, 6, 65280)
+    assert len(off) == 6 and off[0] == 0 and crc == [zlib.crc32(data[i * 65280 : (i + 1) * 65280]) for i in range(6)]
+    # members of three pieces: 12 free bytes, one DEFLATE stream, 8 free bytes
+    for first, end in ((0, off[3]), (3, len(stream))):
+        m = stream[off[first] : end]
+        assert m[:12] == bytes(12) and m[-8:] == bytes(8)
+        o = zlib.decompressobj(-15)
+        assert o.decompress(m[12:-8]) == data[first * 65280 : (first + 3) * 65280] and o.eof
+    with pytest.raises(B.B200BgzfError):
+        codec.compress_pieces(data, B.PieceSpec(1, 20, 8, 0), 6, 65536)      # a stored piece would not fit its slot
+
+
+@pytest.mark.gpu
+def test_gpu_large_inputs_decode(codec):
+    data = H.synth("fastq", 256 << 20)
+    g = codec.container(B.CONTAINER_GZIP, data, 6)
+    assert len(g) < 0.26 * len(data)
+    o = zlib.decompressobj(31)
+    assert zlib.crc32(o.decompress(g)) == zlib.crc32(data) and o.eof
+    m = codec.container(B.CONTAINER_MIGZ, data[: 64 << 20], 6)
+    assert gzip.decompress(m) == data[: 64 << 20]
+    if os.path.exists(H.REF_CIELBOX):
+        for kind in ("gzinga", "dictzip", "razf", "migz"):
+            blob = codec.container(KINDS[kind], data[: 64 << 20], 6)
+            rc, out = H.ref_applet_decode(APPLET[kind], blob)
+            assert out == data[: 64 << 20], (kind, rc)
+
+
+@pytest.mark.gpu
+def test_gpu_dictzip_splits_into_members_of_32762_chunks(codec):
+    # tiny chunks make the member limit reachable: 80000 chunks of 64 bytes -> three members
+    data = H.synth("sam", 80000 * 64)
+    d = codec.container(B.CONTAINER_DICTZIP, data, 6, 64)
+    assert gzip.decompress(d) == data
+    counts, pos = [], 0
+    while pos < len(d):
+        chcnt = struct.unpack_from("<H", d, pos + 20)[0]
+        sizes = struct.unpack_from("<%dH" % chcnt, d, pos + 22)
+        counts.append(chcnt)
+        pos += 22 + 2 * chcnt + sum(sizes) + 10
+    assert counts == [32762, 32762, 80000 - 2 * 32762] and pos == len(d)
+    if os.path.exists(H.REF_CIELBOX):
+        rc, out = H.ref_applet_decode("7dictzip", d)
+        assert out == data, rc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_gpu_reads_its_own_containers(codec, kind):
+    for name in ("fastq", "sam", "noise", "one", "edge", "zeros"):
+        data = INPUTS[name]
+        assert codec.container_inflate(KINDS[kind], codec.container(KINDS[kind], data, 6)) == data, (kind, name)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("kind", ["dictzip", "gzinga", "gzip", "migz", "razf"])
+def test_gpu_reads_reference_written_containers(codec, kind, tmp_path):
+    data = H.synth("sam", 3000017)
+    assert codec.container_inflate(KINDS[kind], _ref_written(kind, data, tmp_path)) == data
+
+
+@pytest.mark.gpu
+def test_gpu_unit_list_errors(codec):
+    data = INPUTS["fastq"]
+    blob = codec.container(B.CONTAINER_DICTZIP, data, 6)
+    units, total = B.container_units(B.CONTAINER_DICTZIP, blob)
+    assert codec.inflate_units(blob, units, total) == data
+    # a piece that claims more output than its blocks hold / a unit beyond the input
+    u = list(units)
+    u[2] = (u[2][0], u[2][1] - 9, u[2][2], u[2][3], 1)
+    with pytest.raises(B.B200BgzfError) as e:
+        codec.inflate_units(blob, u, total)
+    assert e.value.code == B.E_FORMAT
+    u = list(units)
+    u[-1] = (len(blob), 100, 0, 10, 1)
+    with pytest.raises(B.B200BgzfError) as e:
+        codec.inflate_units(blob, u, total)
+    assert e.value.code == B.E_FORMAT
+    assert codec.inflate_units(blob, [], 0) == b""
+
+
+@pytest.mark.gpu
+def test_gpu_large_dictzip_and_razf_round_trip(codec):
+    data = H.synth("fastq", 128 << 20)
+    for kind in (B.CONTAINER_DICTZIP, B.CONTAINER_RAZF, B.CONTAINER_GZINGA):
+        blob = codec.container(kind, data, 6)
+        assert zlib.crc32(codec.container_inflate(kind, blob)) == zlib.crc32(data)
