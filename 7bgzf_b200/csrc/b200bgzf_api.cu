@@ -1302,7 +1302,9 @@ int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const 
                 h_hdr[nb] = un.hdr_len;
                 h_msz[nb] = un.in_len;
                 h_isz[nb] = un.piece ? un.out_len : 0xffffffffu;
-                total += un.piece ? un.out_len : rd32(p + un.in_off + un.in_len - 4);
+                const uint32_t unit_out = un.piece ? un.out_len : rd32(p + un.in_off + un.in_len - 4);
+                if (unit_out > 0x7fffffffu) { drain(); return B200BGZF_E_FORMAT; }      /* (the kernel's positions are 32-bit) */
+                total += unit_out;
                 off = (size_t)(un.in_off + un.in_len);
                 nb++;
                 u++;

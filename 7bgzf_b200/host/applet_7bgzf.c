@@ -426,18 +426,30 @@ static int run_pipeline(int ndevices, int decompress, int level, uint32_t block,
     return ret;
 }
 
+int container_applet(const char *name, int kind, int decompress, int level, unsigned param, int nfiles, char **files);   /* applet_containers.c */
+
+static const struct { const char *name; int kind; } k_personas[] = {
+    { "7bgzf", 0 }, { "7migz", B200BGZF_CONTAINER_MIGZ }, { "7gzip", B200BGZF_CONTAINER_GZIP }, { "7gzinga", B200BGZF_CONTAINER_GZINGA },
+    { "7dictzip", B200BGZF_CONTAINER_DICTZIP }, { "7razf", B200BGZF_CONTAINER_RAZF },
+};
+
 int main(int argc, char **argv)
 {
     int levels[NFLAGS];
-    int decompress = 0, nthreads = 1, bad = 0, ndevices = 1, migz = 0, bsize = 63;
-    const char *gzi_path = NULL;
+    int decompress = 0, nthreads = 1, bad = 0, ndevices = 1, migz = 0, bsize = 0, extreme = 0, kind = 0;
+    const char *gzi_path = NULL, *persona = "7bgzf";
     memset(levels, 0, sizeof levels);
-    /* allow `cielbox 7bgzf ...` style invocation; as `7migz` (applet/7migz.c) the same pipeline writes MiGz members:
-     * -b N = payload KiB per member, at most 63 here (one member = one 64 KiB GPU slot; the reference's default is 512) */
-    if (argc > 1 && (!strcmp(argv[1], "7bgzf") || !strcmp(argv[1], "7migz"))) { argv++; argc--; }
+    /* allow `cielbox 7bgzf ...` style invocation.  As `7migz` (applet/7migz.c) with -b N <= 63 the same pipeline writes MiGz
+     * members of N KiB (one member = one 64 KiB GPU slot); larger members (the reference's default is 512 KiB) and the
+     * other containers (7gzip, 7gzinga, 7dictzip, 7razf) are made of several pieces: applet_containers.c */
+    for (size_t k = 0; k < sizeof k_personas / sizeof k_personas[0]; k++)
+        if (argc > 1 && !strcmp(argv[1], k_personas[k].name)) { argv++; argc--; break; }
     {
         const char *base = strrchr(argv[0], '/');
-        migz = !strcmp(base ? base + 1 : argv[0], "7migz");
+        base = base ? base + 1 : argv[0];
+        for (size_t k = 0; k < sizeof k_personas / sizeof k_personas[0]; k++)
+            if (!strcmp(base, k_personas[k].name)) { kind = k_personas[k].kind; persona = k_personas[k].name; }
+        migz = kind == B200BGZF_CONTAINER_MIGZ;
     }
 
     static const struct option longopts[] = {
@@ -450,11 +462,13 @@ int main(int argc, char **argv)
         { "threads", required_argument, 0, '@' }, { "decompress", no_argument, 0, 'd' },
         { "help", no_argument, 0, 'h' },         { "gzi", required_argument, 0, 1000 },
         { "devices", required_argument, 0, 1001 },  { "bsize", required_argument, 0, 'b' },
+        { "extreme", no_argument, 0, 'X' },
         { 0, 0, 0, 0 },
     };
     int opt;
-    while ((opt = getopt_long(argc, argv, "cz::m::s::l::S::n::C::i::K::Z:T::@:dhb:", longopts, NULL)) != -1) {
+    while ((opt = getopt_long(argc, argv, "cz::m::s::l::S::n::C::i::K::Z:T::@:dhb:X", longopts, NULL)) != -1) {
         if (opt == 'c') continue;
+        if (opt == 'X') { extreme = 1; continue; }
         if (opt == 'd') { decompress = 1; continue; }
         if (opt == '@') { nthreads = atoi(optarg); continue; }
         if (opt == 1000) { gzi_path = optarg; continue; }
@@ -472,12 +486,24 @@ int main(int argc, char **argv)
         usage(argv[0]);
         return 1;
     }
+    struct timeval t0, t1;
+    gettimeofday(&t0, NULL);
+    if (migz && !bsize) bsize = 512;                               /* applet/7migz.c:327 */
+    if (kind && !(migz && (decompress || bsize <= 63) && optind == argc)) {
+        /* a container whose members span several pieces (or one that is read through its index) */
+        int level = level_sum < 1 ? 1 : level_sum > 12 ? 12 : level_sum;
+        if (!decompress) fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
+        if (migz && !decompress && (bsize < 1 || bsize > 4194303)) { fprintf(stderr, "7migz: -b %d: bad member size\n", bsize); return 1; }
+        const unsigned param = migz ? (unsigned)bsize : kind == B200BGZF_CONTAINER_DICTZIP && extreme ? B200BGZF_BLOCK_SIZE : 0u;
+        const int ret = container_applet(persona, kind, decompress, level, param, argc - optind, argv + optind);
+        gettimeofday(&t1, NULL);
+        fprintf(stderr, "ellapsed time: %.6f sec\n", (t1.tv_sec + t1.tv_usec * 0.000001) - (t0.tv_sec + t0.tv_usec * 0.000001));
+        return ret;
+    }
     if (isatty(fileno(stdin)) || isatty(fileno(stdout))) {
         usage(argv[0]);
         return -1;
     }
-    struct timeval t0, t1;
-    gettimeofday(&t0, NULL);
     {
         struct stat st;
         g_in_regular = fstat(0, &st) == 0 && S_ISREG(st.st_mode);
@@ -494,10 +520,6 @@ int main(int argc, char **argv)
         if (level > 12) level = 12;
         /* block size rule of the reference (7bgzf.c:141-147): 0x10000 with one thread, 0xff00 with -@N; the thread count has
          * no other meaning here (the GPU works on all blocks of a slot at once) */
-        if (migz && (bsize < 1 || bsize > 63)) {
-            fprintf(stderr, "7migz: -b %d: members of more than 63 KiB of payload do not fit the GPU codec's 64 KiB slots\n", bsize);
-            return 1;
-        }
         if (migz) g_frame_flags = B200BGZF_FRAME_MIGZ;
         ret = run_pipeline(ndevices, 0, level, migz ? (uint32_t)bsize * 1024u : nthreads == 1 ? B200BGZF_MAX_BLOCK_SIZE : B200BGZF_BLOCK_SIZE, gzi_path);
     }

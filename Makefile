@@ -14,7 +14,8 @@ CU_SRCS   := $(CSRC)/bgzf_compress.cu $(CSRC)/bgzf_inflate.cu $(CSRC)/b200bgzf_a
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.h) include/b200bgzf.h
 
-all: $(PKG)/lib7bgzf_b200.so $(PKG)/7bgzf.so $(PKG)/7bgzf $(PKG)/7migz
+PERSONAS  := $(PKG)/7migz $(PKG)/7gzip $(PKG)/7gzinga $(PKG)/7dictzip $(PKG)/7razf
+all: $(PKG)/lib7bgzf_b200.so $(PKG)/7bgzf.so $(PKG)/7bgzf $(PERSONAS)
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -33,11 +34,11 @@ $(PKG)/7bgzf.so: $(CU_OBJS) $(OBJ)/method.o $(OBJ)/multi.o $(OBJ)/containers.o $
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker --version-script=$(HOST)/exports.map -lpthread
 
 # the applet
-$(PKG)/7bgzf: $(OBJ)/applet_7bgzf.o $(PKG)/lib7bgzf_b200.so
-	$(CC) -o $@ $(OBJ)/applet_7bgzf.o -L$(PKG) -l7bgzf_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
+$(PKG)/7bgzf: $(OBJ)/applet_7bgzf.o $(OBJ)/applet_containers.o $(PKG)/lib7bgzf_b200.so
+	$(CC) -o $@ $(OBJ)/applet_7bgzf.o $(OBJ)/applet_containers.o -L$(PKG) -l7bgzf_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
 
-# the same applet under its MiGz name (applet/7migz.c: the reference is a multi-call binary too)
-$(PKG)/7migz: $(PKG)/7bgzf
+# the same applet under its other names (the reference is a multi-call binary too: cielbox.c:215-223)
+$(PERSONAS): $(PKG)/7bgzf
 	ln -sf 7bgzf $@
 
 # the same library with the bounds asserts compiled in (BG_ASSERT, csrc/bgzf_block.h): point the GPU tests at it with
@@ -65,6 +66,6 @@ oracle/liboracle.so: $(wildcard oracle/*.c)
 	$(CC) -O2 -fPIC -shared -pthread -o $@ $(wildcard oracle/*.c) -ldl
 
 clean:
-	rm -rf build $(PKG)/*.so $(PKG)/7bgzf $(PKG)/7migz oracle/liboracle.so
+	rm -rf build $(PKG)/*.so $(PKG)/7bgzf $(PERSONAS) oracle/liboracle.so
 
 .PHONY: all testlibs clean checked

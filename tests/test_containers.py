@@ -336,3 +336,53 @@ def test_gpu_large_dictzip_and_razf_round_trip(codec):
     for kind in (B.CONTAINER_DICTZIP, B.CONTAINER_RAZF, B.CONTAINER_GZINGA):
         blob = codec.container(kind, data, 6)
         assert zlib.crc32(codec.container_inflate(kind, blob)) == zlib.crc32(data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_gpu_applet_personalities(codec, kind, tmp_path):
+    """the applet under the reference's other names, with the reference's command lines: same bytes as the library call;
+    the reference's applet reads them; ours reads the reference's"""
+    import subprocess
+    data = H.synth("fastq", 1500000)
+    exe = os.path.join(os.path.dirname(B.APPLET_PATH), APPLET[kind])
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    enc = tmp_path / "enc.bin"
+    if kind == "dictzip":
+        r = subprocess.run([exe, "-cl6", str(src), str(enc)], capture_output=True)
+        blob = enc.read_bytes()
+    elif kind == "razf":
+        r = subprocess.run([exe, "-cl6", str(src)], capture_output=True)
+        blob = r.stdout
+    else:
+        r = subprocess.run([exe, "-cl6"], input=data, capture_output=True)
+        blob = r.stdout
+    assert r.returncode == 0, r.stderr
+    assert b"compression level = 6 (libdeflate)" in r.stderr and b"done." in r.stderr and b"ellapsed time" in r.stderr
+    assert blob == codec.container(KINDS[kind], data, 6)
+    enc.write_bytes(blob)
+    # decode: file operand for the indexed containers (as the reference wants it), stdin for gzip / MiGz
+    if kind in ("gzip", "migz"):
+        d = subprocess.run([exe, "-d"], input=blob, capture_output=True)
+    else:
+        d = subprocess.run([exe, "-cd", str(enc)], capture_output=True)
+    assert d.returncode == 0 and d.stdout == data, d.stderr
+    if os.path.exists(H.REF_CIELBOX):
+        rc, out = H.ref_applet_decode(APPLET[kind], blob)
+        assert out == data, rc
+        theirs = tmp_path / "ref.bin"
+        theirs.write_bytes(_ref_written(kind, data, tmp_path))
+        if kind in ("gzip", "migz"):
+            d = subprocess.run([exe, "-d"], input=theirs.read_bytes(), capture_output=True)
+        else:
+            d = subprocess.run([exe, "-cd", str(theirs)], capture_output=True)
+        assert d.returncode == 0 and d.stdout == data, d.stderr
+    if kind == "dictzip":
+        x = subprocess.run([exe, "-cl6", "-X", str(src), str(enc)], capture_output=True)
+        assert x.returncode == 0 and enc.read_bytes() == codec.container(KINDS[kind], data, 6, 65280)
+    # damaged input: an error, not a crash
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(blob[: len(blob) // 2])
+    e = subprocess.run([exe, "-cd", str(bad)] if kind not in ("gzip", "migz") else [exe, "-d"], input=blob[: len(blob) // 2] if kind in ("gzip", "migz") else None, capture_output=True)
+    assert e.returncode != 0
