@@ -584,8 +584,6 @@ extern "C" int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, 
                                              uint64_t *piece_off, uint32_t *piece_crc, size_t piece_cap)
 {
     if (!ps || ps->member_blocks == 0 || ps->head_gap > B200BGZF_MAX_GAP || ps->tail_gap > B200BGZF_MAX_GAP) return B200BGZF_E_ARG;
-    /* a stored piece (5 bytes of block header) and both gaps must stay inside the 64 KiB slot */
-    if ((uint64_t)block_size + 5u + ps->head_gap + ps->tail_gap > B200BGZF_MAX_BLOCK_SIZE) return B200BGZF_E_ARG;
     if (piece_crc && piece_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
     return compress_host_impl(ctx, in, in_bytes, block_size, level, out, out_cap, out_bytes, 0, piece_off, piece_cap, ps, piece_crc);
 }

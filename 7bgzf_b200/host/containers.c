@@ -49,7 +49,7 @@ static void put32(uint8_t *p, uint32_t v) { put16(p, v); put16(p + 2, v >> 16); 
 static void put32be(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 static void put64be(uint8_t *p, uint64_t v) { put32be(p, (uint32_t)(v >> 32)); put32be(p + 4, (uint32_t)v); }
 
-static uint32_t migz_member_bytes(uint32_t param) { return (param ? param : 512u) * 1024u; }
+static uint32_t migz_member_bytes(uint32_t kib) { return (kib ? kib : 512u) * 1024u; }
 
 int b200bgzf_container_plan(int kind, uint32_t param, uint32_t *block_size, b200bgzf_piece_spec *spec)
 {
@@ -61,10 +61,14 @@ int b200bgzf_container_plan(int kind, uint32_t param, uint32_t *block_size, b200
         spec->member_blocks = ONE_MEMBER; spec->head_gap = 10; spec->tail_gap = 8;
         return B200BGZF_OK;
     case B200BGZF_CONTAINER_MIGZ: {
-        if (param > 4u * 1024u * 1024u - 1u) return B200BGZF_E_ARG;           /* ISIZE and the MZ field are 32 bits */
-        const uint32_t m = migz_member_bytes(param);
-        /* the fewest equal pieces of at most 65280 bytes that make up a member exactly */
-        uint32_t k = (m + PIECE_MAX - 1u) / PIECE_MAX;
+        const uint32_t kib = param & ~B200BGZF_PARAM_SAFE;
+        if (kib > 4u * 1024u * 1024u - 1u) return B200BGZF_E_ARG;             /* ISIZE and the MZ field are 32 bits */
+        const uint32_t m = migz_member_bytes(kib);
+        /* the fewest equal pieces that make up a member exactly: of at most 65536 bytes (512 KiB = 8 x 64 KiB; a piece that
+         * does not compress at all then overflows its slot and the call reports B200BGZF_E_NOFIT), or, with
+         * B200BGZF_PARAM_SAFE, of at most 65280 bytes so that even a stored piece fits (512 KiB = 16 x 32 KiB) */
+        const uint32_t most = (param & B200BGZF_PARAM_SAFE) ? PIECE_MAX : 65536u;
+        uint32_t k = (m + most - 1u) / most;
         while (m % k) k++;
         *block_size = m / k;
         spec->member_blocks = k; spec->head_gap = 20; spec->tail_gap = 8;
@@ -93,8 +97,8 @@ size_t b200bgzf_container_bound(int kind, uint32_t param, size_t in_bytes)
 {
     uint32_t bs;
     b200bgzf_piece_spec sp;
-    if (b200bgzf_container_plan(kind, param, &bs, &sp) != 0) return 0;
-    const size_t np = (in_bytes + bs - 1) / bs;
+    if (b200bgzf_container_plan(kind, kind == B200BGZF_CONTAINER_MIGZ ? param | B200BGZF_PARAM_SAFE : param, &bs, &sp) != 0) return 0;
+    const size_t np = (in_bytes + bs - 1) / bs;                                 /* (the plan with the most pieces) */
     size_t extra = 64;
     if (kind == B200BGZF_CONTAINER_GZINGA) extra += 32 + 34 * ((np + 1) / 2);   /* "n:offset;" per member */
     if (kind == B200BGZF_CONTAINER_RAZF) extra += 4 * np + 64;
@@ -280,6 +284,10 @@ int b200bgzf_container_compress_host(b200bgzf_ctx *ctx, int kind, uint32_t param
     } while (done < np_total);
     free(off);
     free(crc);
+    if (rc == B200BGZF_E_NOFIT && kind == B200BGZF_CONTAINER_MIGZ && !(param & B200BGZF_PARAM_SAFE))
+        /* a 64 KiB piece that does not compress overflows its slot: redo the file with pieces that always fit (the reference's
+         * BGZF writer does the same with its 0x10000-byte blocks, applet/7bgzf.c:256-262) */
+        return b200bgzf_container_compress_host(ctx, kind, param | B200BGZF_PARAM_SAFE, in, in_bytes, level, out, out_cap, out_bytes);
     if (rc == 0) *out_bytes = pos;
     return rc;
 }

@@ -158,7 +158,8 @@ int b200bgzf_multi_inflate_host(b200bgzf_multi *m, const void *in, size_t in_byt
  * stream, and each piece also decodes on its own.  head_gap / tail_gap zero bytes are left before a member's first and
  * after its last piece for the container's header and trailer.  Returns the pieces (with their gaps) back to back in
  * `out`, piece_off[b] = where piece b (or its head gap) starts, piece_crc[b] = CRC-32 of block b's input (combine them
- * with b200bgzf_crc32_combine).  block_size + 5 + head_gap + tail_gap must not exceed 65536.
+ * with b200bgzf_crc32_combine).  With block_size + 5 + head_gap + tail_gap <= 65536 every piece fits its 64 KiB slot whatever
+ * the data; beyond that (up to block_size 65536) a piece that does not compress makes the call return B200BGZF_E_NOFIT.
  */
 #define B200BGZF_MAX_GAP 64u
 typedef struct b200bgzf_piece_spec {
@@ -187,6 +188,7 @@ uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
  *            inputs below 4 GiB
  * b200bgzf_container_compress_host = plan + b200bgzf_compress_pieces_host + b200bgzf_container_frame.
  */
+#define B200BGZF_PARAM_SAFE 0x80000000u   /* MiGz: or-ed into param: pieces of at most 65280 bytes (see b200bgzf_container_plan) */
 #define B200BGZF_CONTAINER_GZIP 1
 #define B200BGZF_CONTAINER_MIGZ 2
 #define B200BGZF_CONTAINER_GZINGA 3

@@ -70,6 +70,8 @@ def emul_piece(payload, level=6, head_gap=0, tail_gap=0, final=True, order=0):
     lib.bgemul_set_piece(1, head_gap, tail_gap, 1 if final else 0)
     try:
         rc, m = emul_block(payload, level, order)
+        if rc == 1:
+            raise OverflowError("the piece does not fit its slot")
         assert rc == 0, rc
         return m, lib.bgemul_last_crc()
     finally:
@@ -259,6 +261,16 @@ def emul_container(kind, data, level=6, param=0):
     """The container b200bgzf_container_compress_host writes, with the emulator standing in for the kernel."""
     B = codec_module()
     lib = B.load()
+    bs, sp = B.container_plan(kind, param, lib)
+    if kind == B.CONTAINER_MIGZ and not param & 0x80000000:
+        try:
+            return _emul_container(B, lib, kind, data, level, param)
+        except OverflowError:                      # a 64 KiB piece that does not compress: the library redoes the file with small pieces
+            return _emul_container(B, lib, kind, data, level, param | 0x80000000)
+    return _emul_container(B, lib, kind, data, level, param)
+
+
+def _emul_container(B, lib, kind, data, level, param):
     bs, sp = B.container_plan(kind, param, lib)
     blocks = [data[i : i + bs] for i in range(0, len(data), bs)]
     per = DICTZIP_MAX_CHUNKS if kind == B.CONTAINER_DICTZIP else max(len(blocks), 1)

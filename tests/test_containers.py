@@ -38,10 +38,13 @@ def test_plans_keep_a_stored_piece_inside_its_slot():
         for param in (0, 1, 63, 64, 100, 512, 1000, 4000):
             if kind == B.CONTAINER_DICTZIP and param and param < 16:
                 continue
-            bs, sp = B.container_plan(kind, param if kind in (B.CONTAINER_MIGZ, B.CONTAINER_DICTZIP) else 0, lib)
+            safe = 0x80000000 if kind == B.CONTAINER_MIGZ else 0
+            bs, sp = B.container_plan(kind, (param if kind in (B.CONTAINER_MIGZ, B.CONTAINER_DICTZIP) else 0) | safe, lib)
             assert 0 < bs <= 65280 and bs + 5 + sp.head_gap + sp.tail_gap <= 65536
             if kind == B.CONTAINER_MIGZ:
                 assert bs * sp.member_blocks == (param or 512) * 1024
+                bs, sp = B.container_plan(kind, param, lib)              # the first choice: pieces of up to 64 KiB
+                assert 0 < bs <= 65536 and bs * sp.member_blocks == (param or 512) * 1024
     with pytest.raises(B.B200BgzfError):
         B.container_plan(B.CONTAINER_DICTZIP, 65281, lib)
     with pytest.raises(B.B200BgzfError):
@@ -256,8 +259,20 @@ def test_gpu_pieces_api(codec):
         assert m[:12] == bytes(12) and m[-8:] == bytes(8)
         o = zlib.decompressobj(-15)
         assert o.decompress(m[12:-8]) == data[first * 65280 : (first + 3) * 65280] and o.eof
-    with pytest.raises(B.B200BgzfError):
-        codec.compress_pieces(data, B.PieceSpec(1, 20, 8, 0), 6, 65536)      # a stored piece would not fit its slot
+    # 65536-byte pieces fit while they compress; one that does not is reported, not truncated
+    stream, off, crc = codec.compress_pieces(data, B.PieceSpec(1, 20, 8, 0), 6, 65536)
+    assert len(off) == 5
+    with pytest.raises(B.B200BgzfError) as e:
+        codec.compress_pieces(H.lcg_noise(3 * 65536), B.PieceSpec(1, 20, 8, 0), 6, 65536)
+    assert e.value.code == B.E_NOFIT
+
+
+@pytest.mark.gpu
+def test_gpu_migz_falls_back_to_small_pieces_on_incompressible_data(codec):
+    data = H.synth("fastq", 1 << 20) + H.lcg_noise(1 << 19) + H.synth("sam", 1 << 19)
+    blob = codec.container(B.CONTAINER_MIGZ, data, 6)
+    assert blob == H.emul_container(B.CONTAINER_MIGZ, data, 6, 0x80000000) and gzip.decompress(blob) == data
+    assert codec.container(B.CONTAINER_MIGZ, data[: 1 << 20], 6) == H.emul_container(B.CONTAINER_MIGZ, data[: 1 << 20], 6)
 
 
 @pytest.mark.gpu

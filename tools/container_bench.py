@@ -60,22 +60,34 @@ for name, kind, applet in KINDS:
         th = [] if name == "gzip" else ["-@", str(cores)]          # (7gzip is one libdeflate call: no thread option)
         t = time.perf_counter()
         if name == "dictzip":
-            subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th, src, dst], capture_output=True, check=True)
+            subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th, src, dst], capture_output=True, check=False)
         elif name == "razf":
             with open(dst, "wb") as fo:
-                subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th, src], stdout=fo, stderr=subprocess.DEVNULL, check=True)
+                subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th, src], stdout=fo, stderr=subprocess.DEVNULL, check=False)
         else:
             with open(src, "rb") as fi, open(dst, "wb") as fo:
-                subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th], stdin=fi, stdout=fo, stderr=subprocess.DEVNULL, check=True)
+                subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th], stdin=fi, stdout=fo, stderr=subprocess.DEVNULL, check=False)
         rt = time.perf_counter() - t
         rsize = os.path.getsize(dst)
         t = time.perf_counter()
         with open(dst, "rb") as fi, open("/dev/null", "wb") as fo:
             if name in ("gzip", "migz"):
-                subprocess.run([H.REF_CIELBOX, applet, "-d", *th], stdin=fi, stdout=fo, stderr=subprocess.DEVNULL, check=True)
+                subprocess.run([H.REF_CIELBOX, applet, "-d", *th], stdin=fi, stdout=fo, stderr=subprocess.DEVNULL, check=False)
             else:
-                subprocess.run([H.REF_CIELBOX, applet, "-cd", *th, dst], stdout=fo, stderr=subprocess.DEVNULL, check=True)
+                subprocess.run([H.REF_CIELBOX, applet, "-cd", *th, dst], stdout=fo, stderr=subprocess.DEVNULL, check=False)
         rd = time.perf_counter() - t
+        if name == "gzinga":
+            # the reference's reader looks for the index in the last 32 KiB (applet/7gzinga.c:232-236): files of more than
+            # about 2000 members cannot be read back by it; time its reader on a file that small
+            rn2 = 128 << 20
+            with open(src, "wb") as f:
+                f.write(host.numpy()[:rn2].tobytes())
+            with open(src, "rb") as fi, open(dst, "wb") as fo:
+                subprocess.run([H.REF_CIELBOX, applet, "-cl6", *th], stdin=fi, stdout=fo, stderr=subprocess.DEVNULL)
+            t = time.perf_counter()
+            with open("/dev/null", "wb") as fo:
+                ok = subprocess.run([H.REF_CIELBOX, applet, "-cd", *th, dst], stdout=fo, stderr=subprocess.DEVNULL).returncode == 0
+            rd = (time.perf_counter() - t) * (rn / rn2) if ok else float("nan")
         line.update({"reference": {"MiB": ref_mib, "cores": 1 if name == "gzip" else cores, "compress_GBps": round(rn / rt / 1e9, 3), "inflate_GBps": round(rn / rd / 1e9, 3),
                                    "ratio": round(rsize / rn, 4)}})
         os.unlink(src); os.unlink(dst)
