@@ -33,15 +33,21 @@ static uint32_t mulmodp(uint32_t a, uint32_t b)
     return p;
 }
 
-uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
+/* x^(8 n) mod P */
+static uint32_t xpow8(uint64_t n)
 {
-    /* CRC(A||B) = CRC(A) * x^(8 len B) + CRC(B)  (mod P), the conditioning of both ends cancels */
     uint32_t r = 0x80000000u, sq = 0x00800000u;                 /* 1, x^8 */
-    for (uint64_t n = len_b; n; n >>= 1) {
+    for (; n; n >>= 1) {
         if (n & 1u) r = mulmodp(r, sq);
         sq = mulmodp(sq, sq);
     }
-    return mulmodp(r, crc_a) ^ crc_b;
+    return r;
+}
+
+uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
+{
+    /* CRC(A||B) = CRC(A) * x^(8 len B) + CRC(B)  (mod P), the conditioning of both ends cancels */
+    return mulmodp(xpow8(len_b), crc_a) ^ crc_b;
 }
 
 static void put16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
@@ -106,14 +112,14 @@ size_t b200bgzf_container_bound(int kind, uint32_t param, size_t in_bytes)
     return b200bgzf_compress_bound(in_bytes, bs) + b200bgzf_pieces_gap_bytes(in_bytes, bs, &sp) + extra;
 }
 
-/* CRC-32 and byte count of the input behind pieces [f, l] */
-static uint32_t span_crc(const uint32_t *crc, size_t f, size_t l, size_t npieces, uint32_t bs, size_t in_bytes, uint64_t *bytes)
+/* CRC-32 and byte count of the input behind pieces [f, l]; shift = x^(8 bs): all pieces but the stream's last are bs bytes long */
+static uint32_t span_crc(const uint32_t *crc, size_t f, size_t l, size_t npieces, uint32_t bs, uint32_t shift, size_t in_bytes, uint64_t *bytes)
 {
     uint32_t c = 0;
     uint64_t n = 0;
     for (size_t i = f; i <= l; i++) {
         const uint64_t len = i + 1 == npieces ? in_bytes - (uint64_t)i * bs : bs;
-        c = i == f ? crc[i] : b200bgzf_crc32_combine(c, crc[i], len);
+        c = i == f ? crc[i] : len == bs ? mulmodp(shift, c) ^ crc[i] : b200bgzf_crc32_combine(c, crc[i], len);
         n += len;
     }
     *bytes = n;
@@ -130,6 +136,7 @@ size_t b200bgzf_container_frame(int kind, uint32_t param, void *member, size_t c
     if (npieces && (!piece_off || !piece_crc)) return 0;
     if (npieces != (in_bytes + bs - 1) / bs) return 0;
     uint64_t nbytes = 0;
+    const uint32_t shift = xpow8(bs);
 
     if (kind == B200BGZF_CONTAINER_DICTZIP) {
         if (npieces > DICTZIP_MAX_CHUNKS) return 0;
@@ -151,7 +158,7 @@ size_t b200bgzf_container_frame(int kind, uint32_t param, void *member, size_t c
             if (sz > 0xffffu) return 0;
             put16(o + 22 + 2 * i, (uint32_t)sz);
         }
-        const uint32_t crc = npieces ? span_crc(piece_crc, 0, npieces - 1, npieces, bs, in_bytes, &nbytes) : 0u;
+        const uint32_t crc = npieces ? span_crc(piece_crc, 0, npieces - 1, npieces, bs, shift, in_bytes, &nbytes) : 0u;
         o[end - 10] = 0x03; o[end - 9] = 0x00;                   /* "null deflation to conform normal gzip" (7dictzip.c:311) */
         put32(o + end - 8, crc);
         put32(o + end - 4, (uint32_t)in_bytes);
@@ -179,7 +186,7 @@ size_t b200bgzf_container_frame(int kind, uint32_t param, void *member, size_t c
         const uint64_t start = piece_off[f], end = l + 1 < npieces ? piece_off[l + 1] : stream_bytes;
         if (end < start + sp.head_gap + sp.tail_gap || end > stream_bytes) return 0;
         uint8_t *h = o + start;
-        const uint32_t crc = span_crc(piece_crc, f, l, npieces, bs, in_bytes, &nbytes);
+        const uint32_t crc = span_crc(piece_crc, f, l, npieces, bs, shift, in_bytes, &nbytes);
         switch (kind) {
         case B200BGZF_CONTAINER_MIGZ: {
             static const uint8_t hd[16] = { 0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x08, 0, 'M', 'Z', 0x04, 0 };
