@@ -205,6 +205,31 @@ def test_readers_list_the_units_of_reference_written_containers(kind, tmp_path):
     assert len(units) == {"dictzip": 13, "gzinga": 7, "gzip": 1, "razf": 22}[kind]
 
 
+GOLDEN = {"dictzip": "ref.dz", "gzinga": "ref.gzinga", "gzip": "ref.gz", "razf": "ref.raz", "migz": "ref.migz"}
+
+
+def _golden_input():
+    return H.synth("fastq", 90000) + H.lcg_noise(3000) + H.synth("sam", 60000)      # (tests/golden/make_container_fixtures.py)
+
+
+def _golden(kind):
+    with open(os.path.join(H.GOLDEN, "containers", GOLDEN[kind]), "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("kind", ["dictzip", "gzinga", "gzip", "razf"])
+def test_readers_on_the_committed_reference_written_files(kind):
+    units = _check_units(kind, _golden(kind), _golden_input())
+    assert len(units) == {"dictzip": 3, "gzinga": 2, "gzip": 1, "razf": 5}[kind]
+
+
+def test_committed_reference_files_are_what_the_reference_writes_today(tmp_path):
+    if not os.path.exists(H.REF_CIELBOX):
+        pytest.skip("oracle/_ref not built")
+    for kind in ("dictzip", "razf", "gzinga", "gzip"):
+        assert _ref_written(kind, _golden_input(), tmp_path) == _golden(kind), kind
+
+
 @pytest.mark.parametrize("kind", ["dictzip", "gzinga", "razf"])
 def test_readers_reject_damaged_indexes(kind):
     blob = H.emul_container(KINDS[kind], INPUTS["sam"], 6)
@@ -401,3 +426,9 @@ def test_gpu_applet_personalities(codec, kind, tmp_path):
     bad.write_bytes(blob[: len(blob) // 2])
     e = subprocess.run([exe, "-cd", str(bad)] if kind not in ("gzip", "migz") else [exe, "-d"], input=blob[: len(blob) // 2] if kind in ("gzip", "migz") else None, capture_output=True)
     assert e.returncode != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", sorted(GOLDEN))
+def test_gpu_reads_the_committed_reference_written_files(codec, kind):
+    assert codec.container_inflate(KINDS[kind], _golden(kind)) == _golden_input()
