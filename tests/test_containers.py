@@ -227,7 +227,10 @@ def test_committed_reference_files_are_what_the_reference_writes_today(tmp_path)
     if not os.path.exists(H.REF_CIELBOX):
         pytest.skip("oracle/_ref not built")
     for kind in ("dictzip", "razf", "gzinga", "gzip"):
-        assert _ref_written(kind, _golden_input(), tmp_path) == _golden(kind), kind
+        now, then = _ref_written(kind, _golden_input(), tmp_path), _golden(kind)
+        if kind == "gzip":                          # (its header carries the time of the run)
+            now, then = now[:4] + now[8:], then[:4] + then[8:]
+        assert now == then, kind
 
 
 @pytest.mark.parametrize("kind", ["dictzip", "gzinga", "razf"])
