@@ -46,5 +46,31 @@ for i in range(cases):
     if H.gunzip(got) != data or c.inflate(got) != data:
         bad += 1
         print(f"case {i}: level {level} block {bs} len {len(data)}: round trip failed")
+    if i % 3 == 0 and data:
+        # piece mode with a random member layout: every slot as the emulator makes it, every member one DEFLATE stream
+        import zlib
+        k, hg, tg, nf = rnd.choice([1, 2, 3, 7, 0xFFFFFFFF]), rnd.randrange(0, 65), rnd.randrange(0, 65), rnd.randrange(4) == 0
+        pbs = min(bs, 65536 - 5 - hg - tg)
+        spec = b200bgzf.PieceSpec(k, hg, tg, 1 if nf else 0)
+        stream, off, crc = c.compress_pieces(data, spec, level, pbs)
+        blocks = [data[j : j + pbs] for j in range(0, len(data), pbs)]
+        want = bytearray()
+        for j, b in enumerate(blocks):
+            first, last = j % k == 0, (j + 1) % k == 0 or j + 1 == len(blocks)
+            m, cr = H.emul_piece(b, level, hg if first else 0, tg if last else 0, last and not nf)
+            if off[j] != len(want) or crc[j] != cr:
+                bad += 1
+                print(f"case {i}: piece {j}: offset / CRC differs")
+                break
+            want += m
+        if bytes(want) != stream:
+            bad += 1
+            print(f"case {i}: level {level} block {pbs} spec ({k},{hg},{tg},{nf}): piece stream differs from the emulator's")
+        # (one member when k covers everything: the pieces between the gaps are one DEFLATE stream)
+        if k == 0xFFFFFFFF:
+            o = zlib.decompressobj(-15)
+            if o.decompress(stream[hg : len(stream) - tg]) != data or o.eof == nf:
+                bad += 1
+                print(f"case {i}: the member's DEFLATE stream does not decode")
 print(f"{cases} cases, {total >> 20} MiB: {bad} mismatches")
 sys.exit(1 if bad else 0)
