@@ -29,6 +29,7 @@ EXPORTS = [
     "b200bgzf_pieces_gap_bytes", "b200bgzf_compress_pieces_host", "b200bgzf_crc32_combine", "b200bgzf_container_plan",
     "b200bgzf_container_head", "b200bgzf_container_bound", "b200bgzf_container_frame", "b200bgzf_container_compress_host",
     "b200bgzf_inflate_units_host", "b200bgzf_container_units", "b200bgzf_units_free", "b200bgzf_container_inflate_host",
+    "b200bgzf_multi_container_bound", "b200bgzf_multi_container_compress_host",
 ]
 CONTAINER_GZIP, CONTAINER_MIGZ, CONTAINER_GZINGA, CONTAINER_DICTZIP, CONTAINER_RAZF = 1, 2, 3, 4, 5
 
@@ -38,7 +39,8 @@ class Unit(ctypes.Structure):
 
 
 class PieceSpec(ctypes.Structure):
-    _fields_ = [("member_blocks", ctypes.c_uint32), ("head_gap", ctypes.c_uint32), ("tail_gap", ctypes.c_uint32), ("no_final", ctypes.c_uint32)]
+    _fields_ = [("member_blocks", ctypes.c_uint32), ("head_gap", ctypes.c_uint32), ("tail_gap", ctypes.c_uint32), ("no_final", ctypes.c_uint32),
+                ("piece_base", ctypes.c_uint64), ("piece_total", ctypes.c_uint64)]
 
 
 class B200BgzfError(RuntimeError):
@@ -110,6 +112,9 @@ def load(path=LIB_PATH):
     lib.b200bgzf_units_free.argtypes = [punit]
     lib.b200bgzf_units_free.restype = None
     lib.b200bgzf_container_inflate_host.argtypes = [vp, i32, vp, sz, vp, sz, psz]
+    lib.b200bgzf_multi_container_bound.argtypes = [vp, i32, u32, sz]
+    lib.b200bgzf_multi_container_bound.restype = sz
+    lib.b200bgzf_multi_container_compress_host.argtypes = [vp, i32, u32, vp, sz, i32, vp, sz, psz]
     return lib
 
 
@@ -336,6 +341,14 @@ class MultiCodec:
         out = bytearray(self.bound(len(data), block_size))
         n = self.compress_into(_addr(data) if len(data) else None, len(data), _addr(out), len(out), level, block_size, eof, flags)
         return bytes(out[:n])
+
+    def container(self, kind, data, level=6, param=0):
+        """b200bgzf_multi_container_compress_host"""
+        out = bytearray(self.lib.b200bgzf_multi_container_bound(self.h, kind, param, len(data)))
+        n = ctypes.c_size_t()
+        self._check(self.lib.b200bgzf_multi_container_compress_host(self.h, kind, param, _addr(data) if len(data) else None, len(data), level,
+                                                                    _addr(out), len(out), ctypes.byref(n)))
+        return bytes(out[: n.value])
 
     def inflate_into(self, src_addr, nbytes, dst_addr, dst_cap, flags=0):
         n = ctypes.c_size_t()

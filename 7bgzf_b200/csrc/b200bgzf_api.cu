@@ -528,8 +528,8 @@ int compress_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint3
         PieceLaunch pl;
         if (ps) {
             pl.spec = *ps;
-            pl.base = done;
-            pl.total = nb_total;
+            pl.base = ps->piece_base + done;
+            pl.total = ps->piece_total ? ps->piece_total : nb_total;
             pl.d_crc = l.d_inlen;                               /* (unused by fixed-size batches) */
         }
         if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true,
@@ -574,9 +574,12 @@ extern "C" int b200bgzf_compress_host_index(b200bgzf_ctx *ctx, const void *in, s
 extern "C" size_t b200bgzf_pieces_gap_bytes(size_t in_bytes, uint32_t block_size, const b200bgzf_piece_spec *ps)
 {
     if (!ps || !block_size || !ps->member_blocks) return 0;
-    const uint64_t nb = (in_bytes + block_size - 1) / block_size;
-    const uint64_t members = (nb + ps->member_blocks - 1) / ps->member_blocks;
-    return (size_t)(members * ((uint64_t)ps->head_gap + ps->tail_gap));
+    const uint64_t nb = (in_bytes + block_size - 1) / block_size, k = ps->member_blocks;
+    /* members that begin / end inside the pieces [base, base + nb) of the stream */
+    const uint64_t b0 = ps->piece_base, b1 = b0 + nb, total = ps->piece_total ? ps->piece_total : b1;
+    const uint64_t firsts = (b1 + k - 1) / k - (b0 + k - 1) / k;
+    const uint64_t lasts = b1 / k - b0 / k + (nb && b1 == total && total % k ? 1u : 0u);
+    return (size_t)(firsts * ps->head_gap + lasts * ps->tail_gap);
 }
 
 extern "C" int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level,
@@ -584,6 +587,7 @@ extern "C" int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, 
                                              uint64_t *piece_off, uint32_t *piece_crc, size_t piece_cap)
 {
     if (!ps || ps->member_blocks == 0 || ps->head_gap > B200BGZF_MAX_GAP || ps->tail_gap > B200BGZF_MAX_GAP) return B200BGZF_E_ARG;
+    if (ps->piece_total && ps->piece_base + (in_bytes + block_size - 1) / block_size > ps->piece_total) return B200BGZF_E_ARG;
     if (piece_crc && piece_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
     return compress_host_impl(ctx, in, in_bytes, block_size, level, out, out_cap, out_bytes, 0, piece_off, piece_cap, ps, piece_crc);
 }

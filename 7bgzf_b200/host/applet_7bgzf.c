@@ -426,7 +426,7 @@ static int run_pipeline(int ndevices, int decompress, int level, uint32_t block,
     return ret;
 }
 
-int container_applet(const char *name, int kind, int decompress, int level, unsigned param, int nfiles, char **files);   /* applet_containers.c */
+int container_applet(const char *name, int kind, int decompress, int level, unsigned param, int ndevices, int nfiles, char **files);   /* applet_containers.c */
 
 static const struct { const char *name; int kind; } k_personas[] = {
     { "7bgzf", 0 }, { "7migz", B200BGZF_CONTAINER_MIGZ }, { "7gzip", B200BGZF_CONTAINER_GZIP }, { "7gzinga", B200BGZF_CONTAINER_GZINGA },
@@ -495,7 +495,7 @@ int main(int argc, char **argv)
         if (!decompress) fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
         if (migz && !decompress && (bsize < 1 || bsize > 4194303)) { fprintf(stderr, "7migz: -b %d: bad member size\n", bsize); return 1; }
         const unsigned param = migz ? (unsigned)bsize : kind == B200BGZF_CONTAINER_DICTZIP && extreme ? B200BGZF_BLOCK_SIZE : 0u;
-        const int ret = container_applet(persona, kind, decompress, level, param, argc - optind, argv + optind);
+        const int ret = container_applet(persona, kind, decompress, level, param, ndevices, argc - optind, argv + optind);
         gettimeofday(&t1, NULL);
         fprintf(stderr, "ellapsed time: %.6f sec\n", (t1.tv_sec + t1.tv_usec * 0.000001) - (t0.tv_sec + t0.tv_usec * 0.000001));
         return ret;

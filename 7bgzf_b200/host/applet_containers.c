@@ -38,7 +38,7 @@ static unsigned char *slurp(FILE *f, size_t *n)
 }
 
 /* kind: B200BGZF_CONTAINER_*; files: the operands left after the options */
-int container_applet(const char *name, int kind, int decompress, int level, unsigned param, int nfiles, char **files)
+int container_applet(const char *name, int kind, int decompress, int level, unsigned param, int ndevices, int nfiles, char **files)
 {
     FILE *in = stdin, *out = stdout;
     if (nfiles > 0 && !(in = fopen(files[0], "rb"))) { fprintf(stderr, "failed to open %s\n", files[0]); return 2; }
@@ -49,8 +49,15 @@ int container_applet(const char *name, int kind, int decompress, int level, unsi
     if (!src) { fprintf(stderr, "out of memory\n"); return 1; }
 
     b200bgzf_ctx *ctx = NULL;
+    b200bgzf_multi *multi = NULL;                       /* --devices=N: the pieces are dealt out over N GPUs (compress) */
     const char *dev = getenv("B200BGZF_DEVICE");
-    int r = b200bgzf_create(&ctx, dev && *dev ? atoi(dev) : -1);
+    int r;
+    if (ndevices > 1) {
+        r = b200bgzf_multi_create(&multi, NULL, ndevices);
+        ctx = b200bgzf_multi_ctx(multi, 0);
+    } else {
+        r = b200bgzf_create(&ctx, dev && *dev ? atoi(dev) : -1);
+    }
     if (r != 0) { fprintf(stderr, "b200bgzf: cannot initialise the GPU codec: %s\n", b200bgzf_strerror(r)); free(src); return 1; }
 
     unsigned char *dst = NULL;
@@ -77,11 +84,12 @@ int container_applet(const char *name, int kind, int decompress, int level, unsi
             if (r != 0) { fprintf(stderr, "inflate %d\n", r); ret = 1; }
         }
     } else {
-        cap = b200bgzf_container_bound(kind, param, n);
+        cap = multi ? b200bgzf_multi_container_bound(multi, kind, param, n) : b200bgzf_container_bound(kind, param, n);
         if (!cap || !(dst = (unsigned char *)malloc(cap))) { fprintf(stderr, cap ? "out of memory\n" : "%s: bad block size\n", name); ret = 1; }
         else {
             memset(dst, 0, cap);                 /* fault the pages in before the device copies into them */
-            r = b200bgzf_container_compress_host(ctx, kind, param, src, n, level, dst, cap, &produced);
+            r = multi ? b200bgzf_multi_container_compress_host(multi, kind, param, src, n, level, dst, cap, &produced)
+                      : b200bgzf_container_compress_host(ctx, kind, param, src, n, level, dst, cap, &produced);
             if (r == B200BGZF_E_NOFIT) { fprintf(stderr, "libdeflate_deflate %d\n", 1); ret = 1; }
             else if (r != 0) { fprintf(stderr, "b200bgzf: %s (%s)\n", b200bgzf_strerror(r), b200bgzf_last_error(ctx)); ret = 1; }
             uint32_t bs = 1;
@@ -96,6 +104,7 @@ int container_applet(const char *name, int kind, int decompress, int level, unsi
     if (in != stdin) fclose(in);
     free(dst);
     free(src);
-    b200bgzf_destroy(ctx);
+    if (multi) b200bgzf_multi_destroy(multi);
+    else b200bgzf_destroy(ctx);
     return ret;
 }

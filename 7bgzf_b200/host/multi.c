@@ -193,3 +193,117 @@ int b200bgzf_multi_inflate_host(b200bgzf_multi *m, const void *in, size_t in_byt
     }
     return used ? run_jobs(jobs, used) : B200BGZF_OK;
 }
+
+/* ---- the other containers over several GPUs (SURVEY 8e for the rows of 8f): pieces are independent, GPU g takes a contiguous
+ * range of them — whole members where the container has several — and the framing is written once over the joined stream ---- */
+struct piece_job {
+    pthread_t th;
+    b200bgzf_ctx *ctx;
+    const unsigned char *in;
+    unsigned char *out;
+    size_t in_bytes, cap, bytes, np;
+    uint32_t bs;
+    int level, rc;
+    b200bgzf_piece_spec sp;
+    uint64_t *off;
+    uint32_t *crc;
+};
+
+static void *piece_main(void *arg)
+{
+    struct piece_job *j = (struct piece_job *)arg;
+    j->bytes = 0;
+    j->rc = b200bgzf_compress_pieces_host(j->ctx, j->in, j->in_bytes, j->bs, j->level, &j->sp, j->out, j->cap, &j->bytes, j->off, j->crc, j->np);
+    return NULL;
+}
+
+size_t b200bgzf_multi_container_bound(const b200bgzf_multi *m, int kind, uint32_t param, size_t in_bytes)
+{
+    const size_t b = b200bgzf_container_bound(kind, param, in_bytes);
+    return b && m ? b + (size_t)m->n * (B200BGZF_EOF_BYTES + 2u * B200BGZF_MAX_GAP) : b;
+}
+
+int b200bgzf_multi_container_compress_host(b200bgzf_multi *m, int kind, uint32_t param, const void *in, size_t in_bytes, int level,
+                                           void *out, size_t out_cap, size_t *out_bytes)
+{
+    uint32_t bs;
+    b200bgzf_piece_spec sp;
+    if (!m || !out || !out_bytes || (!in && in_bytes)) return B200BGZF_E_ARG;
+    if (b200bgzf_container_plan(kind, param, &bs, &sp) != 0) return B200BGZF_E_ARG;
+    if (kind == B200BGZF_CONTAINER_RAZF && (in_bytes >> 32)) return B200BGZF_E_ARG;
+    if (out_cap < b200bgzf_multi_container_bound(m, kind, param, in_bytes)) return B200BGZF_E_NOSPACE;
+    *out_bytes = 0;
+    const size_t np_total = (in_bytes + bs - 1) / bs;
+    const size_t per_call = kind == B200BGZF_CONTAINER_DICTZIP ? 32762u : (np_total ? np_total : 1);   /* dictzip: one member per round */
+    const size_t arr = per_call < np_total ? per_call : np_total;
+    uint64_t *off = (uint64_t *)malloc(sizeof(uint64_t) * arr + 8);
+    uint32_t *crc = (uint32_t *)malloc(sizeof(uint32_t) * arr + 8);
+    if (!off || !crc) { free(off); free(crc); return B200BGZF_E_ARG; }
+    int rc = B200BGZF_OK;
+    size_t pos = 0, done = 0;
+    do {
+        const size_t np = np_total - done < per_call ? np_total - done : per_call;
+        const size_t byte0 = done * bs, bytes = (done + np) * (size_t)bs < in_bytes ? np * (size_t)bs : in_bytes - byte0;
+        const size_t head = b200bgzf_container_head(kind, np);
+        size_t stream = 0;
+        if (np) {
+            /* what is dealt out: single pieces of a one-member container, whole members otherwise */
+            const uint64_t k = sp.member_blocks == 0xffffffffu ? 1u : sp.member_blocks;
+            const uint64_t groups = (np + k - 1) / k;
+            int n = m->n;
+            if ((uint64_t)n > groups) n = (int)groups;
+            struct piece_job jobs[MULTI_MAX];
+            memset(jobs, 0, sizeof jobs);
+            size_t place = pos + head;
+            for (int g = 0; g < n; g++) {
+                uint64_t g0, g1;
+                b200bgzf_shard_blocks(groups, g, n, &g0, &g1);
+                const size_t p0 = (size_t)(g0 * k), p1 = (size_t)(g1 * k) < np ? (size_t)(g1 * k) : np;
+                struct piece_job *j = &jobs[g];
+                j->ctx = m->ctx[g];
+                j->bs = bs;
+                j->level = level;
+                j->sp = sp;
+                j->sp.piece_base = p0;
+                j->sp.piece_total = np;
+                j->in = (const unsigned char *)in + byte0 + p0 * (size_t)bs;
+                j->in_bytes = (p1 * (size_t)bs < bytes ? p1 * (size_t)bs : bytes) - p0 * (size_t)bs;
+                j->np = p1 - p0;
+                j->off = off + p0;
+                j->crc = crc + p0;
+                j->out = (unsigned char *)out + place;       /* behind the worst case of the shards before it */
+                j->cap = b200bgzf_compress_bound(j->in_bytes, bs) + b200bgzf_pieces_gap_bytes(j->in_bytes, bs, &j->sp);
+                place += j->cap;
+            }
+            if (place > out_cap) { rc = B200BGZF_E_NOSPACE; break; }
+            for (int g = 1; g < n; g++)
+                if (pthread_create(&jobs[g].th, NULL, piece_main, &jobs[g]) != 0) {
+                    piece_main(&jobs[g]);
+                    jobs[g].th = 0;
+                }
+            piece_main(&jobs[0]);
+            for (int g = 0; g < n; g++) {
+                if (g && jobs[g].th) pthread_join(jobs[g].th, NULL);
+                if (jobs[g].rc < 0 && rc >= 0) rc = jobs[g].rc;
+                else if (jobs[g].rc > 0 && rc == 0) rc = jobs[g].rc;
+            }
+            if (rc != 0) break;
+            /* join the shard streams (shard 0 is in place); piece offsets become offsets in the joined stream */
+            for (int g = 0; g < n; g++) {
+                if (g) memmove((unsigned char *)out + pos + head + stream, jobs[g].out, jobs[g].bytes);
+                for (size_t i = 0; i < jobs[g].np; i++) jobs[g].off[i] += stream;
+                stream += jobs[g].bytes;
+            }
+        }
+        const size_t total = b200bgzf_container_frame(kind, param, (unsigned char *)out + pos, out_cap - pos, stream, off, crc, np, bytes);
+        if (!total && !(kind == B200BGZF_CONTAINER_MIGZ && np == 0)) { rc = B200BGZF_E_NOSPACE; break; }
+        pos += total;
+        done += np;
+    } while (done < np_total);
+    free(off);
+    free(crc);
+    if (rc == B200BGZF_E_NOFIT && kind == B200BGZF_CONTAINER_MIGZ && !(param & B200BGZF_PARAM_SAFE))
+        return b200bgzf_multi_container_compress_host(m, kind, param | B200BGZF_PARAM_SAFE, in, in_bytes, level, out, out_cap, out_bytes);
+    if (rc == 0) *out_bytes = pos;
+    return rc;
+}

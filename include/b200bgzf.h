@@ -167,6 +167,8 @@ typedef struct b200bgzf_piece_spec {
     uint32_t head_gap;        /* <= B200BGZF_MAX_GAP */
     uint32_t tail_gap;        /* <= B200BGZF_MAX_GAP */
     uint32_t no_final;        /* 1: no piece is final (dictzip closes its member with an empty block of its own) */
+    uint64_t piece_base;      /* the call's input is a slice of a longer stream of pieces: index of its first piece, and the */
+    uint64_t piece_total;     /* number of pieces of the whole stream (0: the input is the whole stream) — for sharding over GPUs */
 } b200bgzf_piece_spec;
 size_t b200bgzf_pieces_gap_bytes(size_t in_bytes, uint32_t block_size, const b200bgzf_piece_spec *spec);
 int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level,
@@ -206,6 +208,12 @@ size_t b200bgzf_container_frame(int kind, uint32_t param, void *member, size_t c
                                 const uint32_t *piece_crc, size_t npieces, size_t in_bytes);
 int b200bgzf_container_compress_host(b200bgzf_ctx *ctx, int kind, uint32_t param, const void *in, size_t in_bytes, int level,
                                      void *out, size_t out_cap, size_t *out_bytes);
+/* The same over several GPUs: pieces are independent, so GPU g takes a contiguous range of them (whole members
+ * where a container has several), the shard streams are joined at host-known offsets and framed once; byte-identical to
+ * the single-GPU container for every number of GPUs.  The output buffer must hold b200bgzf_multi_container_bound() bytes. */
+size_t b200bgzf_multi_container_bound(const b200bgzf_multi *m, int kind, uint32_t param, size_t in_bytes);
+int b200bgzf_multi_container_compress_host(b200bgzf_multi *m, int kind, uint32_t param, const void *in, size_t in_bytes, int level,
+                                           void *out, size_t out_cap, size_t *out_bytes);
 
 /* The readers: the unit list of a dictzip / RAZF / GZinga file from its own index (a plain gzip member without an index is
  * one unit: one warp decodes it), to be released with b200bgzf_units_free; out_bytes = the decoded size.  No GPU involved.

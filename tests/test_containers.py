@@ -421,6 +421,9 @@ def test_gpu_applet_personalities(codec, kind, tmp_path):
         else:
             d = subprocess.run([exe, "-cd", str(theirs)], capture_output=True)
         assert d.returncode == 0 and d.stdout == data, d.stderr
+    if kind == "razf":                                  # the pieces over three contexts: the same file
+        x = subprocess.run([exe, "-cl6", "--devices=3", str(src)], env=dict(os.environ, CUDA_VISIBLE_DEVICES="0,0,0"), capture_output=True)
+        assert x.returncode != 0 or x.stdout == blob
     if kind == "dictzip":
         x = subprocess.run([exe, "-cl6", "-X", str(src), str(enc)], capture_output=True)
         assert x.returncode == 0 and enc.read_bytes() == codec.container(KINDS[kind], data, 6, 65280)
@@ -435,3 +438,22 @@ def test_gpu_applet_personalities(codec, kind, tmp_path):
 @pytest.mark.parametrize("kind", sorted(GOLDEN))
 def test_gpu_reads_the_committed_reference_written_files(codec, kind):
     assert codec.container_inflate(KINDS[kind], _golden(kind)) == _golden_input()
+
+
+@pytest.mark.gpu
+def test_gpu_containers_over_several_contexts_are_the_single_gpu_ones(codec):
+    """SURVEY 8e for the containers: piece ranges (whole members where there are several) over the contexts, joined and framed
+    once: the same bytes for every number of shards (three contexts on one GPU here, as in the BGZF sharding test)"""
+    data = H.synth("fastq", 3 * 1024 * 1024 + 12345) + H.synth("sam", 1 << 20)
+    for ctxs in ([0, 0, 0], [0, 0, 0, 0, 0]):
+        m = B.MultiCodec(ctxs)
+        try:
+            for kind in sorted(KINDS):
+                assert m.container(KINDS[kind], data, 6) == codec.container(KINDS[kind], data, 6), (kind, len(ctxs))
+            assert m.container(B.CONTAINER_DICTZIP, data[: 80000 * 64], 6, 64) == codec.container(B.CONTAINER_DICTZIP, data[: 80000 * 64], 6, 64)
+            assert m.container(B.CONTAINER_GZIP, b"x", 6) == codec.container(B.CONTAINER_GZIP, b"x", 6)
+            assert m.container(B.CONTAINER_GZIP, b"", 6) == codec.container(B.CONTAINER_GZIP, b"", 6)
+            noisy = data[: 1 << 20] + H.lcg_noise(1 << 19)
+            assert m.container(B.CONTAINER_MIGZ, noisy, 6) == codec.container(B.CONTAINER_MIGZ, noisy, 6)     # (the redo in small pieces)
+        finally:
+            m.close()
