@@ -40,7 +40,7 @@ class Unit(ctypes.Structure):
 
 class PieceSpec(ctypes.Structure):
     _fields_ = [("member_blocks", ctypes.c_uint32), ("head_gap", ctypes.c_uint32), ("tail_gap", ctypes.c_uint32), ("no_final", ctypes.c_uint32),
-                ("piece_base", ctypes.c_uint64), ("piece_total", ctypes.c_uint64)]
+                ("piece_base", ctypes.c_uint64), ("piece_total", ctypes.c_uint64), ("history", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class B200BgzfError(RuntimeError):

@@ -263,6 +263,7 @@ struct PieceLaunch {
     b200bgzf_piece_spec spec;
     uint64_t base, total;
     uint32_t *d_crc;
+    uint32_t lead;              /* bytes of the stream in the device buffer before the batch's first block (match history) */
 };
 
 int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint64_t in_bytes, uint32_t block_size,
@@ -306,6 +307,8 @@ int launch_compress_batch(b200bgzf_ctx *ctx, Lane &l, const uint8_t *d_in, uint6
             a.piece_base = pl->base;
             a.piece_total = pl->total;
             a.crc_out = pl->d_crc;
+            a.history = pl->spec.history;
+            a.lead = pl->lead;
         }
         if (fused) {
             a.gather_out = d_out;
@@ -495,7 +498,7 @@ int compress_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint3
     static const uint32_t host_batch = [] { const char *e = getenv("B200BGZF_HOST_BATCH"); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : kHostBatchBlocks; }();
     static const uint32_t first_batch = [] { const char *e = getenv("B200BGZF_FIRST_BATCH"); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : 0u; }();
     const uint32_t batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nb_total, 1), host_batch);
-    const size_t batch_in = (size_t)batch * block_size;
+    const size_t batch_in = (size_t)batch * block_size + (ps ? ps->history : 0u);
     const size_t batch_out = b200bgzf_compress_bound(batch_in, block_size) + (ps ? (size_t)batch * (ps->head_gap + ps->tail_gap) : 0);
     static const int nlanes = [] { const char *e = getenv("B200BGZF_LANES"); return e && atoi(e) > 0 ? std::min(atoi(e), kLanes) : kLanes; }();
     uint32_t cur = first_batch ? std::min(first_batch, batch) : batch;
@@ -523,7 +526,13 @@ int compress_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint3
         cur = std::min<uint32_t>(batch, cur * 2);
         const uint64_t off = done * block_size;
         const size_t bytes = (size_t)std::min<uint64_t>((uint64_t)nb * block_size, in_bytes - off);
-        CK(cudaMemcpyAsync(l.d_in, (const uint8_t *)in + off, bytes, cudaMemcpyHostToDevice, l.stream));
+        /* primed pieces: the batch's first blocks find their history in front of them in the device buffer */
+        uint32_t lead = 0;
+        if (ps && ps->history) {
+            const uint64_t before = (ps->piece_base + done) * (uint64_t)block_size;      /* bytes of the stream before this batch */
+            lead = (uint32_t)std::min<uint64_t>(ps->history, before);
+        }
+        CK(cudaMemcpyAsync(l.d_in, (const uint8_t *)in + off - lead, bytes + lead, cudaMemcpyHostToDevice, l.stream));
         CK(cudaMemsetAsync(l.d_total, 0, 4 * sizeof(uint64_t), l.stream));
         PieceLaunch pl;
         if (ps) {
@@ -531,8 +540,9 @@ int compress_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint3
             pl.base = ps->piece_base + done;
             pl.total = ps->piece_total ? ps->piece_total : nb_total;
             pl.d_crc = l.d_inlen;                               /* (unused by fixed-size batches) */
+            pl.lead = lead;
         }
-        if ((r = launch_compress_batch(ctx, l, l.d_in, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true,
+        if ((r = launch_compress_batch(ctx, l, l.d_in + lead, bytes, block_size, nullptr, nullptr, nb, level, l.d_out, 0, l.stream, true,
                                        (flags & B200BGZF_FRAME_MIGZ) ? 20u : 18u, ps ? &pl : nullptr))) return r;
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
         if (member_off || piece_crc) {
@@ -588,6 +598,8 @@ extern "C" int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, 
 {
     if (!ps || ps->member_blocks == 0 || ps->head_gap > B200BGZF_MAX_GAP || ps->tail_gap > B200BGZF_MAX_GAP) return B200BGZF_E_ARG;
     if (ps->piece_total && ps->piece_base + (in_bytes + block_size - 1) / block_size > ps->piece_total) return B200BGZF_E_ARG;
+    if (ps->history % BG_HISTORY_STEP || ps->history > BG_MAX_HISTORY || (ps->history && (uint64_t)block_size + ps->history > BG_MAX_BLOCK))
+        return B200BGZF_E_ARG;
     if (piece_crc && piece_cap < (in_bytes + block_size - 1) / block_size) return B200BGZF_E_NOSPACE;
     return compress_host_impl(ctx, in, in_bytes, block_size, level, out, out_cap, out_bytes, 0, piece_off, piece_cap, ps, piece_crc);
 }

@@ -58,6 +58,8 @@
 #define BG_SUPER_POS (BG_SUPER * BG_CHUNK)
 #define BG_MAX_TOKEN 258u
 #define BG_SLOT_BYTES 65536u  /* one output slot = the largest legal BGZF member */
+#define BG_HISTORY_STEP 272u  /* history comes in multiples of 4 chunks = 17 x 16 bytes: chunk-aligned for the token passes, 16-byte aligned for the bulk load */
+#define BG_MAX_HISTORY 32640u /* 480 chunks: the most history a primed piece carries (the DEFLATE window is 32768) */
 #define BG_CRC_WORDS 17u      /* CRC slice per thread, in 32-bit words (odd => conflict-free smem striding) */
 #define BG_MIN_LOOKUP 3       /* shortest match the chain search can return (3 only where the hash window is 3 bytes: see bg_phase_settle) */
 
@@ -152,11 +154,15 @@ struct BgCtx {
      * gaps of a member's first and last piece).  A piece that is not `final` carries BFINAL = 0 and ends with an empty stored
      * block that pads to the byte ("full flush": what the reference makes of every dictzip / RAZF chunk by clearing the
      * final bit and appending 00 00 ff ff, applet/7dictzip.c:92-126, 7razf_testdecode.c:1023), so pieces concatenate bytewise. */
-    uint32_t frame;
+    uint32_t frame;             /* ... | history chunks << 18 (bg_f_hist) */
     BgParams prm;
 };
 
-BG_HD uint32_t bg_frame(uint32_t hdr, uint32_t trl, uint32_t final, uint32_t piece) { return hdr | (trl << 8) | (final << 16) | (piece << 17); }
+BG_HD uint32_t bg_frame(uint32_t hdr, uint32_t trl, uint32_t final, uint32_t piece, uint32_t hist = 0) { return hdr | (trl << 8) | (final << 16) | (piece << 17) | ((hist / BG_CHUNK) << 18); }
+/* history: the first bg_f_hist(c) bytes of the block buffer (a multiple of BG_HISTORY_STEP, at most BG_MAX_HISTORY) are the input
+ * that precedes this piece: matches may reach into them (dictionary priming, as pigz does between its chunks), nothing is
+ * emitted for them, and CRC-32 / sizes cover the payload behind them only */
+BG_HD uint32_t bg_f_hist(const BgCtx &c) { return (c.frame >> 18) * BG_CHUNK; }
 BG_HD uint32_t bg_f_hdr(const BgCtx &c) { return c.frame & 0xffu; }
 BG_HD uint32_t bg_f_trl(const BgCtx &c) { return (c.frame >> 8) & 0xffu; }
 BG_HD uint32_t bg_f_final(const BgCtx &c) { return (c.frame >> 16) & 1u; }
@@ -318,8 +324,10 @@ BG_HD void bg_phase_scan(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t n = c.n;
     for (uint32_t p = t; p < n; p += T)
         c.litflag[bg_ld8(c.dataw, p)] = 1;
-    /* CRC over the first m = n/4 words, slices right-aligned so the combine exponents are constants */
-    const uint32_t m = n >> 2;
+    /* CRC over the first m = n/4 words (of the payload: hw history words come first), slices right-aligned so the combine
+     * exponents are constants */
+    const uint32_t hw = bg_f_hist(c) >> 2;
+    const uint32_t m = (n >> 2) - hw;
     const uint32_t k = T - 1 - t;                 /* slices after mine */
     const uint32_t endw = m >= BG_CRC_WORDS * k ? m - BG_CRC_WORDS * k : 0;
     const uint32_t begw = endw >= BG_CRC_WORDS ? endw - BG_CRC_WORDS : 0;
@@ -327,7 +335,7 @@ BG_HD void bg_phase_scan(const BgCtx &c, uint32_t t, uint32_t T)
     if (endw > begw) {
         r = begw == 0 ? 0xFFFFFFFFu : 0u;
         for (uint32_t w = begw; w < endw; w++) {
-            uint32_t v = c.dataw[w];
+            uint32_t v = c.dataw[hw + w];
             r = bg_crc_byte(c.crctab, r, v & 0xff);
             r = bg_crc_byte(c.crctab, r, (v >> 8) & 0xff);
             r = bg_crc_byte(c.crctab, r, (v >> 16) & 0xff);
@@ -376,7 +384,7 @@ BG_HD void bg_phase_settle(const BgCtx &c, uint32_t t, uint32_t T)
     if (t != 0) return;
     const uint32_t n = c.n;
     uint32_t r = c.scal[BG_S_CRC];
-    if ((n >> 2) == 0) r = 0xFFFFFFFFu;
+    if (((n - bg_f_hist(c)) >> 2) == 0) r = 0xFFFFFFFFu;
     for (uint32_t p = n & ~3u; p < n; p++)
         r = bg_crc_byte(c.crctab, r, bg_ld8(c.dataw, p));
     c.scal[BG_S_CRC] = ~r;
@@ -565,11 +573,17 @@ BG_HD void bg_phase_search_clear(const BgCtx &c, uint32_t t, uint32_t T)
 BG_HD void bg_phase_search1(const BgCtx &c, uint32_t t, uint32_t T)
 {
     uint32_t *elig = (uint32_t *)(c.regb + BG_B_TODO), *mark = (uint32_t *)(c.regb + BG_B_MARK);
-    if (t == 0) bg_or32(&mark[0], 1u);
+    const uint32_t hist = bg_f_hist(c);
+    if (t == 0) bg_or32(&mark[hist >> 5], 1u << (hist & 31u));      /* the parse starts behind the history */
     const BgSearchPrm sp = bg_search_prm(c);
     for (uint32_t p = t; p < c.n; p += T) {
         bool deep;
         uint32_t target;
+        if (p < hist) {                                             /* history: never a token, never searched */
+            c.R[p] = 0;
+            if (c.prm.opt_passes > 0) bg_cand_init(c, p, 0);
+            continue;
+        }
         c.R[p] = bg_nearest(c, sp, p, &deep, &target);
         if (c.prm.opt_passes > 0) bg_cand_init(c, p, c.R[p]);
         if (deep) bg_or32(&elig[p >> 5], 1u << (p & 31u));
@@ -792,6 +806,14 @@ BG_HD void bg_phase_accept(const BgCtx &c, uint32_t t, uint32_t T)
     }
 }
 
+/* history positions step one byte at a time, whatever the parse decided there: the walk then enters the payload exactly
+ * at its first byte (run after bg_phase_accept / the min-cost passes; hist is a multiple of 4) */
+BG_HD void bg_phase_history_steps(const BgCtx &c, uint32_t t, uint32_t T)
+{
+    const uint32_t hw = bg_f_hist(c) >> 2;
+    for (uint32_t i = t; i < hw; i += T) ((uint32_t *)c.stepcode)[i] = 0;
+}
+
 BG_HD uint32_t bg_step(const BgCtx &c, uint32_t p)
 {
     uint32_t sc = c.stepcode[p];
@@ -959,7 +981,7 @@ BG_HD void bg_phase_tally(const BgCtx &c, uint32_t t, uint32_t T)
     const uint16_t *entry = (const uint16_t *)(c.regb + BG_B_ENTRY);
     for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
         const uint32_t ch = c.perm ? c.perm[i] : i;
-        if (ch * BG_CHUNK >= n) continue;
+        if (ch * BG_CHUNK >= n || ch * BG_CHUNK < bg_f_hist(c)) continue;
         uint32_t p = entry[ch];
         if (p == BG_NOPOS) continue;
         p += ch * BG_CHUNK;
@@ -1461,7 +1483,7 @@ BG_HD uint32_t bg_coded_bytes(const BgCtx &c, uint32_t bits) { return bg_f_final
 /* block type from the exact costs: every thread evaluates the same few scalars */
 BG_HD uint32_t bg_block_type(const BgCtx &c, uint32_t *hdrbits, uint32_t *tokbits, uint32_t *payload)
 {
-    const uint32_t n = c.n;
+    const uint32_t n = c.n - bg_f_hist(c);                     /* payload bytes */
     const uint32_t hdr = c.scal[BG_S_DYNHDR], extra = c.scal[BG_S_EXTRA];
     const uint32_t dyn_bits = hdr + c.scal[BG_S_DYNSYMS] + extra;
     const uint32_t sta_bits = 3 + c.scal[BG_S_STASYMS] + extra;
@@ -1624,7 +1646,7 @@ BG_HD void bg_phase_sizes(const BgCtx &c, uint32_t t, uint32_t T)
     for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
         const uint32_t ch = c.perm ? c.perm[i] : i;
         uint32_t bits = 0;
-        uint32_t p = ch * BG_CHUNK < n ? entry[ch] : BG_NOPOS;
+        uint32_t p = ch * BG_CHUNK < n && ch * BG_CHUNK >= bg_f_hist(c) ? entry[ch] : BG_NOPOS;
         if (coded && p != BG_NOPOS) {
             p += ch * BG_CHUNK;
             uint32_t end = ch * BG_CHUNK + BG_CHUNK;
@@ -1724,7 +1746,7 @@ BG_HD void bg_emit_frame(const BgCtx &c)
     bg_w_flush(w);
     bg_w_init(w, c.out, (bg_f_hdr(c) + payload) * 8);
     bg_w_put(w, c.scal[BG_S_CRC], 32);
-    bg_w_put(w, c.n, 32);
+    bg_w_put(w, c.n - bg_f_hist(c), 32);
     bg_w_flush(w);
 }
 
@@ -1733,12 +1755,12 @@ BG_HD void bg_emit_frame(const BgCtx &c)
 BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
 {
     if (c.scal[BG_S_STATUS]) return;
-    const uint32_t n = c.n;
     uint8_t *rb = c.regb;
     const uint32_t btype = c.scal[BG_S_BTYPE];
     const uint32_t base = bg_f_hdr(c) * 8;
     if (btype == 0) {
         /* stored: [01|00] LEN NLEN raw..., at most two stored blocks (n <= 65536) */
+        const uint32_t hist = bg_f_hist(c), n = c.n - hist;   /* the payload: n bytes behind the history */
         const uint32_t first = n > 65535u ? 65535u : n;
         if (t == 0) {
             bg_emit_frame(c);
@@ -1762,13 +1784,13 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
         const uint32_t w0 = (r0 + 3u) >> 2, hb = 4u * w0 - r0;  /* first full word; payload bytes before it */
         const uint32_t wend = (first + r0) >> 2;               /* first word that is not "full" */
         for (uint32_t wd = w0 + t; wd < wend; wd += T)
-            c.out[wd] = bg_ld32(c.dataw, 4 * wd - r0);
+            c.out[wd] = bg_ld32(c.dataw, hist + 4 * wd - r0);
         const uint32_t s1 = wend > w0 ? 4 * wend - r0 : hb;    /* first source byte past the full words */
         if (t < hb + 15u) {
             uint32_t src = t < hb ? t : s1 + (t - hb);
             if (src < n) {
                 uint32_t dst = r0 + src + (src >= 65535u ? 5 : 0);
-                bg_or32(&c.out[dst >> 2], bg_ld8(c.dataw, src) << (8 * (dst & 3)));
+                bg_or32(&c.out[dst >> 2], bg_ld8(c.dataw, hist + src) << (8 * (dst & 3)));
             }
         }
         return;
@@ -1781,6 +1803,7 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
     const uint32_t *littab = (const uint32_t *)(rb + BG_B_LITTAB), *lentab = (const uint32_t *)(rb + BG_B_LENTAB);
     const uint32_t *offtab = (const uint32_t *)(rb + BG_B_OFFTAB);
     const uint32_t hdrbits = c.scal[BG_S_HDRBITS];
+    const uint32_t n = c.n;
     if (t == 0) {
         bg_emit_frame(c);
         BgWriter w;
@@ -1820,7 +1843,7 @@ BG_HD void bg_phase_emit(const BgCtx &c, uint32_t t, uint32_t T)
     for (uint32_t i = t; i < BG_MAX_CHUNKS; i += T) {
         const uint32_t ch = c.perm ? c.perm[i] : i;
         BG_ASSERT(ch < BG_MAX_CHUNKS);
-        if (ch * BG_CHUNK >= n) continue;
+        if (ch * BG_CHUNK >= n || ch * BG_CHUNK < bg_f_hist(c)) continue;
         uint32_t p = entry[ch];
         if (p == BG_NOPOS) continue;
         p += ch * BG_CHUNK;

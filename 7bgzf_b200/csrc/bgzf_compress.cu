@@ -244,27 +244,33 @@ __device__ __forceinline__ void search_nearest_t(const BgCtx &c, uint32_t t, uin
     uint32_t *elig = (uint32_t *)(c.regb + BG_B_TODO), *mark = (uint32_t *)(c.regb + BG_B_MARK);
     const BgSearchPrm sp = bg_search_prm(c);
     if (sp.depth <= 1) {                                            /* depth 1 (level 1): the nearest candidate is the whole search */
+        const uint32_t hist1 = bg_f_hist(c);
         for (uint32_t p = t; p < n; p += BG_THREADS) {
             if (SPLIT && (p >> 5) % parts != own) continue;
             bool deep;
             uint32_t target;
-            c.R[p] = bg_nearest_t<H3>(c, sp, p, &deep, &target);
+            c.R[p] = p < hist1 ? 0u : bg_nearest_t<H3>(c, sp, p, &deep, &target);
         }
         return;
     }
     const bool opt = c.prm.opt_passes > 0;
-    if (t == 0 && own == 0) atomicOr(&mark[0], 1u);
+    const uint32_t hist = bg_f_hist(c);                             /* history: never a token, never searched (bg_phase_search1) */
+    if (t == 0 && own == 0) mark_bits<SPLIT>(mark, hist >> 5, 1u << (hist & 31u), own, parts);
     for (uint32_t p0 = t - lane; p0 < n; p0 += BG_THREADS) {       /* (warp-uniform trip count) */
         const uint32_t word = p0 >> 5;
         BG_ASSERT(word < 2048u);
         if (SPLIT && word % parts != own) continue;
         const uint32_t p = p0 + lane;
+        if (p0 + 32u <= hist) {                                     /* (uniform) */
+            c.R[p] = 0;
+            if (opt) ((uint4 *)c.cand)[p] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         bool deep = false;
         uint32_t target = p + 1, r = 0;
-        if (p < n) {
-            r = bg_nearest_t<H3>(c, sp, p, &deep, &target);
-            c.R[p] = r;
-        }
+        const bool live = p < n && p >= hist;
+        if (live) r = bg_nearest_t<H3>(c, sp, p, &deep, &target);
+        if (p < n) c.R[p] = r;
         if (opt) {
             /* near-optimal class: every eligible position is searched (no landing marks); the nearest match opens its offset range */
             if (p < n) {
@@ -275,7 +281,7 @@ __device__ __forceinline__ void search_nearest_t(const BgCtx &c, uint32_t t, uin
             if (lane == 0) elig[word] = em;
             continue;
         }
-        const bool lit = p < n && target == p + 1;
+        const bool lit = live && target == p + 1;
         const unsigned lm = __ballot_sync(0xffffffffu, lit), em = __ballot_sync(0xffffffffu, deep);
         const uint32_t before = __shfl_up_sync(0xffffffffu, target, 1);
         if (lane == 0) {
@@ -284,7 +290,7 @@ __device__ __forceinline__ void search_nearest_t(const BgCtx &c, uint32_t t, uin
             if (lm >> 31) mark_bits<SPLIT>(mark, word + 1, 1u, own, parts);
         }
         /* consecutive positions inside one match land on the same position: one of them marks it */
-        if (p < n && !lit && (lane == 0 || before != target)) mark_bits<SPLIT>(mark, target >> 5, 1u << (target & 31u), own, parts);
+        if (live && !lit && (lane == 0 || before != target)) mark_bits<SPLIT>(mark, target >> 5, 1u << (target & 31u), own, parts);
     }
 }
 
@@ -849,14 +855,24 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
             const uint64_t rem = a.in_bytes - off;
             n = rem < a.block_size ? (uint32_t)rem : a.block_size;
         }
-        c.n = n;
         c.out = (uint32_t *)(a.slots + (size_t)b * BG_SLOT_BYTES);
         if (a.piece_mode) {
             /* piece b of the call is piece gb of the stream: members are runs of member_blocks pieces (the last one may be short) */
             const uint64_t gb = a.piece_base + b;
             const bool first = gb % a.member_blocks == 0, last = (gb + 1) % a.member_blocks == 0 || gb + 1 == a.piece_total;
-            c.frame = bg_frame(first ? a.head_gap : 0u, last ? a.tail_gap : 0u, last && !a.no_final ? 1u : 0u, 1u);
+            /* dictionary priming: what precedes the piece in its member, as far as the window reaches */
+            uint32_t hist = 0;
+            if (a.history && !first && !a.in_off) {
+                const uint64_t in_member = (gb % a.member_blocks) * a.block_size, in_buffer = (uint64_t)a.lead + (uint64_t)b * a.block_size;
+                uint64_t h = in_member < in_buffer ? in_member : in_buffer;
+                if (h > a.history) h = a.history;
+                hist = (uint32_t)h - (uint32_t)h % BG_HISTORY_STEP;
+            }
+            src -= hist;
+            n += hist;
+            c.frame = bg_frame(first ? a.head_gap : 0u, last ? a.tail_gap : 0u, last && !a.no_final ? 1u : 0u, 1u, hist);
         }
+        c.n = n;
 
         /* 1. stage the payload: TMA for the 16-byte-aligned bulk, plain loads for the ragged rest */
         const bool aligned = (((uintptr_t)src) & 15u) == 0;
@@ -944,6 +960,10 @@ __device__ __forceinline__ void compress_blocks(BgzfCompressArgs &a)
                 dp_segment_warp(c, t >> 5, t & 31u, (uint32_t *)(smem + SM_REGA + 65536u) + (t >> 5) * BG_DP_RING);
             }
             __syncthreads();
+            if (bg_f_hist(c)) {                                  /* (uniform) */
+                bg_phase_history_steps(c, t, T);
+                __syncthreads();
+            }
             PROF_MARK(15);
             bg_phase_jump(c, t, T);
             __syncthreads();

@@ -44,6 +44,10 @@ struct BgzfCompressArgs {
     uint32_t tail_gap;         /* free bytes after a member's last piece */
     uint32_t no_final;         /* 1: no piece is final (dictzip closes the member with an empty block of its own) */
     uint32_t *crc_out;         /* device u32[nblocks], optional: CRC-32 of every block's input */
+    uint32_t history;          /* piece mode, fixed-size blocks: up to this many bytes (a multiple of 272, <= 32640; block_size + history
+                                  <= 65536) right before a piece are loaded with it as match history (dictionary priming); a member's
+                                  first piece has none */
+    uint32_t lead;             /* bytes of the stream present in the device buffer before `in` (history of this launch's first blocks) */
 };
 
 struct BgzfInflateArgs {

@@ -162,6 +162,7 @@ int b200bgzf_multi_inflate_host(b200bgzf_multi *m, const void *in, size_t in_byt
  * the data; beyond that (up to block_size 65536) a piece that does not compress makes the call return B200BGZF_E_NOFIT.
  */
 #define B200BGZF_MAX_GAP 64u
+#define B200BGZF_MAX_HISTORY 32640u
 typedef struct b200bgzf_piece_spec {
     uint32_t member_blocks;   /* pieces per member, >= 1 (0xffffffff: one member) */
     uint32_t head_gap;        /* <= B200BGZF_MAX_GAP */
@@ -169,6 +170,12 @@ typedef struct b200bgzf_piece_spec {
     uint32_t no_final;        /* 1: no piece is final (dictzip closes its member with an empty block of its own) */
     uint64_t piece_base;      /* the call's input is a slice of a longer stream of pieces: index of its first piece, and the */
     uint64_t piece_total;     /* number of pieces of the whole stream (0: the input is the whole stream) — for sharding over GPUs */
+    uint32_t history;         /* dictionary priming, as pigz does between its chunks: matches of a piece may reach up to this many
+                                 bytes back into the input before it, inside its member (0: independent pieces; else a multiple
+                                 of 272, at most B200BGZF_MAX_HISTORY, and block_size + history <= 65536).  Such pieces still end
+                                 on a byte but no longer decode on their own.  With piece_base > 0 the `history` bytes before
+                                 `in` must be readable: they are the end of the previous slice. */
+    uint32_t reserved;
 } b200bgzf_piece_spec;
 size_t b200bgzf_pieces_gap_bytes(size_t in_bytes, uint32_t block_size, const b200bgzf_piece_spec *spec);
 int b200bgzf_compress_pieces_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, uint32_t block_size, int level,
@@ -180,7 +187,8 @@ uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
 /*
  * The containers (host code in 7bgzf_b200/host/containers.c; `param` = 0 for the reference's default):
  *   GZIP     one gzip member (applet/7gzip.c + zlibrawstdio_compress.h:259-300 hand the whole file to one
- *            libdeflate_deflate call; here: independent 65280-byte pieces, as pigz -i does)
+ *            libdeflate_deflate call; here: 32 KiB pieces primed with the 32 KiB before them, as pigz does, or with
+ *            B200BGZF_PARAM_INDEPENDENT independent 65280-byte pieces, as pigz -i does)
  *   MIGZ     applet/7migz.c:133-243 — members of `param` KiB (default 512), subfield "MZ" = DEFLATE size
  *   GZINGA   applet/7gzinga.c:78-216 — 100 KiB members with an empty comment, then an index member whose comment lists
  *            "n:end-offset;" of every member
@@ -191,6 +199,8 @@ uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
  * b200bgzf_container_compress_host = plan + b200bgzf_compress_pieces_host + b200bgzf_container_frame.
  */
 #define B200BGZF_PARAM_SAFE 0x80000000u   /* MiGz: or-ed into param: pieces of at most 65280 bytes (see b200bgzf_container_plan) */
+#define B200BGZF_PARAM_PRIMED 0x40000000u      /* MiGz: 32 KiB pieces with dictionary priming inside every member (gzip: the default) */
+#define B200BGZF_PARAM_INDEPENDENT 0x20000000u /* gzip: independent 65280-byte pieces, as pigz -i (twice the throughput, +1.6 ... 2.8 % size) */
 #define B200BGZF_CONTAINER_GZIP 1
 #define B200BGZF_CONTAINER_MIGZ 2
 #define B200BGZF_CONTAINER_GZINGA 3

@@ -61,21 +61,26 @@ def emul_block(payload, level=6, order=0):
     return rc, dst.raw[: dl.value]
 
 
-def emul_piece(payload, level=6, head_gap=0, tail_gap=0, final=True, order=0):
-    """One block in piece mode (raw DEFLATE between `head_gap` and `tail_gap` free bytes): (slot bytes, CRC-32 of payload)."""
+def emul_piece(payload, level=6, head_gap=0, tail_gap=0, final=True, order=0, history=b""):
+    """One block in piece mode (raw DEFLATE between `head_gap` and `tail_gap` free bytes): (slot bytes, CRC-32 of payload).
+    history: the input right before the payload that matches may reach into (a multiple of 272 bytes, at most 32640)."""
     lib = _emul()
     lib.bgemul_set_piece.argtypes = [ctypes.c_uint32] * 4
     lib.bgemul_set_piece.restype = None
+    lib.bgemul_set_history.argtypes = [ctypes.c_uint32]
+    lib.bgemul_set_history.restype = None
     lib.bgemul_last_crc.restype = ctypes.c_uint32
     lib.bgemul_set_piece(1, head_gap, tail_gap, 1 if final else 0)
+    lib.bgemul_set_history(len(history))
     try:
-        rc, m = emul_block(payload, level, order)
+        rc, m = emul_block(history + payload, level, order)
         if rc == 1:
             raise OverflowError("the piece does not fit its slot")
         assert rc == 0, rc
         return m, lib.bgemul_last_crc()
     finally:
         lib.bgemul_set_piece(0, 0, 0, 1)
+        lib.bgemul_set_history(0)
 
 
 def emul_stream(data, level=6, block=BLOCK, order=0, eof=True):
@@ -281,7 +286,11 @@ def _emul_container(B, lib, kind, data, level, param):
         for i, b in enumerate(part):
             first = i % sp.member_blocks == 0
             last = (i + 1) % sp.member_blocks == 0 or i + 1 == len(part)
-            m, crc = emul_piece(b, level, sp.head_gap if first else 0, sp.tail_gap if last else 0, last and not sp.no_final)
+            # dictionary priming: what precedes the piece inside its member, as far as the window reaches (multiples of 272)
+            o = (done + i) * bs
+            h = min(sp.history, (i % sp.member_blocks) * bs)
+            h -= h % 272
+            m, crc = emul_piece(b, level, sp.head_gap if first else 0, sp.tail_gap if last else 0, last and not sp.no_final, history=data[o - h : o])
             offs.append(len(stream))
             crcs.append(crc)
             stream += m

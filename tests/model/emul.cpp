@@ -57,6 +57,9 @@ extern "C" void bgemul_set_piece(uint32_t enable, uint32_t head_gap, uint32_t ta
     g_emul_final = final ? 1 : 0;
 }
 extern "C" uint32_t bgemul_last_crc(void) { return g_emul_crc; }
+/* piece mode: the first `hist` bytes of the following calls' src are history (a multiple of 272, at most 32640) */
+static uint32_t g_emul_hist = 0;
+extern "C" void bgemul_set_history(uint32_t hist) { g_emul_hist = hist; }
 
 extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, int order, uint8_t *dst, uint32_t *dlen)
 {
@@ -86,7 +89,8 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
     c.crcpow = e->crcpow.data();
     c.perm = nullptr;
     c.n = n;
-    c.frame = g_emul_piece ? bg_frame(g_emul_head, g_emul_tail, g_emul_final, 1u) : bg_frame(g_emul_hdr, 8u, 1u, 0u);
+    if (g_emul_hist % BG_HISTORY_STEP || g_emul_hist > BG_MAX_HISTORY || g_emul_hist > n) return -3;
+    c.frame = g_emul_piece ? bg_frame(g_emul_head, g_emul_tail, g_emul_final, 1u, g_emul_hist) : bg_frame(g_emul_hdr, 8u, 1u, 0u);
     c.prm = bg_level_params(level);
     uint32_t k = 0;
     run(bg_phase_init, c, order, k++);
@@ -110,6 +114,7 @@ extern "C" int bgemul_compress_block(const uint8_t *src, uint32_t n, int level, 
             uint32_t *rings = (uint32_t *)(c.stepcode + 65536);
             for (uint32_t t = 0; t < BG_THREADS; t++) bg_phase_dp(c, order == 1 ? BG_THREADS - 1 - t : t, BG_THREADS, rings);
         }
+        run(bg_phase_history_steps, c, order, k++);
         run(bg_phase_jump, c, order, k++);
         run(bg_phase_walk_clear, c, order, k++);
         run(bg_phase_walk_mark, c, order, k++);

@@ -113,6 +113,36 @@ def test_migz_members_of_any_size_through_the_reference_reader(kib):
     assert out == data, rc
 
 
+PRIMED, INDEPENDENT = 0x40000000, 0x20000000
+
+
+@needs_ref
+def test_primed_pieces_reach_into_the_input_before_them():
+    """dictionary priming (what pigz does between its chunks; SURVEY 8f rank 4's "GPU route"): gzip by default, MiGz on request.
+    The streams decode everywhere; they are smaller than those of independent pieces; a primed piece decodes with the
+    history as its dictionary"""
+    data = H.synth("sam", 700001)
+    primed, indep = H.emul_container(B.CONTAINER_GZIP, data, 6), H.emul_container(B.CONTAINER_GZIP, data, 6, INDEPENDENT)
+    assert gzip.decompress(primed) == data and gzip.decompress(indep) == data
+    assert len(primed) < 0.985 * len(indep)
+    rc, out = H.ref_applet_decode("7gzip", primed)
+    assert out == data, rc
+    ref = _ref_written("gzip", data, __import__("pathlib").Path(__import__("tempfile").mkdtemp()))
+    assert len(primed) <= 1.03 * len(ref)                         # the reference's one libdeflate call over the whole file
+    m = H.emul_container(B.CONTAINER_MIGZ, data, 6, 512 | PRIMED)
+    assert gzip.decompress(m) == data and len(m) < len(H.emul_container(B.CONTAINER_MIGZ, data, 6, 512))
+    rc, out = H.ref_applet_decode("7migz", m)
+    assert out == data, rc
+    # members stay independent: the second member decodes on its own
+    dsz = struct.unpack_from("<I", m, 16)[0]
+    second = m[20 + dsz + 8 :]
+    assert gzip.decompress(second) == data[512 * 1024 :]
+    # one piece with its history
+    hist, payload = data[32768 - 32640 : 32768], data[32768 : 65536]
+    piece, crc = H.emul_piece(payload, 6, final=False, history=hist)
+    assert crc == zlib.crc32(payload) and zlib.decompressobj(-15, zdict=hist).decompress(piece) == payload
+
+
 def test_container_layouts():
     data = H.synth("fastq", 300000)
     # GZinga: index member lists the end offset of every member
@@ -273,6 +303,41 @@ def test_gpu_containers_are_the_emulated_ones(codec, kind, level):
     for name in ("fastq", "noise", "one", "edge"):
         data = INPUTS[name]
         assert codec.container(KINDS[kind], data, level) == H.emul_container(KINDS[kind], data, level), (kind, name, level)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, 6, 9, 12])
+def test_gpu_primed_containers_are_the_emulated_ones(codec, level):
+    data = H.synth("fastq", 400000) + H.lcg_noise(70000) + H.synth("sam", 300001)
+    for kind, param in ((B.CONTAINER_GZIP, 0), (B.CONTAINER_GZIP, INDEPENDENT), (B.CONTAINER_MIGZ, 512 | PRIMED), (B.CONTAINER_MIGZ, 100 | PRIMED)):
+        blob = codec.container(kind, data, level, param)
+        assert blob == H.emul_container(kind, data, level, param), (kind, hex(param), level)
+        assert gzip.decompress(blob) == data
+
+
+@pytest.mark.gpu
+def test_gpu_primed_pieces_across_batches_and_shards(codec):
+    """the history of a batch's (shard's) first piece is the end of the previous batch (shard): same bytes however the stream is cut"""
+    data = H.synth("sam", 48 << 20)                # 1536 pieces of 32 KiB: several host batches
+    whole = codec.container(B.CONTAINER_GZIP, data, 6)
+    o = zlib.decompressobj(31)
+    assert zlib.crc32(o.decompress(whole)) == zlib.crc32(data) and o.eof
+    m = B.MultiCodec([0, 0, 0])
+    try:
+        assert m.container(B.CONTAINER_GZIP, data, 6) == whole
+    finally:
+        m.close()
+    small = data[: 3 << 20]
+    assert codec.container(B.CONTAINER_GZIP, small, 6) == H.emul_container(B.CONTAINER_GZIP, small, 6)
+    # the piece API with a history the block size does not divide evenly into the window
+    spec = B.PieceSpec(0xFFFFFFFF, 0, 0, 0, 0, 0, 16320, 0)
+    stream, off, crc = codec.compress_pieces(small, spec, 6, 20000)
+    d = zlib.decompressobj(-15)
+    assert d.decompress(stream) == small and d.eof
+    with pytest.raises(B.B200BgzfError):
+        codec.compress_pieces(small, B.PieceSpec(0xFFFFFFFF, 0, 0, 0, 0, 0, 1000, 0), 6, 20000)      # not a multiple of 272
+    with pytest.raises(B.B200BgzfError):
+        codec.compress_pieces(small, B.PieceSpec(0xFFFFFFFF, 0, 0, 0, 0, 0, 32640, 0), 6, 40000)     # piece + history > 64 KiB
 
 
 @pytest.mark.gpu

@@ -51,13 +51,17 @@ for i in range(cases):
         import zlib
         k, hg, tg, nf = rnd.choice([1, 2, 3, 7, 0xFFFFFFFF]), rnd.randrange(0, 65), rnd.randrange(0, 65), rnd.randrange(4) == 0
         pbs = min(bs, 65536 - 5 - hg - tg)
-        spec = b200bgzf.PieceSpec(k, hg, tg, 1 if nf else 0)
+        hcfg = rnd.choice([0, 0, 272, 4080, 16320, 32640])           # dictionary priming
+        if hcfg: pbs = min(pbs, 65536 - hcfg)
+        spec = b200bgzf.PieceSpec(k, hg, tg, 1 if nf else 0, 0, 0, hcfg, 0)
         stream, off, crc = c.compress_pieces(data, spec, level, pbs)
         blocks = [data[j : j + pbs] for j in range(0, len(data), pbs)]
         want = bytearray()
         for j, b in enumerate(blocks):
             first, last = j % k == 0, (j + 1) % k == 0 or j + 1 == len(blocks)
-            m, cr = H.emul_piece(b, level, hg if first else 0, tg if last else 0, last and not nf)
+            h = min(hcfg, (j % k) * pbs)
+            h -= h % 272
+            m, cr = H.emul_piece(b, level, hg if first else 0, tg if last else 0, last and not nf, history=data[j * pbs - h : j * pbs])
             if off[j] != len(want) or crc[j] != cr:
                 bad += 1
                 print(f"case {i}: piece {j}: offset / CRC differs")
