@@ -63,6 +63,8 @@ static void usage(const char *argv0)
             "  -d, --decompress          decompress\n"
             "      --gzi=FILE            (extension) also write a bgzip-style .gzi index of the members to FILE\n"
             "      --devices=N           (extension) spread the blocks over N GPUs (contiguous block ranges, same output)\n"
+            "      --independent         (extension, 7gzip) pieces without the 32 KiB of history before them: faster, 2-3 %% larger\n"
+            "      --primed              (extension, 7migz) pieces of a member see the 32 KiB before them: slower, 2 %% smaller\n"
             "\nNote: every method runs on the B200 BGZF codec (libdeflate level classes 1-12).\n",
             argv0);
 }
@@ -437,6 +439,7 @@ int main(int argc, char **argv)
 {
     int levels[NFLAGS];
     int decompress = 0, nthreads = 1, bad = 0, ndevices = 1, migz = 0, bsize = 0, extreme = 0, kind = 0;
+    unsigned piece_flags = 0;    /* 7gzip --independent: pieces without dictionary priming; 7migz --primed: with it */
     const char *gzi_path = NULL, *persona = "7bgzf";
     memset(levels, 0, sizeof levels);
     /* allow `cielbox 7bgzf ...` style invocation.  As `7migz` (applet/7migz.c) with -b N <= 63 the same pipeline writes MiGz
@@ -462,13 +465,16 @@ int main(int argc, char **argv)
         { "threads", required_argument, 0, '@' }, { "decompress", no_argument, 0, 'd' },
         { "help", no_argument, 0, 'h' },         { "gzi", required_argument, 0, 1000 },
         { "devices", required_argument, 0, 1001 },  { "bsize", required_argument, 0, 'b' },
-        { "extreme", no_argument, 0, 'X' },
+        { "extreme", no_argument, 0, 'X' },      { "independent", no_argument, 0, 1002 },
+        { "primed", no_argument, 0, 1003 },
         { 0, 0, 0, 0 },
     };
     int opt;
     while ((opt = getopt_long(argc, argv, "cz::m::s::l::S::n::C::i::K::Z:T::@:dhb:X", longopts, NULL)) != -1) {
         if (opt == 'c') continue;
         if (opt == 'X') { extreme = 1; continue; }
+        if (opt == 1002) { piece_flags |= B200BGZF_PARAM_INDEPENDENT; continue; }
+        if (opt == 1003) { piece_flags |= B200BGZF_PARAM_PRIMED; continue; }
         if (opt == 'd') { decompress = 1; continue; }
         if (opt == '@') { nthreads = atoi(optarg); continue; }
         if (opt == 1000) { gzi_path = optarg; continue; }
@@ -489,12 +495,12 @@ int main(int argc, char **argv)
     struct timeval t0, t1;
     gettimeofday(&t0, NULL);
     if (migz && !bsize) bsize = 512;                               /* applet/7migz.c:327 */
-    if (kind && !(migz && (decompress || bsize <= 63) && optind == argc)) {
+    if (kind && !(migz && (decompress || (bsize <= 63 && !piece_flags)) && optind == argc)) {
         /* a container whose members span several pieces (or one that is read through its index) */
         int level = level_sum < 1 ? 1 : level_sum > 12 ? 12 : level_sum;
         if (!decompress) fprintf(stderr, "compression level = %d (%s)\n", level_sum, k_flags[chosen].label);
         if (migz && !decompress && (bsize < 1 || bsize > 4194303)) { fprintf(stderr, "7migz: -b %d: bad member size\n", bsize); return 1; }
-        const unsigned param = migz ? (unsigned)bsize : kind == B200BGZF_CONTAINER_DICTZIP && extreme ? B200BGZF_BLOCK_SIZE : 0u;
+        const unsigned param = (migz ? (unsigned)bsize : kind == B200BGZF_CONTAINER_DICTZIP && extreme ? B200BGZF_BLOCK_SIZE : 0u) | piece_flags;
         const int ret = container_applet(persona, kind, decompress, level, param, ndevices, argc - optind, argv + optind);
         gettimeofday(&t1, NULL);
         fprintf(stderr, "ellapsed time: %.6f sec\n", (t1.tv_sec + t1.tv_usec * 0.000001) - (t0.tv_sec + t0.tv_usec * 0.000001));

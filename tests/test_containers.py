@@ -489,6 +489,12 @@ def test_gpu_applet_personalities(codec, kind, tmp_path):
     if kind == "razf":                                  # the pieces over three contexts: the same file
         x = subprocess.run([exe, "-cl6", "--devices=3", str(src)], env=dict(os.environ, CUDA_VISIBLE_DEVICES="0,0,0"), capture_output=True)
         assert x.returncode != 0 or x.stdout == blob
+    if kind == "gzip":
+        x = subprocess.run([exe, "-cl6", "--independent"], input=data, capture_output=True)
+        assert x.returncode == 0 and x.stdout == codec.container(KINDS[kind], data, 6, INDEPENDENT)
+    if kind == "migz":
+        x = subprocess.run([exe, "-cl6", "--primed", "-b", "256"], input=data, capture_output=True)
+        assert x.returncode == 0 and x.stdout == codec.container(KINDS[kind], data, 6, 256 | PRIMED)
     if kind == "dictzip":
         x = subprocess.run([exe, "-cl6", "-X", str(src), str(enc)], capture_output=True)
         assert x.returncode == 0 and enc.read_bytes() == codec.container(KINDS[kind], data, 6, 65280)
