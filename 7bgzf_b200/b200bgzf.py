@@ -29,7 +29,7 @@ EXPORTS = [
     "b200bgzf_pieces_gap_bytes", "b200bgzf_compress_pieces_host", "b200bgzf_crc32_combine", "b200bgzf_container_plan",
     "b200bgzf_container_head", "b200bgzf_container_bound", "b200bgzf_container_frame", "b200bgzf_container_compress_host",
     "b200bgzf_inflate_units_host", "b200bgzf_container_units", "b200bgzf_units_free", "b200bgzf_container_inflate_host",
-    "b200bgzf_multi_container_bound", "b200bgzf_multi_container_compress_host",
+    "b200bgzf_multi_container_bound", "b200bgzf_multi_container_compress_host", "b200bgzf_container_inflate_size",
 ]
 CONTAINER_GZIP, CONTAINER_MIGZ, CONTAINER_GZINGA, CONTAINER_DICTZIP, CONTAINER_RAZF = 1, 2, 3, 4, 5
 
@@ -112,6 +112,7 @@ def load(path=LIB_PATH):
     lib.b200bgzf_units_free.argtypes = [punit]
     lib.b200bgzf_units_free.restype = None
     lib.b200bgzf_container_inflate_host.argtypes = [vp, i32, vp, sz, vp, sz, psz]
+    lib.b200bgzf_container_inflate_size.argtypes = [i32, vp, sz, psz, psz]
     lib.b200bgzf_multi_container_bound.argtypes = [vp, i32, u32, sz]
     lib.b200bgzf_multi_container_bound.restype = sz
     lib.b200bgzf_multi_container_compress_host.argtypes = [vp, i32, u32, vp, sz, i32, vp, sz, psz]
@@ -227,9 +228,11 @@ class Codec:
 
     def container_inflate(self, kind, blob):
         """b200bgzf_container_inflate_host"""
-        if kind == CONTAINER_MIGZ:
-            return self.inflate(blob)
-        _, total = container_units(kind, blob, self.lib)
+        total = ctypes.c_size_t()
+        rc = self.lib.b200bgzf_container_inflate_size(kind, _addr(blob), len(blob), ctypes.byref(total), None)
+        if rc != 0:
+            raise B200BgzfError(rc, "container size")
+        total = total.value
         out = bytearray(max(total, 1))
         n = ctypes.c_size_t()
         self._check(self.lib.b200bgzf_container_inflate_host(self.h, kind, _addr(blob), len(blob), _addr(out), len(out), ctypes.byref(n)))

@@ -65,17 +65,9 @@ int container_applet(const char *name, int kind, int decompress, int level, unsi
     long units = 0;
     int ret = 0;
     if (decompress) {
-        if (kind == B200BGZF_CONTAINER_MIGZ) {
-            size_t members = 0;
-            r = b200bgzf_inflate_size_host(src, n, &cap, &members);
-            units = (long)members;
-        } else {
-            b200bgzf_unit *u = NULL;
-            size_t nu = 0;
-            r = n ? b200bgzf_container_units(kind, src, n, &u, &nu, &cap) : B200BGZF_E_FORMAT;
-            b200bgzf_units_free(u);
-            units = (long)nu;
-        }
+        size_t nu = 0;
+        r = n ? b200bgzf_container_inflate_size(kind, src, n, &cap, &nu) : B200BGZF_E_FORMAT;
+        units = (long)nu;
         if (r != 0) { fprintf(stderr, "%s: not a %s file (possibly corrupted)\n", name, name + 1); ret = 1; }
         else if (!(dst = (unsigned char *)malloc(cap + 1))) { fprintf(stderr, "out of memory\n"); ret = 1; }
         else {

@@ -495,9 +495,35 @@ int b200bgzf_container_units(int kind, const void *in, size_t in_bytes, b200bgzf
 
 void b200bgzf_units_free(b200bgzf_unit *units) { free(units); }
 
+/* members that carry their own size (BGZF, MiGz, mgzip) are found by the header walk and decoded one warp each; `7gzip -d`
+ * takes that route too when its input turns out to be such a stream */
+static int sized_members(int kind, const void *in, size_t in_bytes, size_t *out_bytes, size_t *nmembers)
+{
+    if (kind != B200BGZF_CONTAINER_MIGZ && kind != B200BGZF_CONTAINER_GZIP) return 0;
+    return b200bgzf_inflate_size_host(in, in_bytes, out_bytes, nmembers) == 0;
+}
+
+int b200bgzf_container_inflate_size(int kind, const void *in, size_t in_bytes, size_t *out_bytes, size_t *nunits)
+{
+    size_t total = 0, n = 0;
+    if (!in || !out_bytes) return B200BGZF_E_ARG;
+    if (!sized_members(kind, in, in_bytes, &total, &n)) {
+        if (kind == B200BGZF_CONTAINER_MIGZ) return B200BGZF_E_FORMAT;
+        b200bgzf_unit *u = NULL;
+        const int rc = b200bgzf_container_units(kind, in, in_bytes, &u, &n, &total);
+        if (rc != 0) return rc;
+        free(u);
+    }
+    *out_bytes = total;
+    if (nunits) *nunits = n;
+    return B200BGZF_OK;
+}
+
 int b200bgzf_container_inflate_host(b200bgzf_ctx *ctx, int kind, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes)
 {
-    if (kind == B200BGZF_CONTAINER_MIGZ) return b200bgzf_inflate_host(ctx, in, in_bytes, out, out_cap, out_bytes, 0);
+    size_t sized_total = 0, sized_n = 0;
+    if (kind == B200BGZF_CONTAINER_MIGZ || (in && sized_members(kind, in, in_bytes, &sized_total, &sized_n)))
+        return b200bgzf_inflate_host(ctx, in, in_bytes, out, out_cap, out_bytes, 0);
     b200bgzf_unit *u = NULL;
     size_t n = 0, total = 0;
     int rc = b200bgzf_container_units(kind, in, in_bytes, &u, &n, &total);

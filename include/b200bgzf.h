@@ -233,6 +233,9 @@ int b200bgzf_container_units(int kind, const void *in, size_t in_bytes, b200bgzf
 void b200bgzf_units_free(b200bgzf_unit *units);
 int b200bgzf_container_inflate_host(b200bgzf_ctx *ctx, int kind, const void *in, size_t in_bytes, void *out, size_t out_cap,
                                     size_t *out_bytes);
+/* decoded size (and number of units) of a container, to size the output: MiGz — and gzip input that turns out to be a
+ * stream of members carrying their own size (BGZF, MiGz, mgzip) — by the header walk, the others by their index */
+int b200bgzf_container_inflate_size(int kind, const void *in, size_t in_bytes, size_t *out_bytes, size_t *nunits);
 
 /* Page-locked host memory for the *_host entry points (pageable buffers work too, but are copied at a fraction of
  * the PCIe rate).  The applet reads stdin straight into such buffers. */

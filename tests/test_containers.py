@@ -528,3 +528,17 @@ def test_gpu_containers_over_several_contexts_are_the_single_gpu_ones(codec):
             assert m.container(B.CONTAINER_MIGZ, noisy, 6) == codec.container(B.CONTAINER_MIGZ, noisy, 6)     # (the redo in small pieces)
         finally:
             m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_7gzip_reads_streams_of_sized_members_in_parallel(codec):
+    """`7gzip -d` on a BGZF or MiGz stream: the members carry their size, so the header walk finds them (one warp each)
+    instead of one warp for the whole file"""
+    import subprocess
+    data = H.synth("fastq", 5 << 20)
+    bgzf = codec.compress(data, 6)
+    assert codec.container_inflate(B.CONTAINER_GZIP, bgzf) == data
+    assert codec.container_inflate(B.CONTAINER_GZIP, codec.container(B.CONTAINER_MIGZ, data, 6)) == data
+    exe = os.path.join(os.path.dirname(B.APPLET_PATH), "7gzip")
+    d = subprocess.run([exe, "-d"], input=bgzf, capture_output=True)
+    assert d.returncode == 0 and d.stdout == data and b"82 done." in d.stderr        # 81 members + the EOF marker
