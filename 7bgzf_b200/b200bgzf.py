@@ -107,11 +107,11 @@ def load(path=LIB_PATH):
     lib.b200bgzf_container_frame.restype = sz
     lib.b200bgzf_container_compress_host.argtypes = [vp, i32, u32, vp, sz, i32, vp, sz, psz]
     punit = ctypes.POINTER(Unit)
-    lib.b200bgzf_inflate_units_host.argtypes = [vp, vp, sz, punit, sz, vp, sz, psz, ctypes.c_uint]
+    lib.b200bgzf_inflate_units_host.argtypes = [vp, vp, sz, punit, sz, vp, sz, psz, ctypes.c_uint, pu32]
     lib.b200bgzf_container_units.argtypes = [i32, vp, sz, ctypes.POINTER(punit), psz, psz]
     lib.b200bgzf_units_free.argtypes = [punit]
     lib.b200bgzf_units_free.restype = None
-    lib.b200bgzf_container_inflate_host.argtypes = [vp, i32, vp, sz, vp, sz, psz]
+    lib.b200bgzf_container_inflate_host.argtypes = [vp, i32, vp, sz, vp, sz, psz, ctypes.c_uint]
     lib.b200bgzf_container_inflate_size.argtypes = [i32, vp, sz, psz, psz]
     lib.b200bgzf_multi_container_bound.argtypes = [vp, i32, u32, sz]
     lib.b200bgzf_multi_container_bound.restype = sz
@@ -226,7 +226,7 @@ class Codec:
                                                               _addr(out), len(out), ctypes.byref(n)))
         return bytes(out[: n.value])
 
-    def container_inflate(self, kind, blob):
+    def container_inflate(self, kind, blob, flags=0):
         """b200bgzf_container_inflate_host"""
         total = ctypes.c_size_t()
         rc = self.lib.b200bgzf_container_inflate_size(kind, _addr(blob), len(blob), ctypes.byref(total), None)
@@ -235,15 +235,16 @@ class Codec:
         total = total.value
         out = bytearray(max(total, 1))
         n = ctypes.c_size_t()
-        self._check(self.lib.b200bgzf_container_inflate_host(self.h, kind, _addr(blob), len(blob), _addr(out), len(out), ctypes.byref(n)))
+        self._check(self.lib.b200bgzf_container_inflate_host(self.h, kind, _addr(blob), len(blob), _addr(out), len(out), ctypes.byref(n), flags))
         return bytes(out[: n.value])
 
-    def inflate_units(self, blob, units, out_bytes):
+    def inflate_units(self, blob, units, out_bytes, flags=0, want_crc=False):
         arr = (Unit * len(units))(*[Unit(*u) for u in units])
         out = bytearray(max(out_bytes, 1))
         n = ctypes.c_size_t()
-        self._check(self.lib.b200bgzf_inflate_units_host(self.h, _addr(blob), len(blob), arr, len(units), _addr(out), len(out), ctypes.byref(n), 0))
-        return bytes(out[: n.value])
+        crc = (ctypes.c_uint32 * max(len(units), 1))() if want_crc else None
+        self._check(self.lib.b200bgzf_inflate_units_host(self.h, _addr(blob), len(blob), arr, len(units), _addr(out), len(out), ctypes.byref(n), flags, crc))
+        return (bytes(out[: n.value]), list(crc[: len(units)])) if want_crc else bytes(out[: n.value])
 
     def compress_indexed(self, data, level=6, block_size=BLOCK_SIZE, eof=True):
         """(stream, member offsets) — b200bgzf_compress_host_index"""

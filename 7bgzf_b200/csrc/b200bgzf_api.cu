@@ -1260,7 +1260,7 @@ extern "C" int b200bgzf_inflate_device(b200bgzf_ctx *ctx, const void *d_in, size
 namespace {
 /* units == nullptr: the members are found by walking their headers; else: the caller's list (members and raw pieces) */
 int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const b200bgzf_unit *units, size_t nunits, void *out,
-                      size_t out_cap, size_t *out_bytes, unsigned flags)
+                      size_t out_cap, size_t *out_bytes, unsigned flags, uint32_t *unit_crc = nullptr)
 {
     if (!ctx || !in || !out_bytes) return B200BGZF_E_ARG;
     const uint8_t *p = (const uint8_t *)in;
@@ -1285,6 +1285,7 @@ int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const 
         CK(cudaStreamSynchronize(l.stream));
         if (l.h_total[1] & 1u) bad = true;
         if (l.h_total[1] & 2u) badcrc = true;
+        if (unit_crc) memcpy(unit_crc + l.pend_first, (const uint32_t *)(l.h_meta + 2 * kBatchMax) + 3 * kBatchMax, l.pend_nb * sizeof(uint32_t));
         l.pending = false;
         return 0;
     };
@@ -1304,6 +1305,7 @@ int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const 
         size_t in0 = off;
         const size_t out0 = total;
         size_t nb = 0;
+        const size_t u0 = u;
         if (units) {
             in0 = off = (size_t)units[u].in_off;
             while (nb < batch && u < nunits) {
@@ -1361,9 +1363,15 @@ int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const 
         a.err_flag = (uint32_t *)(l.d_total + 1);
         a.crctab = ctx->d_crctab;
         a.crcpow = ctx->d_crcpow;
-        a.verify_crc = (flags & B200BGZF_VERIFY) ? 1 : 0;
+        a.verify_crc = ((flags & B200BGZF_VERIFY) || unit_crc) ? 1 : 0;
+        if (unit_crc) a.unit_crc = (uint32_t *)l.d_off + kBatchMax;       /* (second half of the u64 array whose first half holds unit_isize) */
         CK(bgzf_launch_inflate(&a, l.stream));
         ctx->launches += 1 + a.verify_crc;
+        if (unit_crc) {
+            CK(cudaMemcpyAsync((uint32_t *)(l.h_meta + 2 * kBatchMax) + 3 * kBatchMax, a.unit_crc, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
+            l.pend_first = u0;
+            l.pend_nb = (uint32_t)nb;
+        }
         if (obytes) CK(cudaMemcpyAsync((uint8_t *)out + out0, l.d_out, obytes, cudaMemcpyDeviceToHost, l.stream));
         CK(cudaMemcpyAsync(l.h_total, l.d_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, l.stream));
         l.pending = true;
@@ -1382,12 +1390,12 @@ extern "C" int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t i
 }
 
 extern "C" int b200bgzf_inflate_units_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const b200bgzf_unit *units, size_t nunits,
-                                           void *out, size_t out_cap, size_t *out_bytes, unsigned flags)
+                                           void *out, size_t out_cap, size_t *out_bytes, unsigned flags, uint32_t *unit_crc)
 {
     if (!units && nunits) return B200BGZF_E_ARG;
     if (nunits == 0) {
         if (out_bytes) *out_bytes = 0;
         return out_bytes ? B200BGZF_OK : B200BGZF_E_ARG;
     }
-    return inflate_host_impl(ctx, in, in_bytes, units, nunits, out, out_cap, out_bytes, flags);
+    return inflate_host_impl(ctx, in, in_bytes, units, nunits, out, out_cap, out_bytes, flags, unit_crc);
 }

@@ -548,14 +548,20 @@ bgzf_verify_kernel(BgzfInflateArgs a)
     extern __shared__ __align__(16) uint8_t vs[];
     const uint32_t t = threadIdx.x, m = blockIdx.x;
     if (m >= a.nblocks || a.status[m] != INF_OK) return;          /* (uniform for the CTA) */
-    if (a.unit_isize && a.unit_isize[m] != 0xffffffffu) return;   /* a piece has no trailer of its own */
+    /* a piece has no trailer of its own: its CRC goes to unit_crc[] for the host to combine (host/containers.c) */
+    const bool piece = a.unit_isize && a.unit_isize[m] != 0xffffffffu;
+    if (piece && !a.unit_crc) return;
     const uint8_t *mem = a.in + a.in_off[m];
     const uint32_t msize = a.hdr_len ? a.msize[m] : ((uint32_t)mem[16] | ((uint32_t)mem[17] << 8)) + 1u;
     const uint8_t *tr = mem + msize - 8;
-    const uint32_t want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
-    const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    uint32_t want = 0, isize;
+    if (piece) {
+        isize = a.unit_isize[m];
+    } else {
+        want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    }
     const uint8_t *out = a.out + a.out_off[m];
-    if (isize > BG_MAX_BLOCK) return;                 /* (members of other containers may be larger than a BGZF block: not checked) */
     BgCtx c;
     memset(&c, 0, sizeof c);
     c.dataw = (uint32_t *)vs;
@@ -563,31 +569,56 @@ bgzf_verify_kernel(BgzfInflateArgs a)
     c.litflag = vs + BG_DATA_BYTES + 1024u;
     c.scal = (uint32_t *)(vs + BG_DATA_BYTES + 1024u + 256u);
     c.crcpow = a.crcpow;
-    c.n = isize;
     c.frame = bg_frame(18u, 8u, 1u, 0u);
-    /* stage: bytes up to the first 16-byte boundary of the source, 16-byte loads for the body, bytes for the rest */
-    const uint32_t head = isize < 16 ? isize : (uint32_t)((16u - ((uintptr_t)out & 15u)) & 15u);
-    const uint32_t body = (isize - head) & ~15u;
-    if (t < head) vs[t] = out[t];
-    for (uint32_t i = t * 16u; i < body; i += BG_THREADS * 16u) {
-        const uint4 v = __ldcs((const uint4 *)(out + head + i));
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-        for (uint32_t k = 0; k < 16; k++) vs[head + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));   /* (destination is not aligned when head != 0) */
-    }
-    for (uint32_t i = head + body + t; i < isize; i += BG_THREADS) vs[i] = out[i];
-    if (t < 28) vs[isize + t] = 0;
     if (t < 256) c.crctab[t] = a.crctab[t];
-    if (t < BG_S_COUNT) c.scal[t] = 0;
-    __syncthreads();
-    bg_phase_scan(c, t, BG_THREADS);
-    __syncthreads();
+    /* members of the other containers may be larger than a BGZF block: tiles of 64 KiB, their CRCs combined as zlib's
+     * crc32_combine does (lib/zlib/crc32.c:1021-1026): crc(A||B) = crc(A) * x^(8 len B) + crc(B) */
+    uint32_t crc = 0;
+    for (uint32_t done = 0; done < isize; done += BG_MAX_BLOCK) {
+        const uint32_t len = isize - done < BG_MAX_BLOCK ? isize - done : BG_MAX_BLOCK;
+        const uint8_t *src = out + done;
+        c.n = len;
+        __syncthreads();                                 /* (the previous tile's thread 0 is done with the buffer) */
+        /* stage: bytes up to the first 16-byte boundary of the source, 16-byte loads for the body, bytes for the rest */
+        const uint32_t head = len < 16 ? len : (uint32_t)((16u - ((uintptr_t)src & 15u)) & 15u);
+        const uint32_t body = (len - head) & ~15u;
+        if (t < head) vs[t] = src[t];
+        for (uint32_t i = t * 16u; i < body; i += BG_THREADS * 16u) {
+            const uint4 v = __ldcs((const uint4 *)(src + head + i));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            for (uint32_t k = 0; k < 16; k++) vs[head + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));   /* (destination is not aligned when head != 0) */
+        }
+        for (uint32_t i = head + body + t; i < len; i += BG_THREADS) vs[i] = src[i];
+        if (t < 28) vs[len + t] = 0;
+        if (t < BG_S_COUNT) c.scal[t] = 0;
+        __syncthreads();
+        bg_phase_scan(c, t, BG_THREADS);
+        __syncthreads();
+        if (t == 0) {
+            uint32_t r = c.scal[BG_S_CRC];
+            if ((len >> 2) == 0) r = 0xFFFFFFFFu;
+            for (uint32_t p = len & ~3u; p < len; p++) r = bg_crc_byte(c.crctab, r, vs[p]);
+            if (done == 0) {
+                crc = ~r;
+            } else {
+                uint32_t shift = 0x80000000u, sq = 0x00800000u;          /* 1, x^8 (reflected: bit 31 is x^0) */
+                for (uint32_t e = len; e; e >>= 1) {
+                    if (e & 1u) shift = bg_crc_mul(shift, sq);
+                    sq = bg_crc_mul(sq, sq);
+                }
+                crc = bg_crc_mul(crc, shift) ^ ~r;
+            }
+        }
+    }
     if (t == 0) {
-        uint32_t r = c.scal[BG_S_CRC];
-        if ((isize >> 2) == 0) r = 0xFFFFFFFFu;
-        for (uint32_t p = isize & ~3u; p < isize; p++) r = bg_crc_byte(c.crctab, r, vs[p]);
-        if (~r != want) {
-            a.status[m] = INF_E_CRC;
-            atomicOr(a.err_flag, 2u);
+        if (piece) {
+            a.unit_crc[m] = crc;
+        } else {
+            if (a.unit_crc) a.unit_crc[m] = crc;
+            if (crc != want) {
+                a.status[m] = INF_E_CRC;
+                atomicOr(a.err_flag, 2u);
+            }
         }
     }
 }

@@ -59,6 +59,7 @@ struct BgzfInflateArgs {
     const uint32_t *msize;     /* device, with hdr_len: whole member size */
     const uint32_t *unit_isize; /* device, optional (with hdr_len): 0xffffffff = a member (ISIZE from its trailer); anything else = a raw
                                   DEFLATE piece of msize bytes (hdr_len bytes skipped, no trailer) that yields this many bytes */
+    uint32_t *unit_crc;        /* device, optional (verify_crc): out: CRC-32 of every unit's output (a piece has no trailer to check it against) */
     uint32_t nblocks;
     uint8_t *out;              /* device */
     uint32_t *status;          /* device: 0 ok, else error code per member */

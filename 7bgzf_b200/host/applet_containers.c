@@ -72,7 +72,7 @@ int container_applet(const char *name, int kind, int decompress, int level, unsi
         else if (!(dst = (unsigned char *)malloc(cap + 1))) { fprintf(stderr, "out of memory\n"); ret = 1; }
         else {
             memset(dst, 0, cap + 1);
-            r = b200bgzf_container_inflate_host(ctx, kind, src, n, dst, cap, &produced);
+            r = b200bgzf_container_inflate_host(ctx, kind, src, n, dst, cap, &produced, B200BGZF_VERIFY);     /* unlike the reference, check every member's CRC-32 */
             if (r != 0) { fprintf(stderr, "inflate %d\n", r); ret = 1; }
         }
     } else {

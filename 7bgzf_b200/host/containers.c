@@ -342,11 +342,33 @@ static size_t gz_header(const uint8_t *p, size_t avail, size_t *xoff, size_t *xl
     return n <= avail ? n : 0;
 }
 
+/* a member made of pieces: units [first, first + count) together must have the CRC-32 its trailer states */
+struct member_check {
+    size_t first, count;
+    uint32_t crc;
+};
 struct unit_list {
     b200bgzf_unit *u;
     size_t n, cap;
     uint64_t out_bytes;
+    struct member_check *chk;
+    size_t nchk, chk_cap;
 };
+static int check_push(struct unit_list *l, size_t first, size_t count, uint32_t crc)
+{
+    if (l->nchk == l->chk_cap) {
+        const size_t cap = l->chk_cap ? l->chk_cap * 2 : 16;
+        struct member_check *c = (struct member_check *)realloc(l->chk, cap * sizeof *c);
+        if (!c) return -1;
+        l->chk = c;
+        l->chk_cap = cap;
+    }
+    l->chk[l->nchk].first = first;
+    l->chk[l->nchk].count = count;
+    l->chk[l->nchk].crc = crc;
+    l->nchk++;
+    return 0;
+}
 static int unit_push(struct unit_list *l, uint64_t in_off, uint64_t in_len, uint32_t hdr_len, uint64_t out_len, int piece)
 {
     if (in_len == 0 || in_len > 0xffffffffull || out_len > 0xffffffffull) return -1;
@@ -389,6 +411,7 @@ static int units_dictzip(const uint8_t *p, size_t n, struct unit_list *l)
         const uint64_t isize = get32(p + at + 4);
         if (chcnt && (isize > (uint64_t)chcnt * chlen || isize + chlen <= (uint64_t)chcnt * chlen)) return B200BGZF_E_FORMAT;
         uint64_t off = pos + h;
+        if (chcnt && check_push(l, l->n, chcnt, get32(p + at))) return B200BGZF_E_FORMAT;
         for (uint32_t i = 0; i < chcnt; i++) {
             const uint32_t sz = get16(x + 10 + 2 * i);
             const uint64_t outl = i + 1 < chcnt ? chlen : isize - (uint64_t)(chcnt - 1) * chlen;
@@ -416,6 +439,7 @@ static int units_razf(const uint8_t *p, size_t n, struct unit_list *l)
     if (fsize == 0) return B200BGZF_OK;
     if (tb + 1 != (fsize + bs - 1) / bs) return B200BGZF_E_FORMAT;
     uint64_t start = h;
+    if (check_push(l, 0, (size_t)tb + 1, get32(p + index_at - 8))) return B200BGZF_E_FORMAT;
     for (uint64_t i = 0; i <= tb; i++) {
         uint64_t next = index_at - 8;                                        /* the last block ends at the trailer */
         if (i < tb) next = get64be(p + index_at + 4 + 8 * (i / binsize)) + get32be(p + cells_at + 4 * i);
@@ -470,19 +494,25 @@ static int units_gzip(const uint8_t *p, size_t n, struct unit_list *l)
     return unit_push(l, 0, n, (uint32_t)h, get32(p + n - 4), 0) ? B200BGZF_E_FORMAT : B200BGZF_OK;
 }
 
+static int list_units(int kind, const void *in, size_t in_bytes, struct unit_list *l)
+{
+    memset(l, 0, sizeof *l);
+    switch (kind) {
+    case B200BGZF_CONTAINER_DICTZIP: return units_dictzip((const uint8_t *)in, in_bytes, l);
+    case B200BGZF_CONTAINER_RAZF: return units_razf((const uint8_t *)in, in_bytes, l);
+    case B200BGZF_CONTAINER_GZINGA: return units_gzinga((const uint8_t *)in, in_bytes, l);
+    case B200BGZF_CONTAINER_GZIP: return units_gzip((const uint8_t *)in, in_bytes, l);
+    }
+    return B200BGZF_E_ARG;
+}
+
 int b200bgzf_container_units(int kind, const void *in, size_t in_bytes, b200bgzf_unit **units, size_t *nunits, size_t *out_bytes)
 {
     if (!in || !units || !nunits) return B200BGZF_E_ARG;
     if (in_bytes == 0) return B200BGZF_E_FORMAT;
-    struct unit_list l = { NULL, 0, 0, 0 };
-    int rc;
-    switch (kind) {
-    case B200BGZF_CONTAINER_DICTZIP: rc = units_dictzip((const uint8_t *)in, in_bytes, &l); break;
-    case B200BGZF_CONTAINER_RAZF: rc = units_razf((const uint8_t *)in, in_bytes, &l); break;
-    case B200BGZF_CONTAINER_GZINGA: rc = units_gzinga((const uint8_t *)in, in_bytes, &l); break;
-    case B200BGZF_CONTAINER_GZIP: rc = units_gzip((const uint8_t *)in, in_bytes, &l); break;
-    default: rc = B200BGZF_E_ARG;
-    }
+    struct unit_list l;
+    const int rc = list_units(kind, in, in_bytes, &l);
+    free(l.chk);
     if (rc != 0) {
         free(l.u);
         return rc;
@@ -519,18 +549,35 @@ int b200bgzf_container_inflate_size(int kind, const void *in, size_t in_bytes, s
     return B200BGZF_OK;
 }
 
-int b200bgzf_container_inflate_host(b200bgzf_ctx *ctx, int kind, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes)
+int b200bgzf_container_inflate_host(b200bgzf_ctx *ctx, int kind, const void *in, size_t in_bytes, void *out, size_t out_cap, size_t *out_bytes,
+                                    unsigned flags)
 {
     size_t sized_total = 0, sized_n = 0;
     if (kind == B200BGZF_CONTAINER_MIGZ || (in && sized_members(kind, in, in_bytes, &sized_total, &sized_n)))
-        return b200bgzf_inflate_host(ctx, in, in_bytes, out, out_cap, out_bytes, 0);
-    b200bgzf_unit *u = NULL;
-    size_t n = 0, total = 0;
-    int rc = b200bgzf_container_units(kind, in, in_bytes, &u, &n, &total);
-    if (rc != 0) return rc;
-    if (out_bytes) *out_bytes = total;
-    if (total > out_cap) rc = B200BGZF_E_NOSPACE;
-    else rc = b200bgzf_inflate_units_host(ctx, in, in_bytes, u, n, out, out_cap, out_bytes, 0);
-    free(u);
+        return b200bgzf_inflate_host(ctx, in, in_bytes, out, out_cap, out_bytes, flags);
+    if (!in || in_bytes == 0) return in ? B200BGZF_E_FORMAT : B200BGZF_E_ARG;
+    struct unit_list l;
+    int rc = list_units(kind, in, in_bytes, &l);
+    uint32_t *crc = NULL;
+    if (rc == 0) {
+        if (out_bytes) *out_bytes = (size_t)l.out_bytes;
+        /* B200BGZF_VERIFY: members are checked against their trailers on the device; the CRC-32 of a member made of pieces
+         * (dictzip, RAZF) is combined here from those of its pieces (the reference's readers check neither) */
+        if ((flags & B200BGZF_VERIFY) && l.nchk && !(crc = (uint32_t *)malloc(sizeof(uint32_t) * (l.n + 1)))) rc = B200BGZF_E_ARG;
+        else if (l.out_bytes > out_cap) rc = B200BGZF_E_NOSPACE;
+        else rc = b200bgzf_inflate_units_host(ctx, in, in_bytes, l.u, l.n, out, out_cap, out_bytes, flags, crc);
+    }
+    if (rc == 0 && crc)
+        for (size_t k = 0; k < l.nchk && rc == 0; k++) {
+            uint32_t c = 0;
+            for (size_t i = 0; i < l.chk[k].count; i++) {
+                const size_t ui = l.chk[k].first + i;
+                c = i ? b200bgzf_crc32_combine(c, crc[ui], l.u[ui].out_len) : crc[ui];
+            }
+            if (c != l.chk[k].crc) rc = B200BGZF_E_CRC;
+        }
+    free(crc);
+    free(l.u);
+    free(l.chk);
     return rc;
 }

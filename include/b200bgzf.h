@@ -116,7 +116,9 @@ int b200bgzf_inflate_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, vo
  * a gzip member (piece = 0: hdr_len bytes of header, DEFLATE data, CRC32 + ISIZE; out_len is ignored, ISIZE counts) or a raw
  * DEFLATE piece (piece = 1: in_len bytes after hdr_len skipped bytes, no trailer) that is complete once it has produced
  * out_len bytes at a block boundary.  Units are listed in ascending input order; their outputs follow one another in `out`.
- * One warp decodes one unit, as for BGZF members.  (B200BGZF_VERIFY checks the members only: pieces carry no CRC.)
+ * One warp decodes one unit, as for BGZF members.  B200BGZF_VERIFY checks the members against their trailers (members of
+ * any size); unit_crc (optional, nunits entries) receives the CRC-32 of every unit's output — a piece carries none of its
+ * own: the caller combines them (b200bgzf_crc32_combine) and compares with its container's member trailer.
  */
 typedef struct b200bgzf_unit {
     uint64_t in_off;
@@ -126,7 +128,7 @@ typedef struct b200bgzf_unit {
     uint32_t piece;
 } b200bgzf_unit;
 int b200bgzf_inflate_units_host(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const b200bgzf_unit *units, size_t nunits,
-                                void *out, size_t out_cap, size_t *out_bytes, unsigned flags);
+                                void *out, size_t out_cap, size_t *out_bytes, unsigned flags, uint32_t *unit_crc);
 
 /*
  * Several GPUs behind one call (the reference's fan-out over blocks: applet/7bgzf.c:159-227).  GPU g of G takes
@@ -232,7 +234,7 @@ int b200bgzf_multi_container_compress_host(b200bgzf_multi *m, int kind, uint32_t
 int b200bgzf_container_units(int kind, const void *in, size_t in_bytes, b200bgzf_unit **units, size_t *nunits, size_t *out_bytes);
 void b200bgzf_units_free(b200bgzf_unit *units);
 int b200bgzf_container_inflate_host(b200bgzf_ctx *ctx, int kind, const void *in, size_t in_bytes, void *out, size_t out_cap,
-                                    size_t *out_bytes);
+                                    size_t *out_bytes, unsigned flags);   /* flags: 0 or B200BGZF_VERIFY (CRC-32 of every member) */
 /* decoded size (and number of units) of a container, to size the output: MiGz — and gzip input that turns out to be a
  * stream of members carrying their own size (BGZF, MiGz, mgzip) — by the header walk, the others by their index */
 int b200bgzf_container_inflate_size(int kind, const void *in, size_t in_bytes, size_t *out_bytes, size_t *nunits);

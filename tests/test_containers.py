@@ -542,3 +542,35 @@ def test_gpu_7gzip_reads_streams_of_sized_members_in_parallel(codec):
     exe = os.path.join(os.path.dirname(B.APPLET_PATH), "7gzip")
     d = subprocess.run([exe, "-d"], input=bgzf, capture_output=True)
     assert d.returncode == 0 and d.stdout == data and b"82 done." in d.stderr        # 81 members + the EOF marker
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", sorted(KINDS))
+def test_gpu_verify_flag_checks_the_crc_of_every_member(codec, kind):
+    """B200BGZF_VERIFY on the containers: members of any size against their trailers (64 KiB tiles combined on the device),
+    members made of pieces (dictzip, RAZF) from the CRCs of their pieces combined on the host.  A flipped byte inside a
+    stored block changes the output without upsetting the decoder: only the check sees it"""
+    data = H.synth("fastq", 300000) + H.lcg_noise(200000) + H.synth("sam", 300000)
+    blob = codec.container(KINDS[kind], data, 6)
+    assert codec.container_inflate(KINDS[kind], blob, B.VERIFY) == data
+    at = blob.index(H.lcg_noise(200000)[70000:70032])            # raw bytes of a stored piece
+    dmg = bytearray(blob)
+    dmg[at + 5] ^= 0x20
+    got = codec.container_inflate(KINDS[kind], bytes(dmg))        # no check: decodes, one byte off
+    assert got != data and len(got) == len(data)
+    with pytest.raises(B.B200BgzfError) as e:
+        codec.container_inflate(KINDS[kind], bytes(dmg), B.VERIFY)
+    assert e.value.code == B.E_CRC
+
+
+@pytest.mark.gpu
+def test_gpu_unit_crcs(codec):
+    data = H.synth("sam", 400000)
+    blob = codec.container(B.CONTAINER_RAZF, data, 6)
+    units, total = B.container_units(B.CONTAINER_RAZF, blob)
+    out, crcs = codec.inflate_units(blob, units, total, want_crc=True)
+    assert out == data and crcs == [zlib.crc32(data[i : i + 32768]) for i in range(0, len(data), 32768)]
+    z = codec.container(B.CONTAINER_GZINGA, data, 6)               # members of 100 KiB: two tiles each on the device
+    units, total = B.container_units(B.CONTAINER_GZINGA, z)
+    out, crcs = codec.inflate_units(z, units, total, want_crc=True)
+    assert out == data and crcs == [zlib.crc32(data[i : i + 102400]) for i in range(0, len(data), 102400)]

@@ -42,7 +42,7 @@ for name, kind, applet, param in KINDS:
     tc = timed(comp)
     clen = got.value
     def dec():
-        rc = c.lib.b200bgzf_container_inflate_host(c.h, kind, out.data_ptr(), clen, back.data_ptr(), n, ctypes.byref(got))
+        rc = c.lib.b200bgzf_container_inflate_host(c.h, kind, out.data_ptr(), clen, back.data_ptr(), n, ctypes.byref(got), 0)
         assert rc == 0 and got.value == n, (rc, got.value)
     line = {"container": name, "MiB": mib, "level": 6, "compress_e2e_GBps": round(n / tc / 1e9, 2), "ratio": round(clen / n, 4)}
     if kind != B.CONTAINER_GZIP:              # (a gzip member without an index is one unit: one warp — timed on a small sample below)

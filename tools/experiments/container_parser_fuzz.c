@@ -12,7 +12,8 @@ size_t b200bgzf_compress_bound(size_t n, uint32_t bs) { return n + 38 * ((n + bs
 size_t b200bgzf_pieces_gap_bytes(size_t a, uint32_t b, const b200bgzf_piece_spec *s) { return 0; }
 int b200bgzf_compress_pieces_host(b200bgzf_ctx *c, const void *in, size_t n, uint32_t bs, int l, const b200bgzf_piece_spec *s, void *o, size_t cap, size_t *ob, uint64_t *po, uint32_t *pc, size_t pcap) { return -2; }
 int b200bgzf_inflate_host(b200bgzf_ctx *c, const void *in, size_t n, void *o, size_t cap, size_t *ob, unsigned f) { return -2; }
-int b200bgzf_inflate_units_host(b200bgzf_ctx *c, const void *in, size_t n, const b200bgzf_unit *u, size_t nu, void *o, size_t cap, size_t *ob, unsigned f) { return -2; }
+int b200bgzf_inflate_units_host(b200bgzf_ctx *c, const void *in, size_t n, const b200bgzf_unit *u, size_t nu, void *o, size_t cap, size_t *ob, unsigned f, uint32_t *crc) { return -2; }
+int b200bgzf_inflate_size_host(const void *in, size_t n, size_t *ob, size_t *nm) { return -3; }
 static unsigned long long rs = 88172645463325252ull;
 static unsigned rnd(void) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (unsigned)(rs >> 11); }
 int main(int argc, char **argv)
