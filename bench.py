@@ -156,6 +156,41 @@ def newest_traffic_file():
     return best[1] if best else None
 
 
+def container_lines(codec, h_in, n, h_out, h_back):
+    """whole-stream gzip (primed pieces), MiGz (512 KiB members), GZinga, dictzip, RAZF through b200bgzf_container_*_host:
+    GB/s end to end (pinned host buffers, H2D + kernels + D2H + host framing in the timed call) and compressed size"""
+    import torch
+    import b200bgzf
+    kinds = (("gzip", b200bgzf.CONTAINER_GZIP), ("migz", b200bgzf.CONTAINER_MIGZ), ("gzinga", b200bgzf.CONTAINER_GZINGA),
+             ("dictzip", b200bgzf.CONTAINER_DICTZIP), ("razf", b200bgzf.CONTAINER_RAZF))
+    res = {"MiB": n >> 20, "level": 6, "unit": "GB/s"}
+    got = ctypes.c_size_t()
+    for name, kind in kinds:
+        cap = codec.lib.b200bgzf_container_bound(kind, 0, n)
+        if cap > h_out.numel():
+            continue
+
+        def comp():
+            rc = codec.lib.b200bgzf_container_compress_host(codec.h, kind, 0, h_in.data_ptr(), n, 6, h_out.data_ptr(), h_out.numel(), ctypes.byref(got))
+            assert rc == 0, rc
+
+        comp()
+        t0 = time.perf_counter(); comp(); tc = time.perf_counter() - t0
+        clen = got.value
+        entry = {"compress_e2e": round(n / tc / 1e9, 2), "ratio": round(clen / n, 4)}
+        if kind != b200bgzf.CONTAINER_GZIP:          # (a gzip member has no index: one warp decodes it)
+            def dec():
+                rc = codec.lib.b200bgzf_container_inflate_host(codec.h, kind, h_out.data_ptr(), clen, h_back.data_ptr(), n, ctypes.byref(got), 0)
+                assert rc == 0 and got.value == n, (rc, got.value)
+
+            dec()
+            t0 = time.perf_counter(); dec(); td = time.perf_counter() - t0
+            entry["inflate_e2e"] = round(n / td / 1e9, 2)
+            entry["roundtrip_ok"] = bool(torch.equal(h_back[:n], h_in[:n]))
+        res[name] = entry
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +203,7 @@ def main():
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--kind", default="fastq", choices=["fastq", "sam"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-containers", action="store_true", help="skip the extra lines for the other containers (SURVEY 8f)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -384,6 +420,13 @@ def main():
             "gpu_launches": launches_c + launches_i,
             "clocks": clk.summary(),
         }
+        if world == 1 and args.level == 6 and not args.no_containers:
+            # SURVEY 8f ranks 3 / 4 on the same kernels (piece mode): the other containers end to end from the same pinned input
+            # (first 256 MiB), one timed call each after a warm-up; tools/container_bench.py has the reference's applets beside them
+            try:
+                line["containers"] = container_lines(codec, h_in, min(nbytes, 256 << 20), h_out, h_back)
+            except Exception as e:  # an extra: it must never sink the measurement
+                line["containers"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             try:
                 cb = cpu_reference(args, h_in.data_ptr(), nbytes, args.kind)
