@@ -189,7 +189,7 @@ uint32_t b200bgzf_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
 /*
  * The containers (host code in 7bgzf_b200/host/containers.c; `param` = 0 for the reference's default):
  *   GZIP     one gzip member (applet/7gzip.c + zlibrawstdio_compress.h:259-300 hand the whole file to one
- *            libdeflate_deflate call; here: 32 KiB pieces primed with the 32 KiB before them, as pigz does, or with
+ *            libdeflate_deflate call; here: 48 KiB pieces primed with the 16 KiB before them, as pigz primes its chunks, or with
  *            B200BGZF_PARAM_INDEPENDENT independent 65280-byte pieces, as pigz -i does)
  *   MIGZ     applet/7migz.c:133-243 — members of `param` KiB (default 512), subfield "MZ" = DEFLATE size
  *   GZINGA   applet/7gzinga.c:78-216 — 100 KiB members with an empty comment, then an index member whose comment lists
