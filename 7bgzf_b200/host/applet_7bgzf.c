@@ -63,7 +63,7 @@ static void usage(const char *argv0)
             "  -d, --decompress          decompress\n"
             "      --gzi=FILE            (extension) also write a bgzip-style .gzi index of the members to FILE\n"
             "      --devices=N           (extension) spread the blocks over N GPUs (contiguous block ranges, same output)\n"
-            "      --independent         (extension, 7gzip) pieces without the 32 KiB of history before them: faster, 2-3 %% larger\n"
+            "      --independent         (extension, 7gzip) pieces without the 16 KiB of history before them: faster, 2-3 %% larger\n"
             "      --primed              (extension, 7migz) pieces of a member see the 32 KiB before them: slower, 2 %% smaller\n"
             "\nNote: every method runs on the B200 BGZF codec (libdeflate level classes 1-12).\n",
             argv0);
