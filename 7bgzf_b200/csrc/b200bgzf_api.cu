@@ -1319,7 +1319,8 @@ int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const 
                 h_msz[nb] = un.in_len;
                 h_isz[nb] = un.piece ? un.out_len : 0xffffffffu;
                 const uint32_t unit_out = un.piece ? un.out_len : rd32(p + un.in_off + un.in_len - 4);
-                if (unit_out > 0x7fffffffu) { drain(); return B200BGZF_E_FORMAT; }      /* (the kernel's positions are 32-bit) */
+                /* (the kernel's positions are 32-bit; DEFLATE cannot expand its input more than 1032 times) */
+                if (unit_out > 0x7fffffffu || unit_out > 1032ull * (un.in_len - un.hdr_len) + 1032u) { drain(); return B200BGZF_E_FORMAT; }
                 total += unit_out;
                 off = (size_t)(un.in_off + un.in_len);
                 nb++;
@@ -1334,7 +1335,9 @@ int inflate_host_impl(b200bgzf_ctx *ctx, const void *in, size_t in_bytes, const 
             l.h_meta[kBatchMax + nb] = total - out0;
             h_hdr[nb] = hlen;
             h_msz[nb] = (uint32_t)sz;
-            total += rd32(p + off + sz - 4);           /* ISIZE: the member's share of the output */
+            const uint32_t isz = rd32(p + off + sz - 4);   /* ISIZE: the member's share of the output */
+            if (isz > 1032ull * (sz - hlen) + 1032u) { drain(); return B200BGZF_E_FORMAT; }   /* (more than DEFLATE can expand its input) */
+            total += isz;
             off += (size_t)sz;
             nb++;
         }

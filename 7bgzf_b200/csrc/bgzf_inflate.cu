@@ -101,7 +101,9 @@ __device__ __forceinline__ void ow_flush_lines(OutWin &o, uint32_t upto_line)
 
 /* Literals are not checked against the end of the output one by one: the window is circular, so a corrupt stream
  * can do no harm there, and what leaves for global memory is clipped to the member.  The check happens here, when a
- * line completes (at most 128 + 258 bytes late).  Returns true when the stream has produced more than ISIZE. */
+ * line completes (at most 128 + 258 bytes late).  Returns true when a line completed: the caller then checks that the stream
+ * has not produced more than ISIZE — and that it has not run past its input either (beyond it the reader yields zeros,
+ * which a corrupt member with a large ISIZE claim would otherwise decode for as long as that claim lasts). */
 __device__ __forceinline__ bool ow_advance(OutWin &o, uint32_t nbytes)
 {
     o.apos += nbytes;
@@ -109,7 +111,7 @@ __device__ __forceinline__ bool ow_advance(OutWin &o, uint32_t nbytes)
     if (complete != o.flushed) {
         __syncwarp();
         ow_flush_lines(o, complete);
-        return o.apos > o.end;
+        return true;
     }
     return false;
 }
@@ -484,7 +486,7 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
                 const uint32_t cnt = 1u + ((e >> 14) & 1u);          /* F_LIT2: two literals in one entry */
                 br_consume(r, nb);
                 if (lane < cnt) o.win[(o.apos + lane) & (INF_WIN - 1u)] = (uint8_t)(e >> (16 + 8 * lane));
-                if (ow_advance(o, cnt)) { err = INF_E_OVERRUN; break; }
+                if (ow_advance(o, cnt) && (o.apos > o.end || br_overrun(r))) { err = INF_E_OVERRUN; break; }
                 continue;
             }
             const uint32_t kind = (e >> 8) & 7u;
@@ -500,7 +502,7 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
             const uint32_t dist = (d >> 16) + ((win >> nb) & ((1u << dxb) - 1u));
             br_consume(r, nb + dxb);
             if (dist > o.apos - o.first) { err = INF_E_DIST; break; }
-            if (o.apos + len > end_apos) { err = INF_E_OVERRUN; break; }
+            if (o.apos + len > end_apos || br_overrun(r)) { err = INF_E_OVERRUN; break; }
             __syncwarp();   /* earlier window/global stores of this warp are visible to all its lanes */
             if (dist + len <= INF_WIN) {
                 /* near: the source is still in the window.  Bytes are produced 32 at a time; with an overlapping
