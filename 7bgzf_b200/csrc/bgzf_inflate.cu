@@ -101,11 +101,11 @@ __device__ __forceinline__ void ow_flush_lines(OutWin &o, uint32_t upto_line)
 
 /* Literals are not checked against the end of the output one by one: the window is circular, so a corrupt stream
  * can do no harm there, and what leaves for global memory is clipped to the member.  The check happens here, when a
- * line completes (at most 128 + 258 bytes late).  Returns true when a line completed: the caller then checks that the stream
- * has not produced more than ISIZE — and that it has not run past its input either (beyond it the reader yields zeros,
- * which a corrupt member with a large ISIZE claim would otherwise decode as literals for as long as that claim lasts; the
- * same test on every match costs 4 % of the kernel and is left out: the host bounds every claim by DEFLATE's maximum
- * expansion of the member's input, so a corrupt member costs no more than a legitimate one of its size can). */
+ * line completes (at most 128 + 258 bytes late).  Returns true when the stream has produced more than ISIZE.
+ * (Running past the INPUT is only tested at the end of a block: beyond it the reader yields zeros, which a corrupt member
+ * decodes until its ISIZE claim is used up.  Testing it here as well cost 1.5 % of the kernel, on every match 4 %; instead the
+ * host bounds every claim by DEFLATE's maximum expansion of the member's input — b200bgzf_api.cu — so that a corrupt member
+ * costs no more than a legitimate one of its size can.) */
 __device__ __forceinline__ bool ow_advance(OutWin &o, uint32_t nbytes)
 {
     o.apos += nbytes;
@@ -113,7 +113,7 @@ __device__ __forceinline__ bool ow_advance(OutWin &o, uint32_t nbytes)
     if (complete != o.flushed) {
         __syncwarp();
         ow_flush_lines(o, complete);
-        return true;
+        return o.apos > o.end;
     }
     return false;
 }
@@ -488,7 +488,7 @@ bgzf_inflate_kernel(BgzfInflateArgs a)
                 const uint32_t cnt = 1u + ((e >> 14) & 1u);          /* F_LIT2: two literals in one entry */
                 br_consume(r, nb);
                 if (lane < cnt) o.win[(o.apos + lane) & (INF_WIN - 1u)] = (uint8_t)(e >> (16 + 8 * lane));
-                if (ow_advance(o, cnt) && (o.apos > o.end || br_overrun(r))) { err = INF_E_OVERRUN; break; }
+                if (ow_advance(o, cnt)) { err = INF_E_OVERRUN; break; }
                 continue;
             }
             const uint32_t kind = (e >> 8) & 7u;
