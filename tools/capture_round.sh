@@ -14,6 +14,7 @@ python tools/e2e_probe.py 1024 >> $O/pcie_$R.txt 2>&1
 bash tools/applet_compare.sh 1024 > $O/applet_$R.txt 2>&1
 python tools/container_bench.py 1024 256 > $O/containers_$R.jsonl 2>> $O/bench_$R.err
 (python tools/compress_fuzz.py 400 7; python tools/compress_fuzz.py 300 23) > $O/compress_fuzz_$R.txt 2>&1
+(timeout 300 python tools/container_fuzz.py 300 5; timeout 200 python tools/container_fuzz.py 150 9) > $O/container_fuzz_$R.txt 2>&1
 # launch list of the bench command (shares per kernel; times under ncu are cold-cache and serialised)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$R.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_bench_$R.log 2>&1
 # one full capture of each dominant kernel
