@@ -51,6 +51,20 @@ def test_plans_keep_a_stored_piece_inside_its_slot():
         B.container_plan(9, 0, lib)
 
 
+def test_gap_bytes_of_a_slice_of_the_piece_stream():
+    """b200bgzf_pieces_gap_bytes with piece_base / piece_total (a GPU shard's slice): head gaps of the members that begin in the
+    slice, tail gaps of those that end in it — against a walk over the pieces"""
+    import ctypes
+    lib = B.load()
+    for k in (1, 2, 3, 7, 0xFFFFFFFF):
+        for total in (1, 2, 6, 7, 20):
+            for base in range(0, total):
+                for nb in range(0, total - base + 1):
+                    spec = B.PieceSpec(k, 11, 8, 0, base, total, 0, 0)
+                    want = sum((11 if gb % k == 0 else 0) + (8 if (gb + 1) % k == 0 or gb + 1 == total else 0) for gb in range(base, base + nb))
+                    assert lib.b200bgzf_pieces_gap_bytes(nb * 1000, 1000, ctypes.byref(spec)) == want, (k, total, base, nb)
+
+
 def test_non_final_pieces_end_on_a_byte_and_decode_alone():
     data = H.synth("fastq", 4 * 32768 + 17)
     whole = zlib.decompressobj(-15)
