@@ -51,6 +51,18 @@ def test_plans_keep_a_stored_piece_inside_its_slot():
         B.container_plan(9, 0, lib)
 
 
+@pytest.mark.parametrize("level", [1, 6, 9, 12])
+def test_piece_and_history_phases_do_not_depend_on_the_thread_order(level):
+    """race check of the piece-mode and history code: the emulator runs the phases with the threads in forward, reverse and
+    shuffled order (as tests/test_emulator.py does for members); the bytes must not change"""
+    data = H.synth("fastq", 40000) + H.lcg_noise(500) + H.synth("sam", 40000)
+    hist, payload = data[: 16320], data[16320 : 16320 + 49152]
+    for history, final, head, tail in ((b"", True, 10, 8), (b"", False, 0, 0), (hist, False, 0, 0), (hist, True, 0, 8), (data[:272], False, 20, 0)):
+        base = H.emul_piece(payload, level, head, tail, final, 0, history)
+        for order in (1, 2):
+            assert H.emul_piece(payload, level, head, tail, final, order, history) == base, (level, len(history), final, order)
+
+
 def test_gap_bytes_of_a_slice_of_the_piece_stream():
     """b200bgzf_pieces_gap_bytes with piece_base / piece_total (a GPU shard's slice): head gaps of the members that begin in the
     slice, tail gaps of those that end in it — against a walk over the pieces"""
